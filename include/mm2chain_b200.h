@@ -1,0 +1,131 @@
+/* mm2chain_b200 — C ABI of the B200-native chaining backend for minimap2 (drop-in for the FPGA offload of
+ * kisarur/minimap2-fpga).  Plain C: pointers and sizes only, no CUDA or torch types in any signature.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *
+ *   mm_chain_dp            chain.c:29 / mmpriv.h:65     same name, same 16 positional arguments, same ownership rules.
+ *                                                       Called per read from mm_map_frag (map.c:316, map.c:338).  Every
+ *                                                       read is chained on the GPU; there is no HW/SW predictor and no
+ *                                                       CPU fallback (chain.c:51-101 is gone).
+ *   mm2b_init              chain_hardware.h:70 / chain_hardware.cpp:278  hardware_init(long, char*): OpenCL platform,
+ *                                                       xclbin load, device buffers  ->  CUDA devices, streams, pinned rings.
+ *   mm2b_shutdown          chain_hardware.h:71 / chain_hardware.cpp:403  cleanup()
+ *   mm2b_chain_batch       chain_hardware.h:68 / chain_hardware.cpp:27   run_chaining_on_hw(): one blocking offload call
+ *                                                       with host buffers — but for MANY reads at once and with the full
+ *                                                       software semantics (max_skip, max_iter, gap_scale, is_cdna, n_segs),
+ *                                                       returning final chains (u[], b[]) instead of raw f[]/p[].
+ *   mm2b_chain_batch_device  (no equivalent)            the same computation on buffers already resident in HBM, on a
+ *                                                       caller-supplied stream: the building block the two above use.
+ *   mm2b_last_error        chain_hardware.h:72 / chain_hardware.cpp:208  checkError(): the reference prints and exit()s;
+ *                                                       mm_chain_dp keeps that behaviour, the mm2b_* calls return codes.
+ *
+ * C++ hosts that still call hardware_init()/cleanup() by those names (main.c:367, main.c:430) include
+ * minimap2-fpga_b200/host/compat/chain_hardware.h, which maps them onto mm2b_init/mm2b_shutdown.
+ */
+#ifndef MM2CHAIN_B200_H
+#define MM2CHAIN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM2B_ABI_VERSION 1
+
+/* == mm128_t (minimap.h:53).  x = rev<<63 | rid<<32 | ref_pos;  y = seg_id<<48 | flags(40..43) | q_span<<32 | q_pos */
+typedef struct { uint64_t x, y; } mm2b_anchor_t;
+
+/* The chaining arguments of mm_chain_dp (chain.c:29) in call order. */
+typedef struct {
+	int32_t max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs;
+	float gap_scale;
+} mm2b_params_t;
+
+/* Per-read outcome, mirroring the three ways mm_chain_dp returns:
+ *   EMPTY     n == 0                       -> returns NULL, *_u = NULL, *n_u_ = 0      (chain.c:38-41)
+ *   NO_CHAIN  no chain end reaches min_sc  -> returns NULL, *_u = NULL, *n_u_ = 0      (chain.c:355-358)
+ *   OK        otherwise                    -> *_u non-NULL (even when n_u == 0), b = kmalloc(n_v*16) */
+enum { MM2B_READ_EMPTY = 0, MM2B_READ_NO_CHAIN = 1, MM2B_READ_OK = 2 };
+
+/* Return codes */
+enum { MM2B_OK = 0, MM2B_ERR_CUDA = -1, MM2B_ERR_ARG = -2, MM2B_ERR_CAPACITY = -3, MM2B_ERR_NOT_INIT = -4 };
+
+typedef struct {
+	int64_t n_reads, n_anchors;
+	int64_t n_chains, n_chained;     /* totals: sum n_u, sum n_v */
+	int64_t cells_issued;            /* GPU lanes evaluated (32 per chunk); the reference-semantics cell count comes from the oracle */
+	int64_t n_general_reads;         /* reads that took the general (multi-segment / cDNA / gap_scale != 1) scoring path */
+	double  h2d_ms, kernel_ms, d2h_ms; /* device-side timings of the last host-buffer call (CUDA events), 0 for device calls */
+} mm2b_stats_t;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+
+/* Bind the backend to `n_devices` CUDA devices (ids in `devices`, or NULL for 0..n_devices-1; n_devices <= 0 means
+ * "all visible", or the MM2B_DEVICES environment variable if set).  Creates per-device streams and worker threads. */
+int mm2b_init(int n_devices, const int *devices);
+void mm2b_shutdown(void);
+int mm2b_num_devices(void);                 /* devices bound by mm2b_init (0 before) */
+int mm2b_cuda_device_count(void);           /* devices visible to the CUDA runtime; <= 0 when there is no usable GPU */
+const char *mm2b_last_error(void);          /* thread-local text of the last failure */
+int mm2b_abi_version(void);
+
+/* Pinned host memory for batch inputs/outputs (H2D/D2H run at PCIe speed only from pinned pages). */
+void *mm2b_host_alloc(size_t bytes);
+void mm2b_host_free(void *p);
+
+/* ---- batch chaining, host buffers (the end-to-end path) ------------------------------------------------------- */
+
+/* Chain `n_reads` independent reads.  Read r owns anchors a[off[r] .. off[r+1]) (sorted by x, as map.c:245 leaves them).
+ * Reads are sharded over the bound devices by per-device worker threads; results come back in input order:
+ *   n_u[r], n_v[r], status[r]                 per read
+ *   u[u_off[r] .. u_off[r]+n_u[r])            == the reference's final u[] for read r   (chain.c:419)
+ *   b[b_off[r] .. b_off[r]+n_v[r])            == the reference's final b[] for read r   (chain.c:420)
+ * u_off/b_off have n_reads+1 entries.  u_cap/b_cap are the capacities of u/b in elements; off[n_reads] always suffices.
+ * `stats` may be NULL.  Blocking.  Thread-safe. */
+int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
+                     int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
+                     uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats);
+
+/* ---- batch chaining, device buffers (inputs already in HBM) --------------------------------------------------- */
+
+typedef struct mm2b_workspace mm2b_workspace_t;
+
+/* Scratch for batches of up to max_anchors anchors / max_reads reads on `device` (40 B per anchor + 64 B per read). */
+mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_reads);
+void mm2b_ws_destroy(mm2b_workspace_t *ws);
+size_t mm2b_ws_bytes(const mm2b_workspace_t *ws);
+
+/* All d_* pointers are device memory on the workspace's device; `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Asynchronous: work is enqueued on `stream` and the call returns.  `n_anchors` == off[n_reads] (known to the host).
+ * d_u_off/d_b_off: n_reads+1 entries; d_u/d_b: capacity n_anchors elements each is always enough. */
+int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
+                            const int64_t *d_off, const mm2b_anchor_t *d_a,
+                            int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
+                            uint64_t *d_u, mm2b_anchor_t *d_b, void *stream);
+
+/* Counters of the last batch run on this workspace (synchronises the given stream). */
+int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream, mm2b_stats_t *stats);
+/* Kernels launched by this library since load (for bench.py's gpu_launches). */
+int64_t mm2b_launch_count(void);
+/* Debug / test access to the per-anchor DP state of the last batch: f[], p[], v[] as the reference has them at chain.c:238.
+ * Only valid when the workspace was created with the environment variable MM2B_KEEP_FPV=1 (costs 12 B/anchor extra). */
+int mm2b_ws_copy_fpv(mm2b_workspace_t *ws, void *stream, int64_t n_anchors, int32_t *h_f, int32_t *h_p, int32_t *h_v);
+
+/* Measured INT32 issue peak of `device` in G int-ops/s (IADD3/LOP3/IMNMX mix, all SMs), for the roofline. */
+double mm2b_measure_int32_peak(int device);
+
+/* ---- the reference's own per-read boundary -------------------------------------------------------------------- */
+
+/* Drop-in for chain.c:29.  Takes ownership of `a` (kfree(km, a) on every path); returns b and *_u allocated with
+ * kmalloc(km, ...).  Re-entrant; called concurrently from the kt_for worker threads (map.c:561).  Initialises the backend
+ * on first use if mm2b_init was not called.  Fatal CUDA errors print to stderr and exit(1), as checkError does. */
+mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
+                           float gap_scale, int is_cdna, int n_segs, int64_t n, mm2b_anchor_t *a, int *n_u_, uint64_t **_u,
+                           void *km, int tid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,267 @@
+"""ctypes view of the C ABI in include/mm2chain_b200.h (libmm2chain_b200.so, built in-tree by build.py).
+
+This is the Python mirror of the reference's accelerator boundary (chain_hardware.h:68-72 / chain.c:29):
+  init()/shutdown()      <- hardware_init()/cleanup()
+  chain_batch()          <- run_chaining_on_hw(), but many reads per call and final chains out
+  chain_read()           <- mm_chain_dp() itself (same positional arguments)
+  DeviceBatch            <- inputs/outputs resident in HBM (torch tensors only as device memory)
+There is NO CPU fallback: if the library is missing, or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmm2chain_b200.so")
+ANCHOR = np.dtype([("x", "<u8"), ("y", "<u8")])
+READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
+
+EXPORTS = ["mm2b_init", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
+           "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
+           "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_measure_int32_peak",
+           "mm_chain_dp"]
+
+
+class Params(C.Structure):
+    """mm2b_params_t — the chaining arguments of mm_chain_dp (chain.c:29); defaults are map-ont / asm20 (options.c:24-31)."""
+    _fields_ = [(k, C.c_int32) for k in
+                ("max_dist_x", "max_dist_y", "bw", "max_skip", "max_iter", "min_cnt", "min_sc", "is_cdna", "n_segs")] + \
+               [("gap_scale", C.c_float)]
+
+    def __init__(self, max_dist_x=5000, max_dist_y=5000, bw=500, max_skip=25, max_iter=5000, min_cnt=3, min_sc=40,
+                 is_cdna=0, n_segs=1, gap_scale=1.0):
+        super().__init__(max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale)
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "n_general_reads")] + \
+               [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Mm2bError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the native library and bind every symbol the header declares; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Mm2bError("native library %s not built: run `python __graft_entry__.py` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        getattr(L, name)        # AttributeError if the C ABI is incomplete
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.mm2b_init.restype, L.mm2b_init.argtypes = i32, [i32, vp]
+    L.mm2b_shutdown.restype, L.mm2b_shutdown.argtypes = None, []
+    L.mm2b_num_devices.restype = i32
+    L.mm2b_cuda_device_count.restype = i32
+    L.mm2b_last_error.restype = C.c_char_p
+    L.mm2b_abi_version.restype = i32
+    L.mm2b_host_alloc.restype, L.mm2b_host_alloc.argtypes = vp, [C.c_size_t]
+    L.mm2b_host_free.restype, L.mm2b_host_free.argtypes = None, [vp]
+    L.mm2b_chain_batch.restype = i32
+    L.mm2b_chain_batch.argtypes = [C.POINTER(Params), i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, C.POINTER(Stats)]
+    L.mm2b_ws_create.restype, L.mm2b_ws_create.argtypes = vp, [i32, i64, i64]
+    L.mm2b_ws_destroy.restype, L.mm2b_ws_destroy.argtypes = None, [vp]
+    L.mm2b_ws_bytes.restype, L.mm2b_ws_bytes.argtypes = C.c_size_t, [vp]
+    L.mm2b_chain_batch_device.restype = i32
+    L.mm2b_chain_batch_device.argtypes = [vp, C.POINTER(Params), i64, i64] + [vp] * 9 + [vp]
+    L.mm2b_ws_stats.restype, L.mm2b_ws_stats.argtypes = i32, [vp, vp, C.POINTER(Stats)]
+    L.mm2b_launch_count.restype = i64
+    L.mm2b_ws_copy_fpv.restype, L.mm2b_ws_copy_fpv.argtypes = i32, [vp, vp, i64, vp, vp, vp]
+    L.mm2b_measure_int32_peak.restype, L.mm2b_measure_int32_peak.argtypes = C.c_double, [i32]
+    L.mm_chain_dp.restype = vp
+    L.mm_chain_dp.argtypes = [i32] * 7 + [C.c_float, i32, i32, i64, vp, C.POINTER(i32), C.POINTER(vp), vp, i32]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise Mm2bError("%s failed (%d): %s" % (what, rc, load().mm2b_last_error().decode()))
+
+
+def init(devices=None):
+    """hardware_init() equivalent. devices: None (all / $MM2B_DEVICES), an int count, or a list of CUDA device ids."""
+    L = load()
+    if devices is None:
+        _check(L.mm2b_init(0, None), "mm2b_init")
+    elif isinstance(devices, int):
+        _check(L.mm2b_init(devices, None), "mm2b_init")
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        _check(L.mm2b_init(len(devices), arr), "mm2b_init")
+
+
+def shutdown():
+    load().mm2b_shutdown()
+
+
+class PinnedArray:
+    """numpy array over pinned host memory from mm2b_host_alloc (H2D/D2H run at PCIe speed only from pinned pages)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = load().mm2b_host_alloc(max(n, 1))
+        if not self.ptr:
+            raise Mm2bError("mm2b_host_alloc(%d) failed: %s" % (n, load().mm2b_last_error().decode()))
+        buf = (C.c_char * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().mm2b_host_free(self.ptr)
+            self.ptr = None
+
+
+def _p(arr):
+    return arr.ctypes.data_as(C.c_void_p)
+
+
+def chain_batch(par, off, a, out=None, want_stats=True):
+    """Chain a CSR batch of reads through mm2b_chain_batch (host buffers; H2D, kernels and D2H inside the call).
+
+    off: int64[n_reads+1]; a: ANCHOR[off[-1]].  `out` may carry preallocated (ideally pinned) arrays
+    n_u, n_v, status, u_off, b_off, u, b; otherwise numpy arrays are allocated.  Returns a dict with those plus stats.
+    """
+    L = load()
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    a = np.ascontiguousarray(a, dtype=ANCHOR)
+    n_reads, n_anchors = len(off) - 1, int(off[-1]) if len(off) else 0
+    o = dict(out) if out else {}
+    o.setdefault("n_u", np.empty(n_reads, np.int32))
+    o.setdefault("n_v", np.empty(n_reads, np.int32))
+    o.setdefault("status", np.empty(n_reads, np.int32))
+    o.setdefault("u_off", np.empty(n_reads + 1, np.int64))
+    o.setdefault("b_off", np.empty(n_reads + 1, np.int64))
+    o.setdefault("u", np.empty(max(n_anchors, 1), np.uint64))
+    o.setdefault("b", np.empty(max(n_anchors, 1), ANCHOR))
+    st = Stats()
+    rc = L.mm2b_chain_batch(C.byref(par), n_reads, _p(off), _p(a), _p(o["n_u"]), _p(o["n_v"]), _p(o["status"]), _p(o["u_off"]),
+                            _p(o["b_off"]), _p(o["u"]), len(o["u"]), _p(o["b"]), len(o["b"]), C.byref(st) if want_stats else None)
+    _check(rc, "mm2b_chain_batch")
+    o["stats"] = st
+    return o
+
+
+def chain_read(par, a):
+    """One read through the drop-in mm_chain_dp (km = NULL, so malloc/free like kalloc.c does without an arena).
+    Returns (u, b, u_is_null, b_is_null) like the reference's return convention."""
+    L = load()
+    libc = C.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = C.c_void_p, [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    a = np.ascontiguousarray(a, dtype=ANCHOR)
+    n = len(a)
+    pa = None
+    if n:
+        pa = libc.malloc(n * 16)                   # consumed by mm_chain_dp (chain.c:421)
+        C.memmove(pa, a.ctypes.data, n * 16)
+    n_u, pu = C.c_int(0), C.c_void_p(0)
+    pb = L.mm_chain_dp(par.max_dist_x, par.max_dist_y, par.bw, par.max_skip, par.max_iter, par.min_cnt, par.min_sc,
+                       par.gap_scale, par.is_cdna, par.n_segs, n, pa, C.byref(n_u), C.byref(pu), None, 0)
+    u = np.empty(n_u.value, np.uint64)
+    if n_u.value:
+        C.memmove(u.ctypes.data, pu.value, n_u.value * 8)
+    n_v = int((u & np.uint64(0xffffffff)).sum())
+    b = np.empty(n_v, ANCHOR)
+    if n_v:
+        C.memmove(b.ctypes.data, pb, n_v * 16)
+    u_null, b_null = not pu.value, not pb
+    if pu.value:
+        libc.free(pu)
+    if pb:
+        libc.free(pb)
+    return u, b, u_null, b_null
+
+
+class DeviceBatch:
+    """A batch whose inputs and outputs live in HBM (torch tensors used purely as device memory + stream handles).
+
+    run() enqueues K0..K3 on the current torch stream through mm2b_chain_batch_device and returns immediately.
+    """
+
+    def __init__(self, par, off, a, device=0, keep_fpv=False):
+        import torch
+        self.torch = torch
+        self.L = load()
+        self.par = par
+        self.device = torch.device("cuda", device)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        a = np.ascontiguousarray(a, dtype=ANCHOR)
+        self.n_reads, self.n_anchors = len(off) - 1, int(off[-1])
+        with torch.cuda.device(self.device):
+            self.d_off = torch.from_numpy(off).to(self.device)
+            self.d_a = torch.from_numpy(a.view(np.int64).reshape(-1, 2).copy()).to(self.device)
+            i32 = dict(dtype=torch.int32, device=self.device)
+            i64 = dict(dtype=torch.int64, device=self.device)
+            self.d_n_u = torch.empty(max(self.n_reads, 1), **i32)
+            self.d_n_v = torch.empty(max(self.n_reads, 1), **i32)
+            self.d_status = torch.empty(max(self.n_reads, 1), **i32)
+            self.d_u_off = torch.empty(self.n_reads + 1, **i64)
+            self.d_b_off = torch.empty(self.n_reads + 1, **i64)
+            self.d_u = torch.empty(max(self.n_anchors, 1), **i64)
+            self.d_b = torch.empty((max(self.n_anchors, 1), 2), **i64)
+        if keep_fpv:
+            os.environ["MM2B_KEEP_FPV"] = "1"
+        self.ws = self.L.mm2b_ws_create(device, self.n_anchors, self.n_reads)
+        if keep_fpv:
+            os.environ.pop("MM2B_KEEP_FPV", None)
+        if not self.ws:
+            raise Mm2bError("mm2b_ws_create failed: %s" % self.L.mm2b_last_error().decode())
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def run(self):
+        rc = self.L.mm2b_chain_batch_device(self.ws, C.byref(self.par), self.n_reads, self.n_anchors,
+                                            self.d_off.data_ptr(), self.d_a.data_ptr(), self.d_n_u.data_ptr(), self.d_n_v.data_ptr(),
+                                            self.d_status.data_ptr(), self.d_u_off.data_ptr(), self.d_b_off.data_ptr(),
+                                            self.d_u.data_ptr(), self.d_b.data_ptr(), self._stream())
+        _check(rc, "mm2b_chain_batch_device")
+
+    def stats(self):
+        st = Stats()
+        _check(self.L.mm2b_ws_stats(self.ws, self._stream(), C.byref(st)), "mm2b_ws_stats")
+        return st
+
+    def fpv(self):
+        f, p, v = (np.empty(self.n_anchors, np.int32) for _ in range(3))
+        _check(self.L.mm2b_ws_copy_fpv(self.ws, self._stream(), self.n_anchors, _p(f), _p(p), _p(v)), "mm2b_ws_copy_fpv")
+        return f, p, v
+
+    def results(self):
+        """Copy results to the host (numpy), same keys as chain_batch()."""
+        self.torch.cuda.synchronize(self.device)
+        n_u = self.d_n_u[:self.n_reads].cpu().numpy()
+        n_v = self.d_n_v[:self.n_reads].cpu().numpy()
+        u_off, b_off = self.d_u_off.cpu().numpy(), self.d_b_off.cpu().numpy()
+        u = self.d_u[:int(u_off[-1])].cpu().numpy().view(np.uint64)
+        b = self.d_b[:int(b_off[-1])].cpu().numpy().reshape(-1).view(ANCHOR)
+        return dict(n_u=n_u, n_v=n_v, status=self.d_status[:self.n_reads].cpu().numpy(), u_off=u_off, b_off=b_off, u=u, b=b)
+
+    def close(self):
+        if self.ws:
+            self.L.mm2b_ws_destroy(self.ws)
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,184 @@
+// C-ABI shim over the CUDA kernels: workspaces and the device-buffer batch call (include/mm2chain_b200.h).
+// The host-buffer batch call, the device worker threads and the mm_chain_dp drop-in live in host/chain_backend.cpp.
+#include "chain_kernels.cuh"
+#include "shim_internal.h"
+#include <atomic>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace mm2b {
+
+static thread_local char g_err[512];
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, const char *a, const char *b)
+{
+	snprintf(g_err, sizeof(g_err), fmt, a ? a : "", b ? b : "");
+}
+bool cuda_ok(cudaError_t e, const char *what)
+{
+	if (e == cudaSuccess) return true;
+	set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+	return false;
+}
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace mm2b
+
+using namespace mm2b;
+
+struct mm2b_workspace {
+	int device, n_sms;
+	int64_t max_anchors, max_reads;
+	uint8_t *scratch;           // SCRATCH_BYTES_PER_ANCHOR * max_anchors
+	int32_t *order;             // max_reads
+	int64_t *tile;              // 2 * ceil(max_reads / 2048)
+	int *small;                 // [0] work counter, [64..320) length buckets
+	unsigned long long *counters;
+	int32_t *dbg_fpv;           // 3 * max_anchors when MM2B_KEEP_FPV=1
+	size_t bytes;
+	int64_t last_reads, last_anchors;
+	const int32_t *last_n_u, *last_n_v;
+	const int64_t *last_u_off, *last_b_off;
+};
+
+extern "C" {
+
+const char *mm2b_last_error(void) { return g_err; }
+int mm2b_abi_version(void) { return MM2B_ABI_VERSION; }
+int64_t mm2b_launch_count(void) { return g_launches.load(); }
+
+int mm2b_cuda_device_count(void)
+{
+	int n = 0;
+	if (!cuda_ok(cudaGetDeviceCount(&n), "cudaGetDeviceCount")) return -1;
+	return n;
+}
+
+void *mm2b_host_alloc(size_t bytes)
+{
+	void *p = 0;
+	if (!cuda_ok(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable), "cudaHostAlloc")) return 0;
+	return p;
+}
+void mm2b_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_reads)
+{
+	if (max_anchors < 1) max_anchors = 1;
+	if (max_reads < 1) max_reads = 1;
+	if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return 0;
+	mm2b_workspace_t *ws = (mm2b_workspace_t*)calloc(1, sizeof(*ws));
+	ws->device = device, ws->max_anchors = max_anchors, ws->max_reads = max_reads;
+	cudaDeviceGetAttribute(&ws->n_sms, cudaDevAttrMultiProcessorCount, device);
+	const size_t sz_scratch = (size_t)max_anchors * SCRATCH_BYTES_PER_ANCHOR;
+	const size_t sz_order = (size_t)max_reads * sizeof(int32_t);
+	const size_t sz_tile = ((size_t)max_reads / 2048 + 2) * 2 * sizeof(int64_t);
+	const char *keep = getenv("MM2B_KEEP_FPV");
+	bool ok = cuda_ok(cudaMalloc(&ws->scratch, sz_scratch), "cudaMalloc(scratch)")
+	       && cuda_ok(cudaMalloc(&ws->order, sz_order), "cudaMalloc(order)")
+	       && cuda_ok(cudaMalloc(&ws->tile, sz_tile), "cudaMalloc(tile)")
+	       && cuda_ok(cudaMalloc(&ws->small, 512 * sizeof(int)), "cudaMalloc(small)")
+	       && cuda_ok(cudaMalloc(&ws->counters, 4 * sizeof(unsigned long long)), "cudaMalloc(counters)");
+	ws->bytes = sz_scratch + sz_order + sz_tile + 512 * sizeof(int) + 32;
+	if (ok && keep && atoi(keep) > 0) {
+		ok = cuda_ok(cudaMalloc(&ws->dbg_fpv, (size_t)max_anchors * 12), "cudaMalloc(dbg_fpv)");
+		ws->bytes += (size_t)max_anchors * 12;
+	}
+	if (ok) ok = cuda_ok(cudaMemset(ws->counters, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
+	if (!ok) { mm2b_ws_destroy(ws); return 0; }
+	return ws;
+}
+
+void mm2b_ws_destroy(mm2b_workspace_t *ws)
+{
+	if (!ws) return;
+	cudaSetDevice(ws->device);
+	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->tile), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
+	free(ws);
+}
+
+size_t mm2b_ws_bytes(const mm2b_workspace_t *ws) { return ws ? ws->bytes : 0; }
+
+int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
+                            const int64_t *d_off, const mm2b_anchor_t *d_a,
+                            int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
+                            uint64_t *d_u, mm2b_anchor_t *d_b, void *stream_)
+{
+	if (!ws || !par || n_reads < 0 || n_anchors < 0) { set_error("%s%s", "mm2b_chain_batch_device: bad argument", ""); return MM2B_ERR_ARG; }
+	if (n_reads > ws->max_reads || n_anchors > ws->max_anchors || n_reads >= (1ll << 31)) {
+		set_error("%s%s", "mm2b_chain_batch_device: batch exceeds workspace capacity", "");
+		return MM2B_ERR_CAPACITY;
+	}
+	cudaStream_t stream = (cudaStream_t)stream_;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	if (prev != ws->device && !cuda_ok(cudaSetDevice(ws->device), "cudaSetDevice")) return MM2B_ERR_CUDA;
+	int launches = 0;
+	launches += launch_order(n_reads, d_off, ws->order, ws->small + 64, stream);
+	BatchArgs ba;
+	memset(&ba, 0, sizeof(ba));
+	ba.par = *par, ba.n_reads = n_reads, ba.off = d_off, ba.a = d_a, ba.scratch = ws->scratch;
+	ba.n_u = d_n_u, ba.n_v = d_n_v, ba.status = d_status, ba.order = ws->order, ba.work_counter = ws->small;
+	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors;
+	launches += launch_chain(ba, ws->n_sms, stream);
+	launches += launch_offsets(n_reads, d_n_u, d_n_v, d_u_off, d_b_off, ws->tile, stream);
+	EmitArgs ea;
+	ea.n_reads = n_reads, ea.off = d_off, ea.a = d_a, ea.scratch = ws->scratch, ea.n_u = d_n_u, ea.n_v = d_n_v;
+	ea.u_off = d_u_off, ea.b_off = d_b_off, ea.u = d_u, ea.b = d_b;
+	launches += launch_emit(ea, ws->n_sms, stream);
+	count_launches(launches);
+	ws->last_reads = n_reads, ws->last_anchors = n_anchors;
+	ws->last_n_u = d_n_u, ws->last_n_v = d_n_v, ws->last_u_off = d_u_off, ws->last_b_off = d_b_off;
+	const bool ok = cuda_ok(cudaGetLastError(), "kernel launch");
+	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
+	return ok ? MM2B_OK : MM2B_ERR_CUDA;
+}
+
+int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
+{
+	if (!ws || !st) return MM2B_ERR_ARG;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	if (prev != ws->device) cudaSetDevice(ws->device);
+	unsigned long long c[2] = {0, 0};
+	int64_t tot[2] = {0, 0};
+	bool ok = cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize")
+	       && cuda_ok(cudaMemcpy(c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
+	if (ok && ws->last_u_off && ws->last_reads >= 0) {
+		ok = cuda_ok(cudaMemcpy(&tot[0], ws->last_u_off + ws->last_reads, 8, cudaMemcpyDeviceToHost), "cudaMemcpy(u_off)")
+		  && cuda_ok(cudaMemcpy(&tot[1], ws->last_b_off + ws->last_reads, 8, cudaMemcpyDeviceToHost), "cudaMemcpy(b_off)");
+	}
+	memset(st, 0, sizeof(*st));
+	st->n_reads = ws->last_reads, st->n_anchors = ws->last_anchors;
+	st->n_chains = tot[0], st->n_chained = tot[1];
+	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1];
+	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
+	return ok ? MM2B_OK : MM2B_ERR_CUDA;
+}
+
+int mm2b_ws_copy_fpv(mm2b_workspace_t *ws, void *stream_, int64_t n_anchors, int32_t *h_f, int32_t *h_p, int32_t *h_v)
+{
+	if (!ws || !ws->dbg_fpv) { set_error("%s%s", "mm2b_ws_copy_fpv: workspace was not created with MM2B_KEEP_FPV=1", ""); return MM2B_ERR_ARG; }
+	if (n_anchors > ws->max_anchors) return MM2B_ERR_CAPACITY;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	if (prev != ws->device) cudaSetDevice(ws->device);
+	const size_t sz = (size_t)n_anchors * 4;
+	bool ok = cuda_ok(cudaStreamSynchronize((cudaStream_t)stream_), "cudaStreamSynchronize")
+	       && cuda_ok(cudaMemcpy(h_f, ws->dbg_fpv, sz, cudaMemcpyDeviceToHost), "cudaMemcpy(f)")
+	       && cuda_ok(cudaMemcpy(h_p, ws->dbg_fpv + ws->max_anchors, sz, cudaMemcpyDeviceToHost), "cudaMemcpy(p)")
+	       && cuda_ok(cudaMemcpy(h_v, ws->dbg_fpv + 2 * ws->max_anchors, sz, cudaMemcpyDeviceToHost), "cudaMemcpy(v)");
+	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
+	return ok ? MM2B_OK : MM2B_ERR_CUDA;
+}
+
+double mm2b_measure_int32_peak(int device)
+{
+	count_launches(6);
+	return measure_int32_peak(device);
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Internal declarations shared by the CUDA kernels (chain_kernels.cu) and the C-ABI shim (chain_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mm2chain_b200.h"
+
+namespace mm2b {
+
+// Per-read scratch layout in HBM.  Read r with n anchors starting at global anchor offset o owns the
+// SCRATCH_BYTES_PER_ANCHOR*n bytes at scratch + SCRATCH_BYTES_PER_ANCHOR*o, carved as
+//   [F 4n][P 4n][X 8n][V 4n][T 4n][U 8n][UF 8n]
+//   F,P,V  DP state (chain.c:236-237);  T visit stamps / marks;  U chain-end keys, then kept chains
+//   X      second buffer of the radix sort of U;  W (16 B per chain, final order sort) aliases F+P+X once the backtrack is done
+//   V -> PATH (backtrack index list), T -> OUTIDX (anchor indices in output order), UF final u[]
+constexpr int SCRATCH_BYTES_PER_ANCHOR = 40;
+
+struct BatchArgs {
+	mm2b_params_t par;
+	int64_t n_reads;
+	const int64_t *off;
+	const mm2b_anchor_t *a;
+	uint8_t *scratch;
+	int32_t *n_u, *n_v, *status;
+	const int32_t *order;           // processing order (longest reads first) or nullptr
+	int *work_counter;              // persistent-warp work queue
+	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path
+	int32_t *dbg_fpv;               // optional 3 x n_anchors int32 (f, p, v) copy for tests, or nullptr
+	int64_t n_anchors;
+};
+
+struct EmitArgs {
+	int64_t n_reads;
+	const int64_t *off;
+	const mm2b_anchor_t *a;
+	const uint8_t *scratch;
+	const int32_t *n_u, *n_v;
+	const int64_t *u_off, *b_off;
+	uint64_t *u;
+	mm2b_anchor_t *b;
+};
+
+// launchers (all asynchronous on `stream`); each returns the number of kernels it launched
+int launch_order(int64_t n_reads, const int64_t *off, int32_t *order, int *bucket_scratch, cudaStream_t stream);
+int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream);
+int launch_offsets(int64_t n_reads, const int32_t *n_u, const int32_t *n_v, int64_t *u_off, int64_t *b_off,
+                   int64_t *tile_scratch, cudaStream_t stream);
+int launch_emit(const EmitArgs &args, int n_sms, cudaStream_t stream);
+double measure_int32_peak(int device);
+
+}  // namespace mm2b

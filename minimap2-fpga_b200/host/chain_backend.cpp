@@ -1,0 +1,484 @@
+// Host backend of the B200 chaining offload: the C++ side above the C-ABI device calls.
+//
+// It replaces the reference's OpenCL host code (/root/reference/chain_hardware.cpp):
+//   hardware_init  (chain_hardware.cpp:278-400)  ->  mm2b_init       bind CUDA devices, start one worker thread per device
+//   cleanup        (chain_hardware.cpp:403-441)  ->  mm2b_shutdown
+//   run_chaining_on_hw (chain_hardware.cpp:27-205, one read, mutex-arbitrated single kernel, f/p out)
+//                                                ->  mm2b_chain_batch many reads, sharded over devices, final chains out
+//   mm_chain_dp    (chain.c:29)                  ->  mm_chain_dp     same signature; every read goes to the GPU
+//
+// Reads are independent, so a batch is cut into sub-batches (contiguous read ranges of <= MM2B_SUB_ANCHORS anchors) that the
+// per-device worker threads pull from a shared counter; each worker keeps NSLOT sub-batches in flight on separate streams so
+// H2D copies, kernels and D2H copies of neighbouring sub-batches overlap.  No collective, no NCCL: nothing is exchanged
+// between devices.  Outputs land in the caller's arrays in input order.
+#include <cuda_runtime_api.h>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mm2chain_b200.h"
+#include "../csrc/shim_internal.h"
+
+// kalloc of the host application (kalloc.c); weak so that the library also loads stand-alone (tests, bench)
+extern "C" void *kmalloc(void *km, size_t size) __attribute__((weak));
+extern "C" void kfree(void *km, void *ptr) __attribute__((weak));
+
+namespace {
+
+using mm2b::cuda_ok;
+using mm2b::set_error;
+
+constexpr int NSLOT = 3;
+
+template <class T> cudaError_t dmalloc(T **p, size_t bytes) { return cudaMalloc((void**)p, bytes ? bytes : 1); }
+template <class T> cudaError_t hmalloc(T **p, size_t bytes, unsigned flags) { return cudaHostAlloc((void**)p, bytes ? bytes : 1, flags); }
+
+void *host_kmalloc(void *km, size_t size)
+{
+	if (kmalloc) return kmalloc(km, size);
+	if (km) { fprintf(stderr, "[mm2b] a kalloc arena was passed but the host application exports no kmalloc\n"); exit(1); }
+	return size ? malloc(size) : 0;     // kalloc.c:133-134
+}
+void host_kfree(void *km, void *p)
+{
+	if (kfree) { kfree(km, p); return; }
+	if (km) { fprintf(stderr, "[mm2b] a kalloc arena was passed but the host application exports no kfree\n"); exit(1); }
+	free(p);
+}
+
+// Device + pinned buffers for one sub-batch in flight
+struct Slot {
+	int device = -1;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[6] = {};     // 0 start, 1 h2d done, 2 kernels done, 3 counts d2h done, 4 out d2h start, 5 out d2h done
+	mm2b_workspace_t *ws = nullptr;
+	int64_t cap_anchors = 0, cap_reads = 0;
+	int64_t *d_off = nullptr, *d_u_off = nullptr, *d_b_off = nullptr;
+	mm2b_anchor_t *d_a = nullptr, *d_b = nullptr;
+	uint64_t *d_u = nullptr;
+	int32_t *d_n_u = nullptr, *d_n_v = nullptr, *d_status = nullptr;
+	int64_t *h_off = nullptr, *h_u_off = nullptr, *h_b_off = nullptr;   // pinned
+	// the sub-batch currently occupying the slot
+	int sub = -1;
+	int stage = 0;              // 0 free, 1 kernels + counts in flight, 2 outputs in flight
+
+	bool create(int dev)
+	{
+		device = dev;
+		if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
+		if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
+		return true;
+	}
+	void release()
+	{
+		if (device < 0) return;
+		cudaSetDevice(device);
+		mm2b_ws_destroy(ws), ws = nullptr;
+		cudaFree(d_off), cudaFree(d_u_off), cudaFree(d_b_off), cudaFree(d_a), cudaFree(d_b), cudaFree(d_u);
+		cudaFree(d_n_u), cudaFree(d_n_v), cudaFree(d_status);
+		cudaFreeHost(h_off), cudaFreeHost(h_u_off), cudaFreeHost(h_b_off);
+		d_off = d_u_off = d_b_off = nullptr, d_a = d_b = nullptr, d_u = nullptr, d_n_u = d_n_v = d_status = nullptr;
+		h_off = h_u_off = h_b_off = nullptr;
+		cap_anchors = cap_reads = 0;
+	}
+	void destroy()
+	{
+		release();
+		if (device < 0) return;
+		for (auto &e : ev) if (e) cudaEventDestroy(e);
+		if (stream) cudaStreamDestroy(stream);
+		device = -1;
+	}
+	bool ensure(int64_t n_anchors, int64_t n_reads)
+	{
+		if (n_anchors <= cap_anchors && n_reads <= cap_reads) return true;
+		const int64_t na = std::max<int64_t>(n_anchors + n_anchors / 4, std::max<int64_t>(cap_anchors, 1024));
+		const int64_t nr = std::max<int64_t>(n_reads + n_reads / 4, std::max<int64_t>(cap_reads, 64));
+		cudaStreamSynchronize(stream);
+		release();
+		ws = mm2b_ws_create(device, na, nr);
+		if (!ws) return false;
+		bool ok = cuda_ok(dmalloc(&d_off, (nr + 1) * 8), "cudaMalloc") && cuda_ok(dmalloc(&d_u_off, (nr + 1) * 8), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_b_off, (nr + 1) * 8), "cudaMalloc") && cuda_ok(dmalloc(&d_a, na * 16), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_b, na * 16), "cudaMalloc") && cuda_ok(dmalloc(&d_u, na * 8), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_n_u, nr * 4), "cudaMalloc") && cuda_ok(dmalloc(&d_n_v, nr * 4), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_status, nr * 4), "cudaMalloc")
+		       && cuda_ok(hmalloc(&h_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_u_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_b_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc");
+		if (!ok) return false;
+		cap_anchors = na, cap_reads = nr;
+		return true;
+	}
+};
+
+struct SubBatch { int64_t r0, r1; };     // reads [r0, r1)
+
+struct Job {
+	const mm2b_params_t *par;
+	int64_t n_reads;
+	const int64_t *off;
+	const mm2b_anchor_t *a;
+	int32_t *n_u, *n_v, *status;
+	int64_t *u_off, *b_off;
+	uint64_t *u;
+	mm2b_anchor_t *b;
+	std::vector<SubBatch> subs;
+	std::atomic<int> next{0};
+	std::atomic<int> failed{0};
+	char err[512] = {0};
+	std::mutex mu;
+	std::condition_variable cv;
+	int workers_left = 0;
+	// stats
+	std::atomic<int64_t> n_chains{0}, n_chained{0}, cells_issued{0}, n_general{0};
+	double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;   // guarded by mu
+};
+
+struct Device {
+	int id = -1;
+	Slot slots[NSLOT];
+	std::thread worker;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<Job*> queue;
+	bool stop = false;
+};
+
+struct Backend {
+	std::vector<Device*> devs;
+	std::mutex mu;              // guards init/shutdown
+	bool up = false;
+	int64_t sub_anchors = 4 << 20;
+	bool want_stats = true;
+} g;
+
+void job_fail(Job *job)
+{
+	std::lock_guard<std::mutex> lk(job->mu);
+	if (!job->failed.exchange(1)) snprintf(job->err, sizeof(job->err), "%s", mm2b_last_error());
+}
+
+// enqueue H2D + kernels + D2H of the per-read counts for sub-batch `si` on `s`
+bool stage_issue(Slot &s, Job *job, int si)
+{
+	const SubBatch sb = job->subs[si];
+	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0], na = job->off[sb.r1] - a0;
+	if (!s.ensure(na, nr)) return false;
+	for (int64_t r = 0; r <= nr; ++r) s.h_off[r] = job->off[sb.r0 + r] - a0;
+	cudaStream_t st = s.stream;
+	bool ok = cuda_ok(cudaEventRecord(s.ev[0], st), "cudaEventRecord")
+	       && cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off")
+	       && (na == 0 || cuda_ok(cudaMemcpyAsync(s.d_a, job->a + a0, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors"))
+	       && cuda_ok(cudaEventRecord(s.ev[1], st), "cudaEventRecord");
+	if (!ok) return false;
+	if (mm2b_chain_batch_device(s.ws, job->par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st) != MM2B_OK)
+		return false;
+	ok = cuda_ok(cudaEventRecord(s.ev[2], st), "cudaEventRecord")
+	  && cuda_ok(cudaMemcpyAsync(job->n_u + sb.r0, s.d_n_u, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_u")
+	  && cuda_ok(cudaMemcpyAsync(job->n_v + sb.r0, s.d_n_v, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_v")
+	  && cuda_ok(cudaMemcpyAsync(job->status + sb.r0, s.d_status, nr * 4, cudaMemcpyDeviceToHost, st), "D2H status")
+	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
+	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
+	  && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord");
+	s.sub = si, s.stage = 1;
+	return ok;
+}
+
+// counts are on the host: publish offsets, enqueue the D2H of exactly the packed u[] / b[] bytes
+bool stage_outputs(Slot &s, Job *job)
+{
+	const SubBatch sb = job->subs[s.sub];
+	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0];
+	if (!cuda_ok(cudaEventSynchronize(s.ev[3]), "cudaEventSynchronize")) return false;
+	const int64_t tot_u = s.h_u_off[nr], tot_b = s.h_b_off[nr];
+	// sub-batch outputs are packed from the sub-batch's own anchor offset: they always fit there since n_v <= n per read
+	for (int64_t r = 0; r < nr; ++r) job->u_off[sb.r0 + r] = a0 + s.h_u_off[r], job->b_off[sb.r0 + r] = a0 + s.h_b_off[r];
+	cudaStream_t st = s.stream;
+	bool ok = cuda_ok(cudaEventRecord(s.ev[4], st), "cudaEventRecord")
+	       && (tot_u == 0 || cuda_ok(cudaMemcpyAsync(job->u + a0, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"))
+	       && (tot_b == 0 || cuda_ok(cudaMemcpyAsync(job->b + a0, s.d_b, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st), "D2H b"))
+	       && cuda_ok(cudaEventRecord(s.ev[5], st), "cudaEventRecord");
+	job->n_chains += tot_u, job->n_chained += tot_b;
+	s.stage = 2;
+	return ok;
+}
+
+bool stage_finish(Slot &s, Job *job)
+{
+	if (!cuda_ok(cudaEventSynchronize(s.ev[5]), "cudaEventSynchronize")) return false;
+	if (g.want_stats) {
+		float h2d = 0, ker = 0, d2h0 = 0, d2h1 = 0;
+		cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]), cudaEventElapsedTime(&ker, s.ev[1], s.ev[2]);
+		cudaEventElapsedTime(&d2h0, s.ev[2], s.ev[3]), cudaEventElapsedTime(&d2h1, s.ev[4], s.ev[5]);
+		mm2b_stats_t st;
+		if (mm2b_ws_stats(s.ws, s.stream, &st) == MM2B_OK) job->cells_issued += st.cells_issued, job->n_general += st.n_general_reads;
+		std::lock_guard<std::mutex> lk(job->mu);
+		job->h2d_ms += h2d, job->kernel_ms += ker, job->d2h_ms += d2h0 + d2h1;
+	}
+	s.stage = 0, s.sub = -1;
+	return true;
+}
+
+void run_job_on_device(Device *d, Job *job)
+{
+	cudaSetDevice(d->id);
+	std::deque<int> fifo;       // slot indices in issue order
+	const int n_subs = (int)job->subs.size();
+	bool more = true;
+	for (;;) {
+		// fill free slots
+		while (more && (int)fifo.size() < NSLOT && !job->failed.load()) {
+			const int si = job->next.fetch_add(1);
+			if (si >= n_subs) { more = false; break; }
+			int k = 0;
+			while (d->slots[k].stage != 0) ++k;
+			if (!stage_issue(d->slots[k], job, si)) { job_fail(job); d->slots[k].stage = 0; break; }
+			fifo.push_back(k);
+		}
+		if (fifo.empty()) break;
+		const int k = fifo.front();
+		fifo.pop_front();
+		Slot &s = d->slots[k];
+		if (job->failed.load()) { cudaStreamSynchronize(s.stream); s.stage = 0; continue; }
+		if (s.stage == 1) {
+			if (!stage_outputs(s, job)) { job_fail(job); s.stage = 0; continue; }
+			fifo.push_back(k);      // comes round again once younger sub-batches have been looked at
+		} else {
+			if (!stage_finish(s, job)) { job_fail(job); s.stage = 0; }
+		}
+	}
+}
+
+void device_worker(Device *d)
+{
+	cudaSetDevice(d->id);
+	for (;;) {
+		Job *job = nullptr;
+		{
+			std::unique_lock<std::mutex> lk(d->mu);
+			d->cv.wait(lk, [&] { return d->stop || !d->queue.empty(); });
+			if (d->queue.empty()) return;
+			job = d->queue.front();
+			d->queue.pop_front();
+		}
+		run_job_on_device(d, job);
+		{
+			std::lock_guard<std::mutex> lk(job->mu);
+			--job->workers_left;
+		}
+		job->cv.notify_all();
+	}
+}
+
+int parse_device_list(const char *s, std::vector<int> &out)
+{
+	while (s && *s) {
+		char *e;
+		long v = strtol(s, &e, 10);
+		if (e == s) break;
+		out.push_back((int)v);
+		s = *e == ',' ? e + 1 : e;
+	}
+	return (int)out.size();
+}
+
+// ---- per-thread single-read path (mm_chain_dp) -------------------------------------------------------------------
+struct ThreadCtx {
+	Slot slot;
+	int32_t *h_cnt = nullptr;           // pinned: n_u, n_v, status
+	mm2b_anchor_t *h_a = nullptr, *h_b = nullptr;   // pinned staging, cap_anchors
+	uint64_t *h_u = nullptr;
+	int64_t h_cap = 0;
+	bool live = false;
+};
+std::mutex g_tctx_mu;
+std::vector<ThreadCtx*> g_tctx;
+std::atomic<int> g_tctx_rr{0};
+
+ThreadCtx *thread_ctx()
+{
+	static thread_local ThreadCtx *t = nullptr;
+	if (t && t->live) return t;
+	t = new ThreadCtx();
+	const int dev = g.devs[g_tctx_rr.fetch_add(1) % g.devs.size()]->id;
+	if (!t->slot.create(dev)) { fprintf(stderr, "[mm2b] %s\n", mm2b_last_error()); exit(1); }
+	hmalloc(&t->h_cnt, 64, cudaHostAllocPortable);
+	t->live = true;
+	std::lock_guard<std::mutex> lk(g_tctx_mu);
+	g_tctx.push_back(t);
+	return t;
+}
+
+[[noreturn]] void fatal(const char *what)
+{
+	fprintf(stderr, "[mm2b] fatal: %s: %s\n", what, mm2b_last_error());     // same behaviour as checkError (chain_hardware.cpp:208)
+	exit(EXIT_FAILURE);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mm2b_init(int n_devices, const int *devices)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (g.up) return MM2B_OK;
+	int visible = 0;
+	if (!cuda_ok(cudaGetDeviceCount(&visible), "cudaGetDeviceCount") || visible <= 0) {
+		if (visible <= 0) set_error("%s%s", "mm2b_init: no CUDA device visible", "");
+		return MM2B_ERR_CUDA;
+	}
+	std::vector<int> ids;
+	if (n_devices > 0 && devices) ids.assign(devices, devices + n_devices);
+	else if (n_devices > 0) for (int i = 0; i < n_devices; ++i) ids.push_back(i);
+	else if (!parse_device_list(getenv("MM2B_DEVICES"), ids)) for (int i = 0; i < visible; ++i) ids.push_back(i);
+	for (int id : ids) if (id < 0 || id >= visible) { set_error("%s%s", "mm2b_init: device id out of range", ""); return MM2B_ERR_ARG; }
+	if (const char *s = getenv("MM2B_SUB_ANCHORS")) { const long long v = atoll(s); if (v > 0) g.sub_anchors = v; }
+	for (int id : ids) {
+		Device *d = new Device();
+		d->id = id;
+		for (auto &s : d->slots) if (!s.create(id)) return MM2B_ERR_CUDA;
+		g.devs.push_back(d);
+	}
+	for (Device *d : g.devs) d->worker = std::thread(device_worker, d);
+	g.up = true;
+	return MM2B_OK;
+}
+
+void mm2b_shutdown(void)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.up) return;
+	for (Device *d : g.devs) {
+		{ std::lock_guard<std::mutex> l2(d->mu); d->stop = true; }
+		d->cv.notify_all();
+	}
+	for (Device *d : g.devs) {
+		if (d->worker.joinable()) d->worker.join();
+		for (auto &s : d->slots) s.destroy();
+		delete d;
+	}
+	g.devs.clear();
+	{
+		std::lock_guard<std::mutex> l3(g_tctx_mu);
+		for (ThreadCtx *t : g_tctx) {
+			t->slot.destroy();
+			cudaFreeHost(t->h_cnt), cudaFreeHost(t->h_a), cudaFreeHost(t->h_b), cudaFreeHost(t->h_u);
+			t->live = false;    // the owning thread re-creates it on next use
+		}
+		g_tctx.clear();
+	}
+	g.up = false;
+}
+
+int mm2b_num_devices(void) { return g.up ? (int)g.devs.size() : 0; }
+
+int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
+                     int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
+                     uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats)
+{
+	if (!g.up) {
+		const int rc = mm2b_init(0, nullptr);
+		if (rc != MM2B_OK) return rc;
+	}
+	if (!par || n_reads < 0 || !off || !n_u || !n_v || !status || !u_off || !b_off) { set_error("%s%s", "mm2b_chain_batch: NULL argument", ""); return MM2B_ERR_ARG; }
+	const int64_t n_anchors = n_reads > 0 ? off[n_reads] : 0;
+	if (n_anchors > 0 && (!a || !u || !b)) { set_error("%s%s", "mm2b_chain_batch: NULL buffer", ""); return MM2B_ERR_ARG; }
+	if (u_cap < n_anchors || b_cap < n_anchors) { set_error("%s%s", "mm2b_chain_batch: u_cap and b_cap must be >= off[n_reads]", ""); return MM2B_ERR_CAPACITY; }
+	Job job;
+	job.par = par, job.n_reads = n_reads, job.off = off, job.a = a;
+	job.n_u = n_u, job.n_v = n_v, job.status = status, job.u_off = u_off, job.b_off = b_off, job.u = u, job.b = b;
+	for (int64_t r0 = 0; r0 < n_reads;) {       // cut into sub-batches of <= sub_anchors anchors (a larger single read stands alone)
+		const int64_t lim = off[r0] + g.sub_anchors;
+		int64_t r1 = std::upper_bound(off + r0 + 1, off + n_reads + 1, lim) - off - 1;
+		if (r1 <= r0) r1 = r0 + 1;
+		if (r1 - r0 > (1 << 20)) r1 = r0 + (1 << 20);
+		job.subs.push_back(SubBatch{r0, r1});
+		r0 = r1;
+	}
+	u_off[n_reads] = n_anchors, b_off[n_reads] = n_anchors;
+	if (!job.subs.empty()) {
+		const int n_workers = (int)std::min<size_t>(g.devs.size(), job.subs.size());
+		job.workers_left = n_workers;
+		for (int i = 0; i < n_workers; ++i) {
+			Device *d = g.devs[i];
+			{ std::lock_guard<std::mutex> lk(d->mu); d->queue.push_back(&job); }
+			d->cv.notify_one();
+		}
+		std::unique_lock<std::mutex> lk(job.mu);
+		job.cv.wait(lk, [&] { return job.workers_left == 0; });
+	}
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		stats->n_reads = n_reads, stats->n_anchors = n_anchors, stats->n_chains = job.n_chains, stats->n_chained = job.n_chained;
+		stats->cells_issued = job.cells_issued, stats->n_general_reads = job.n_general;
+		stats->h2d_ms = job.h2d_ms, stats->kernel_ms = job.kernel_ms, stats->d2h_ms = job.d2h_ms;
+	}
+	if (job.failed.load()) { set_error("%s%s", job.err, ""); return MM2B_ERR_CUDA; }
+	return MM2B_OK;
+}
+
+mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
+                           float gap_scale, int is_cdna, int n_segs, int64_t n, mm2b_anchor_t *a, int *n_u_, uint64_t **_u,
+                           void *km, int tid)
+{
+	(void)tid;
+	if (_u) *_u = 0, *n_u_ = 0;
+	if (n == 0 || a == 0) {                                           // chain.c:38-41
+		host_kfree(km, a);
+		return 0;
+	}
+	if (!g.up && mm2b_init(0, nullptr) != MM2B_OK) fatal("mm2b_init");
+	ThreadCtx *t = thread_ctx();
+	Slot &s = t->slot;
+	cudaSetDevice(s.device);
+	if (!s.ensure(n, 1)) fatal("workspace allocation");
+	if (n > t->h_cap) {
+		cudaFreeHost(t->h_a), cudaFreeHost(t->h_b), cudaFreeHost(t->h_u);
+		t->h_cap = s.cap_anchors;
+		if (!cuda_ok(hmalloc(&t->h_a, t->h_cap * 16, cudaHostAllocPortable), "cudaHostAlloc") ||
+		    !cuda_ok(hmalloc(&t->h_b, t->h_cap * 16, cudaHostAllocPortable), "cudaHostAlloc") ||
+		    !cuda_ok(hmalloc(&t->h_u, t->h_cap * 8, cudaHostAllocPortable), "cudaHostAlloc")) fatal("pinned staging");
+	}
+	const mm2b_params_t par = {max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
+	memcpy(t->h_a, a, (size_t)n * 16);
+	s.h_off[0] = 0, s.h_off[1] = n;
+	cudaStream_t st = s.stream;
+	bool ok = cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, 16, cudaMemcpyHostToDevice, st), "H2D off")
+	       && cuda_ok(cudaMemcpyAsync(s.d_a, t->h_a, (size_t)n * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
+	if (!ok || mm2b_chain_batch_device(s.ws, &par, 1, n, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st) != MM2B_OK)
+		fatal("enqueue");
+	ok = cuda_ok(cudaMemcpyAsync(t->h_cnt, s.d_n_u, 4, cudaMemcpyDeviceToHost, st), "D2H")
+	  && cuda_ok(cudaMemcpyAsync(t->h_cnt + 1, s.d_n_v, 4, cudaMemcpyDeviceToHost, st), "D2H")
+	  && cuda_ok(cudaMemcpyAsync(t->h_cnt + 2, s.d_status, 4, cudaMemcpyDeviceToHost, st), "D2H")
+	  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+	if (!ok) fatal("chain");
+	const int n_u = t->h_cnt[0], n_v = t->h_cnt[1], status = t->h_cnt[2];
+	if (n_u > 0) {
+		ok = cuda_ok(cudaMemcpyAsync(t->h_u, s.d_u, (size_t)n_u * 8, cudaMemcpyDeviceToHost, st), "D2H u")
+		  && cuda_ok(cudaMemcpyAsync(t->h_b, s.d_b, (size_t)n_v * 16, cudaMemcpyDeviceToHost, st), "D2H b")
+		  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+		if (!ok) fatal("copy back");
+	}
+	host_kfree(km, a);                                                // chain.c:356 / :421 — `a` is consumed on every path
+	if (status != MM2B_READ_OK) return 0;                             // chain.c:355-358
+	// chain.c:359, :397: u has the size of the chain-END list in the reference; only its first n_u entries are defined, so
+	// an allocation of max(n_u,1) entries is indistinguishable to the caller (map.c:344-379 reads u[0..n_u) and frees it)
+	uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(n_u, 1) * 8);
+	mm2b_anchor_t *b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)n_v * 16);      // kmalloc(km, 0) == NULL, as at chain.c:397
+	if (n_u > 0) memcpy(u, t->h_u, (size_t)n_u * 8);
+	if (n_v > 0) memcpy(b, t->h_b, (size_t)n_v * 16);
+	*n_u_ = n_u, *_u = u;
+	return b;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/*.h declares.
+No compute calls are made here (there is no GPU on the build machine)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_functions(header):
+    src = open(header).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    return sorted(set(re.findall(r"\b(mm2b_[a-z0-9_]+|mm_chain_dp)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    bld = pkg("build")
+    lib = bld.build_all()
+    assert os.path.exists(lib)
+    L = ctypes.CDLL(lib)
+    names = _declared_functions(os.path.join(ROOT, "include", "mm2chain_b200.h"))
+    assert "mm_chain_dp" in names and "mm2b_chain_batch" in names and len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "C ABI symbol missing from the library: " + n
+    binding = pkg("binding")
+    assert sorted(binding.EXPORTS) == names, "binding.EXPORTS out of sync with the header"
+    assert binding.load().mm2b_abi_version() == 1
+
+
+def test_params_struct_layout_matches_oracle(pkg, oracle):
+    binding = pkg("binding")
+    assert ctypes.sizeof(binding.Params) == ctypes.sizeof(oracle.Params) == 40
+    assert [f[0] for f in binding.Params._fields_] == [f[0] for f in oracle.Params._fields_]
+
+
+def test_no_cpu_fallback_without_gpu(pkg):
+    """On a machine without a usable CUDA device the product path must fail loudly, not compute on the CPU."""
+    binding = pkg("binding")
+    L = binding.load()
+    if L.mm2b_cuda_device_count() > 0:
+        pytest.skip("a GPU is present")
+    import numpy as np
+    off = np.array([0, 3], np.int64)
+    a = np.zeros(3, binding.ANCHOR)
+    with pytest.raises(binding.Mm2bError):
+        binding.chain_batch(binding.Params(), off, a)
+    with pytest.raises(binding.Mm2bError):
+        binding.init()
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under minimap2-fpga_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("minimap2-fpga_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c")):
+                    txt = open(os.path.join(dp, fn), errors="replace").read()
+                    if re.search(r"import oracle|from oracle|oracle_py|oracle/|mm2o_|liboracle|libmm2ref|chain_oracle", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad

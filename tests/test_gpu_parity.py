@@ -1,0 +1,121 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libmm2chain_b200.so; the oracle (pinned against the reference by tests/test_oracle.py) and the committed reference
+captures in tests/golden/ are the checkers.  Bit-exact: integer scores, indices and anchor bytes must be identical.
+"""
+import numpy as np
+import pytest
+
+import fuzz
+from conftest import golden_names, load_golden
+from test_oracle import PARAM_SETS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def binding(pkg):
+    b = pkg("binding")
+    L = b.load()
+    assert L.mm2b_cuda_device_count() > 0, "no CUDA device: the GPU tests must run on the B200 box"
+    b.init(1)
+    yield b
+    b.shutdown()
+
+
+def _groups(recs):
+    """Group capture records by parameter set (the sr preset changes max_dist per read)."""
+    out = {}
+    for r in recs:
+        out.setdefault(tuple(sorted(r["par"].as_dict().items())), []).append(r)
+    return list(out.values())
+
+
+def _compare_batch(res, recs_or_ref, off, name):
+    for r in range(len(off) - 1):
+        if isinstance(recs_or_ref, list):
+            u_ref, b_ref = recs_or_ref[r]["u"], recs_or_ref[r]["b"]
+            ok_ref = not recs_or_ref[r]["u_null"]
+        else:
+            o, nu, nv = int(off[r]), int(recs_or_ref["n_u"][r]), int(recs_or_ref["n_v"][r])
+            u_ref, b_ref = recs_or_ref["u"][o:o + nu], recs_or_ref["b"][o:o + nv]
+            ok_ref = None
+        nu, nv = int(res["n_u"][r]), int(res["n_v"][r])
+        assert nu == len(u_ref) and nv == len(b_ref), (name, r, nu, len(u_ref), nv, len(b_ref))
+        uo, bo = int(res["u_off"][r]), int(res["b_off"][r])
+        assert np.array_equal(res["u"][uo:uo + nu], u_ref), (name, r, "u")
+        assert np.array_equal(res["b"][bo:bo + nv], b_ref), (name, r, "b")
+        if ok_ref is not None:
+            assert (int(res["status"][r]) == 2) == ok_ref, (name, r, "status")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_device_batch_matches_reference_capture(binding, name):
+    """f/p/v per anchor and u[]/b[] per read against what the reference CLI itself produced."""
+    from oracle import dumpio
+    for recs in _groups(load_golden(name)):
+        off, a = dumpio.to_batch(recs)
+        par = binding.Params(**recs[0]["par"].as_dict())
+        db = binding.DeviceBatch(par, off, a, device=0, keep_fpv=True)
+        db.run()
+        f, p, v = db.fpv()
+        res = db.results()
+        for k, r in enumerate(recs):
+            s, e = int(off[k]), int(off[k + 1])
+            assert np.array_equal(f[s:e], r["f"]), (name, k, "f", int(np.argmax(f[s:e] != r["f"])))
+            assert np.array_equal(p[s:e], r["p"]), (name, k, "p", int(np.argmax(p[s:e] != r["p"])))
+            assert np.array_equal(v[s:e], r["v"]), (name, k, "v")
+        _compare_batch(res, recs, off, name)
+        db.close()
+
+
+@pytest.mark.parametrize("name", ["mt_map-ont", "inv_map-ont", "syn_ont_n1m5", "sr_paired", "splice"])
+def test_mm_chain_dp_dropin_matches_reference_capture(binding, name):
+    """The per-read boundary itself: same 16 positional arguments, same NULL conventions as chain.c:29."""
+    for r in load_golden(name):
+        par = binding.Params(**r["par"].as_dict())
+        u, b, u_null, b_null = binding.chain_read(par, r["a"])
+        assert np.array_equal(u, r["u"]) and np.array_equal(b, r["b"])
+        assert u_null == r["u_null"] and b_null == r["b_null"]
+    u, b, u_null, b_null = binding.chain_read(binding.Params(), np.empty(0, binding.ANCHOR))
+    assert u_null and b_null and len(u) == 0
+
+
+@pytest.mark.parametrize("pi", range(len(PARAM_SETS)))
+def test_host_batch_matches_oracle_fuzz(binding, oracle, pi):
+    """Adversarial inputs (ties, dr==0 / dq==0, dense windows, many chains, empty and 1-anchor reads) through the host-buffer call."""
+    kw = PARAM_SETS[pi]
+    off, a = fuzz.mixed_batch(200 + pi, n_reads=64, seg_ids=kw.get("n_segs", 1))
+    ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=4)
+    res = binding.chain_batch(binding.Params(**kw), off, a)
+    _compare_batch(res, ref, off, kw)
+    assert res["stats"].n_chains == int(ref["n_u"].sum()) and res["stats"].n_chained == int(ref["n_v"].sum())
+
+
+def test_deep_lookback_and_long_reads(binding, oracle):
+    """Windows far deeper than the 256-slot shared-memory ring, max_iter clamp, > 64 chains (radix tie order)."""
+    rng = np.random.default_rng(5)
+    reads = [fuzz.dense_repeat(rng, 6000, width=4500, qwidth=4000), fuzz.dense_repeat(rng, 3000, width=800, qwidth=6000),
+             fuzz.many_chains(rng, 400, 4), fuzz.lattice(rng, 5000), fuzz.collinear(rng, 20000, 500)]
+    off, a = fuzz.batch(reads)
+    for kw in (dict(), dict(max_iter=300, max_skip=2), dict(min_cnt=1, min_sc=1)):
+        ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=8)
+        res = binding.chain_batch(binding.Params(**kw), off, a)
+        _compare_batch(res, ref, off, kw)
+
+
+def test_subbatching_and_order_independence(binding, oracle, monkeypatch):
+    """Results must not depend on how the batch is cut into sub-batches or on read order."""
+    off, a = fuzz.mixed_batch(77, n_reads=120, scale=0.5)
+    par, opar = binding.Params(), oracle.Params()
+    ref = oracle.replay(opar, off, a, n_threads=4)
+    res = binding.chain_batch(par, off, a)
+    _compare_batch(res, ref, off, "whole")
+    perm = np.random.default_rng(1).permutation(len(off) - 1)
+    reads = [a[off[r]:off[r + 1]] for r in perm]
+    off2, a2 = fuzz.batch(reads)
+    res2 = binding.chain_batch(par, off2, a2)
+    for k, r in enumerate(perm):
+        nu, nv = int(res["n_u"][r]), int(res["n_v"][r])
+        assert int(res2["n_u"][k]) == nu and int(res2["n_v"][k]) == nv
+        assert np.array_equal(res2["u"][res2["u_off"][k]:res2["u_off"][k] + nu], res["u"][res["u_off"][r]:res["u_off"][r] + nu])
+        assert np.array_equal(res2["b"][res2["b_off"][k]:res2["b_off"][k] + nv], res["b"][res["b_off"][r]:res["b_off"][r] + nv])
