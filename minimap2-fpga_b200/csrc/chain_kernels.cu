@@ -382,12 +382,15 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 	if (n_u == 0) { n_u_out = 0, n_v_out = 0, status = MM2B_READ_NO_CHAIN; return; }   // chain.c:355-358
 	status = MM2B_READ_OK;
 
-	// chain.c:368-372: descending order (keys are distinct: the low word is the anchor index)
+	// chain.c:368-372: descending order (a total order on values, so any correct sort gives the reference's result)
 	if (n_u > 1) {
 		if (n_u <= 32) {
 			const uint64_t key = lane < n_u ? U[lane] : 0;
 			int rank = 0;
-			for (int t = 0; t < n_u; ++t) rank += __shfl_sync(FULL, key, t) > key;
+			for (int t = 0; t < n_u; ++t) {     // two ends can share a peak => equal keys: break ties by position
+				const uint64_t kt = __shfl_sync(FULL, key, t);
+				rank += kt > key || (kt == key && t < lane);
+			}
 			__syncwarp();
 			if (lane < n_u) U[rank] = key;
 		} else {

@@ -180,7 +180,7 @@ int mm2o_chain(const mm2o_params_t *par, int64_t n, const mm2o_anchor_t *a, int3
 			u[n_u++] = (uint64_t)f[j] << 32 | (uint64_t)j;
 		}
 	}
-	qsort(u, (size_t)n_u, 8, cmp_u64_desc);               /* chain.c:368-372: ascending + reverse == descending; values distinct */
+	qsort(u, (size_t)n_u, 8, cmp_u64_desc);               /* chain.c:368-372: ascending + reverse == descending; equal values (two ends sharing a peak) are interchangeable */
 
 	/* chain.c:374-391 — greedy backtrack in score order; marks persist even when a candidate is dropped */
 	path = (int32_t*)malloc((size_t)n * 4);
