@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Benchmark of the chaining hot path (mm_chain_dp) on B200 — contract in the task brief.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic reads (BASELINE.json configs[1]: map-ont,
+100k ONT reads of 10 kb mean / ~10 % error vs a 100 Mbp random reference, per GPU: weak scaling).
+  value   GCUPS with anchors already resident in HBM (K0..K3 on the device, CUDA-event timed)
+  e2e     GCUPS through the host-buffer C-ABI call mm2b_chain_batch: pinned host anchors in, u[]/b[] out, H2D and D2H inside
+GCUPS counts reference-semantics cells (iterations of chain.c:197), which the kernel tallies exactly (tests check the tally
+against the oracle).  The reference arm (--impl reference) and the cpu_baseline object time the reference's own compiled
+software chaining (oracle/_ref/libmm2ref.so, else the oracle port) on all host cores over the same reads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+INT_OPS_PER_CELL = 30          # INT32-equivalent ops per reference cell
+BYTES_PER_ANCHOR = 40          # unavoidable device traffic per anchor (16 in, <=16 b out, <=8 u/indices)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(n_reads, seed):
+    wl = load_package("workload")
+    t0 = time.time()
+    off, a = wl.synth_anchor_batch(n_reads, seed=seed)
+    return off, a, time.time() - t0
+
+
+def cpu_arm(off, a, n_threads, steps, warmup, sample_reads=None):
+    """Reference's CPU chaining over (a sample of) the batch with n_threads host threads. Returns dict."""
+    from oracle import oracle_py as O
+    O.build()
+    n_reads = len(off) - 1
+    ns = n_reads if sample_reads is None else min(sample_reads, n_reads)
+    off_s, a_s = off[:ns + 1], a[:int(off[ns])]
+    par = O.Params()
+    cells = O.replay(par, off_s, a_s, n_threads=n_threads, want_out=False)["stats"].cells      # the port counts cells; also warms caches
+    kind = "reference" if O.have_ref() else "port"
+    times = []
+    for it in range(warmup + steps):
+        r = O.replay(par, off_s, a_s, n_threads=n_threads, use_ref=(kind == "reference"), want_out=False)
+        if it >= warmup:
+            times.append(r["seconds"])
+    sec = sum(times) / len(times)
+    return dict(value=cells / sec / 1e9, unit="GCUPS", cores=n_threads, kind=kind, seconds_per_step=sec, reads_per_s=ns / sec,
+                sample="%d of %d reads (%d anchors, %d reference cells) per step, %d steps" % (ns, n_reads, len(a_s), cells, steps),
+                cells=int(cells), reads=ns)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=100000, help="reads per GPU (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "map-ont: %d synthetic ONT reads per GPU (10 kb mean, ~10%% error) vs 100 Mbp random reference; "
+                          "chaining parameters of -x map-ont (max_dist 5000, bw 500, max_skip 25, max_iter 5000, min_cnt 3, min_sc 40)" % args.reads,
+              "reads_per_gpu": args.reads, "l2": "inputs (anchors + 40 B/anchor scratch) exceed the 126 MB L2, no flush needed",
+              "parallelism": "read-sharded, %d GPU(s), no collective" % world}
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        off, a, _ = make_workload(args.reads, seed=1000)
+        cores = os.cpu_count() or 1
+        r = cpu_arm(off, a, cores, max(args.steps, 1), max(args.warmup, 0))
+        line = {"impl": "reference", "metric": "chain_dp_gcups", "value": r["value"], "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": config, "reads_per_s": r["reads_per_s"],
+                "cpu_baseline": {"value": r["value"], "unit": "GCUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    binding = load_package("binding")
+    L = binding.load()
+    if not torch.cuda.is_available() or L.mm2b_cuda_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    off, a, gen_s = make_workload(args.reads, seed=1000 + rank)
+    n_reads, n_anchors = len(off) - 1, int(off[-1])
+    par = binding.Params()
+    binding.init([local_rank])
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------------------
+    db = binding.DeviceBatch(par, off, a, device=local_rank)
+    for _ in range(args.warmup):
+        db.run()
+    st = db.stats()
+    cells = int(st.cells_ref)
+    launches0 = L.mm2b_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        db.run()
+    e1.record()
+    barrier()
+    ms_value = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches_value = L.mm2b_launch_count() - launches0
+    # dominant-kernel duration: CUDA events on the launching stream around each launch, averaged over separate timed launches
+    k1 = []
+    for _ in range(min(args.steps, 5)):
+        db.run()
+        k1.append(db.chain_kernel_ms())
+    k1_avg = sum(k1) / len(k1)
+    clocks = sampler.stop() if rank == 0 else None
+    tot_cells = sum_over_ranks(cells)
+    tot_reads = sum_over_ranks(n_reads)
+    tot_anchors = sum_over_ranks(n_anchors)
+    value = tot_cells / (ms_value * 1e-3) / 1e9
+
+    # ---- e2e: pinned host buffers through mm2b_chain_batch ------------------------------------------------------
+    pin = {}
+    try:
+        h_a = binding.PinnedArray(max(n_anchors, 1), binding.ANCHOR)
+        h_a.array[:n_anchors] = a
+        pin = {"u": binding.PinnedArray(max(n_anchors, 1), np.uint64), "b": binding.PinnedArray(max(n_anchors, 1), binding.ANCHOR),
+               "n_u": binding.PinnedArray(n_reads, np.int32), "n_v": binding.PinnedArray(n_reads, np.int32), "status": binding.PinnedArray(n_reads, np.int32)}
+        out = {k: v.array for k, v in pin.items()}
+        res = None
+        for _ in range(args.warmup):
+            res = binding.chain_batch(par, off, h_a.array[:n_anchors], out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = binding.chain_batch(par, off, h_a.array[:n_anchors], out=out)
+        torch.cuda.synchronize(dev)
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        est = res["stats"]
+        h2d = 16 * n_anchors + 8 * (n_reads + 1)
+        d2h = int(est.n_chained) * 16 + int(est.n_chains) * 8 + n_reads * 12 + 16 * (n_reads + 1)
+        e2e = {"value": tot_cells / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+               "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": ms_e2e, "reads_per_s": tot_reads / (ms_e2e * 1e-3),
+               "api": "mm2b_chain_batch (pinned host anchors in, u[]/b[] out)", "stage_ms_sum_over_subbatches": {"h2d": est.h2d_ms, "kernels": est.kernel_ms, "d2h": est.d2h_ms}}
+    finally:
+        pin["a"] = h_a
+
+    # ---- CPU baseline on rank 0, N=1 only -------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(off, a, os.cpu_count() or 1, steps=2, warmup=1)
+        cpu = {"value": r["value"], "unit": "GCUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "reads_per_s": r["reads_per_s"]}
+        assert r["cells"] == cells, "GPU cell tally %d != oracle %d" % (cells, r["cells"])
+
+    if rank == 0:
+        peaks, how = measured_peaks()
+        int_peak = L.mm2b_measure_int32_peak(local_rank)      # G int-ops/s, measured live on this GPU
+        hbm_ach = BYTES_PER_ANCHOR * n_anchors / (k1_avg * 1e-3) / 1e9
+        int_ach = cells * INT_OPS_PER_CELL / (k1_avg * 1e-3) / 1e9
+        line = {"metric": "chain_dp_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": config, "reads_per_s": tot_reads / (ms_value * 1e-3), "anchors_per_s": tot_anchors / (ms_value * 1e-3),
+                "cells_per_step": int(tot_cells), "cells_issued_per_step_rank0": int(st.cells_issued), "anchors_per_step": int(tot_anchors),
+                "e2e": e2e, "gpu_launches": int(launches_value), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "chain_reads_kernel", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                             "algorithmic_bytes_per_launch": BYTES_PER_ANCHOR * n_anchors, "kernel_ms": k1_avg,
+                             "note": "the path is INT32-issue bound, not HBM bound (SURVEY.md 8d): see roofline_int32"},
+                "roofline_int32": {"bound": "int32_issue", "achieved": int_ach, "peak": int_peak, "unit": "Gop/s", "frac": int_ach / int_peak if int_peak > 0 else None,
+                                   "ops_per_cell": INT_OPS_PER_CELL, "peak_source": "measured live: mm2b_measure_int32_peak (IADD/LOP3/IMNMX mix on all SMs)"},
+                "cpu_baseline": cpu, "workload_gen_s": gen_s}
+        print(json.dumps(line), flush=True)
+    for v in pin.values():
+        v.free()
+    db.close()
+    binding.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

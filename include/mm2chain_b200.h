@@ -55,7 +55,9 @@ enum { MM2B_OK = 0, MM2B_ERR_CUDA = -1, MM2B_ERR_ARG = -2, MM2B_ERR_CAPACITY = -
 typedef struct {
 	int64_t n_reads, n_anchors;
 	int64_t n_chains, n_chained;     /* totals: sum n_u, sum n_v */
-	int64_t cells_issued;            /* GPU lanes evaluated (32 per chunk); the reference-semantics cell count comes from the oracle */
+	int64_t cells_issued;            /* GPU lanes evaluated (32 per chunk) */
+	int64_t cells_ref;               /* iterations of the reference's inner j loop (chain.c:197) these reads take, `continue`d ones
+	                                    included, up to the max_skip break: the "cell" of the GCUPS metric */
 	int64_t n_general_reads;         /* reads that took the general (multi-segment / cDNA / gap_scale != 1) scoring path */
 	double  h2d_ms, kernel_ms, d2h_ms; /* device-side timings of the last host-buffer call (CUDA events), 0 for device calls */
 } mm2b_stats_t;
@@ -107,6 +109,9 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 
 /* Counters of the last batch run on this workspace (synchronises the given stream). */
 int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream, mm2b_stats_t *stats);
+/* Device time of the dominant kernel (the warp-per-read chaining kernel) in the last batch run on this workspace, in ms,
+ * from CUDA events recorded on the launching stream around that one launch (synchronises on the second event). */
+double mm2b_ws_chain_kernel_ms(mm2b_workspace_t *ws);
 /* Kernels launched by this library since load (for bench.py's gpu_launches). */
 int64_t mm2b_launch_count(void);
 /* Debug / test access to the per-anchor DP state of the last batch: f[], p[], v[] as the reference has them at chain.c:238.

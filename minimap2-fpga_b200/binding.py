@@ -19,7 +19,7 @@ READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 
 EXPORTS = ["mm2b_init", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
-           "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_measure_int32_peak",
+           "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_measure_int32_peak",
            "mm_chain_dp"]
 
 
@@ -38,7 +38,7 @@ class Params(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "n_general_reads")] + \
+    _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "cells_ref", "n_general_reads")] + \
                [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")]
 
     def as_dict(self):
@@ -79,6 +79,7 @@ def load():
     L.mm2b_chain_batch_device.restype = i32
     L.mm2b_chain_batch_device.argtypes = [vp, C.POINTER(Params), i64, i64] + [vp] * 9 + [vp]
     L.mm2b_ws_stats.restype, L.mm2b_ws_stats.argtypes = i32, [vp, vp, C.POINTER(Stats)]
+    L.mm2b_ws_chain_kernel_ms.restype, L.mm2b_ws_chain_kernel_ms.argtypes = C.c_double, [vp]
     L.mm2b_launch_count.restype = i64
     L.mm2b_ws_copy_fpv.restype, L.mm2b_ws_copy_fpv.argtypes = i32, [vp, vp, i64, vp, vp, vp]
     L.mm2b_measure_int32_peak.restype, L.mm2b_measure_int32_peak.argtypes = C.c_double, [i32]
@@ -239,6 +240,9 @@ class DeviceBatch:
         st = Stats()
         _check(self.L.mm2b_ws_stats(self.ws, self._stream(), C.byref(st)), "mm2b_ws_stats")
         return st
+
+    def chain_kernel_ms(self):
+        return float(self.L.mm2b_ws_chain_kernel_ms(self.ws))
 
     def fpv(self):
         f, p, v = (np.empty(self.n_anchors, np.int32) for _ in range(3))

@@ -38,6 +38,7 @@ struct mm2b_workspace {
 	unsigned long long *counters;
 	int32_t *dbg_fpv;           // 3 * max_anchors when MM2B_KEEP_FPV=1
 	size_t bytes;
+	cudaEvent_t ev_k1[2];       // around the chaining kernel of the last batch
 	int64_t last_reads, last_anchors;
 	const int32_t *last_n_u, *last_n_v;
 	const int64_t *last_u_off, *last_b_off;
@@ -87,6 +88,7 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 		ws->bytes += (size_t)max_anchors * 12;
 	}
 	if (ok) ok = cuda_ok(cudaMemset(ws->counters, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
+	if (ok) ok = cuda_ok(cudaEventCreate(&ws->ev_k1[0]), "cudaEventCreate") && cuda_ok(cudaEventCreate(&ws->ev_k1[1]), "cudaEventCreate");
 	if (!ok) { mm2b_ws_destroy(ws); return 0; }
 	return ws;
 }
@@ -95,6 +97,8 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 {
 	if (!ws) return;
 	cudaSetDevice(ws->device);
+	if (ws->ev_k1[0]) cudaEventDestroy(ws->ev_k1[0]);
+	if (ws->ev_k1[1]) cudaEventDestroy(ws->ev_k1[1]);
 	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->tile), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
 	free(ws);
 }
@@ -122,7 +126,9 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	ba.par = *par, ba.n_reads = n_reads, ba.off = d_off, ba.a = d_a, ba.scratch = ws->scratch;
 	ba.n_u = d_n_u, ba.n_v = d_n_v, ba.status = d_status, ba.order = ws->order, ba.work_counter = ws->small;
 	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors;
+	cudaEventRecord(ws->ev_k1[0], stream);
 	launches += launch_chain(ba, ws->n_sms, stream);
+	cudaEventRecord(ws->ev_k1[1], stream);
 	launches += launch_offsets(n_reads, d_n_u, d_n_v, d_u_off, d_b_off, ws->tile, stream);
 	EmitArgs ea;
 	ea.n_reads = n_reads, ea.off = d_off, ea.a = d_a, ea.scratch = ws->scratch, ea.n_u = d_n_u, ea.n_v = d_n_v;
@@ -143,7 +149,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	int prev = -1;
 	cudaGetDevice(&prev);
 	if (prev != ws->device) cudaSetDevice(ws->device);
-	unsigned long long c[2] = {0, 0};
+	unsigned long long c[3] = {0, 0, 0};
 	int64_t tot[2] = {0, 0};
 	bool ok = cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize")
 	       && cuda_ok(cudaMemcpy(c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
@@ -154,7 +160,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	memset(st, 0, sizeof(*st));
 	st->n_reads = ws->last_reads, st->n_anchors = ws->last_anchors;
 	st->n_chains = tot[0], st->n_chained = tot[1];
-	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1];
+	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1], st->cells_ref = (int64_t)c[2];
 	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
 	return ok ? MM2B_OK : MM2B_ERR_CUDA;
 }
@@ -173,6 +179,15 @@ int mm2b_ws_copy_fpv(mm2b_workspace_t *ws, void *stream_, int64_t n_anchors, int
 	       && cuda_ok(cudaMemcpy(h_v, ws->dbg_fpv + 2 * ws->max_anchors, sz, cudaMemcpyDeviceToHost), "cudaMemcpy(v)");
 	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
 	return ok ? MM2B_OK : MM2B_ERR_CUDA;
+}
+
+double mm2b_ws_chain_kernel_ms(mm2b_workspace_t *ws)
+{
+	if (!ws || ws->last_reads <= 0) return 0.0;
+	float ms = 0;
+	if (!cuda_ok(cudaEventSynchronize(ws->ev_k1[1]), "cudaEventSynchronize") ||
+	    !cuda_ok(cudaEventElapsedTime(&ms, ws->ev_k1[0], ws->ev_k1[1]), "cudaEventElapsedTime")) return -1.0;
+	return (double)ms;
 }
 
 double mm2b_measure_int32_peak(int device)

@@ -84,7 +84,7 @@ __device__ __forceinline__ int skip_walk(unsigned recmask, unsigned hitmask, int
 // ---------------------------------------------------------------------------------------------------------------
 template <bool GENERAL>
 __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, int32_t *ring, int lane,
-                        unsigned long long &n_chunks, int32_t *dbg_fpv, int64_t dbg_stride, int64_t dbg_off)
+                        unsigned long long &n_chunks, unsigned long long &n_cells, int32_t *dbg_fpv, int64_t dbg_stride, int64_t dbg_off)
 {
 	int32_t *rx = ring, *ry = ring + RING, *rf = ring + 2 * RING, *rp = ring + 3 * RING, *rv = ring + 4 * RING, *rt = ring + 5 * RING;
 	const ulonglong2 *A = rc.A;
@@ -180,8 +180,9 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 					sc += fj;
 				}
 				if (!valid) sc = INT_MIN;
+				const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
 				const unsigned vmask = __ballot_sync(FULL, valid);
-				if (vmask == 0) continue;        // every cell `continue`d: no stamps, no n_skip change
+				if (vmask == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
 
 				// running max BEFORE each lane (lanes are visited in order 0..31): inclusive prefix max, shifted by one
 				int32_t m = sc;
@@ -215,6 +216,7 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 					v_best = __shfl_sync(FULL, vj, last);
 					max_j = jt - last;
 				}
+				n_cells += brk < 32 ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
 				if (brk < 32) break;                                                      // chain.c:230-231
 			}
 			if (lane == 0) {
@@ -506,7 +508,7 @@ chain_reads_kernel(const BatchArgs args)
 	__shared__ int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * RING];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int32_t *ring = smem_ring[warp];
-	unsigned long long n_chunks = 0, n_general = 0;
+	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0;
 
 	for (;;) {
 		int64_t slot = 0;
@@ -549,9 +551,9 @@ chain_reads_kernel(const BatchArgs args)
 		__syncwarp();
 		if (general) {
 			++n_general;
-			dp_fill<true>(args.par, rc, avg, ring, lane, n_chunks, args.dbg_fpv, args.n_anchors, o);
+			dp_fill<true>(args.par, rc, avg, ring, lane, n_chunks, n_cells, args.dbg_fpv, args.n_anchors, o);
 		} else {
-			dp_fill<false>(args.par, rc, avg, ring, lane, n_chunks, args.dbg_fpv, args.n_anchors, o);
+			dp_fill<false>(args.par, rc, avg, ring, lane, n_chunks, n_cells, args.dbg_fpv, args.n_anchors, o);
 		}
 		int n_u = 0, n_v = 0, status = MM2B_READ_OK;
 		extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
@@ -560,6 +562,7 @@ chain_reads_kernel(const BatchArgs args)
 	if (lane == 0) {
 		if (n_chunks) atomicAdd(&args.counters[0], n_chunks);
 		if (n_general) atomicAdd(&args.counters[1], n_general);
+		if (n_cells) atomicAdd(&args.counters[2], n_cells);
 	}
 }
 
@@ -728,7 +731,7 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 {
 	if (args.n_reads <= 0) return 0;
 	cudaMemsetAsync(args.work_counter, 0, sizeof(int), stream);
-	cudaMemsetAsync(args.counters, 0, 2 * sizeof(unsigned long long), stream);
+	cudaMemsetAsync(args.counters, 0, 4 * sizeof(unsigned long long), stream);
 	int64_t ctas = (args.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const int64_t resident = (int64_t)n_sms * CTAS_PER_SM;
 	if (ctas > resident) ctas = resident;

@@ -139,7 +139,7 @@ struct Job {
 	std::condition_variable cv;
 	int workers_left = 0;
 	// stats
-	std::atomic<int64_t> n_chains{0}, n_chained{0}, cells_issued{0}, n_general{0};
+	std::atomic<int64_t> n_chains{0}, n_chained{0}, cells_issued{0}, cells_ref{0}, n_general{0};
 	double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;   // guarded by mu
 };
 
@@ -220,7 +220,7 @@ bool stage_finish(Slot &s, Job *job)
 		cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]), cudaEventElapsedTime(&ker, s.ev[1], s.ev[2]);
 		cudaEventElapsedTime(&d2h0, s.ev[2], s.ev[3]), cudaEventElapsedTime(&d2h1, s.ev[4], s.ev[5]);
 		mm2b_stats_t st;
-		if (mm2b_ws_stats(s.ws, s.stream, &st) == MM2B_OK) job->cells_issued += st.cells_issued, job->n_general += st.n_general_reads;
+		if (mm2b_ws_stats(s.ws, s.stream, &st) == MM2B_OK) job->cells_issued += st.cells_issued, job->cells_ref += st.cells_ref, job->n_general += st.n_general_reads;
 		std::lock_guard<std::mutex> lk(job->mu);
 		job->h2d_ms += h2d, job->kernel_ms += ker, job->d2h_ms += d2h0 + d2h1;
 	}
@@ -420,7 +420,7 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
 	if (stats) {
 		memset(stats, 0, sizeof(*stats));
 		stats->n_reads = n_reads, stats->n_anchors = n_anchors, stats->n_chains = job.n_chains, stats->n_chained = job.n_chained;
-		stats->cells_issued = job.cells_issued, stats->n_general_reads = job.n_general;
+		stats->cells_issued = job.cells_issued, stats->cells_ref = job.cells_ref, stats->n_general_reads = job.n_general;
 		stats->h2d_ms = job.h2d_ms, stats->kernel_ms = job.kernel_ms, stats->d2h_ms = job.d2h_ms;
 	}
 	if (job.failed.load()) { set_error("%s%s", job.err, ""); return MM2B_ERR_CUDA; }

@@ -119,3 +119,19 @@ def test_subbatching_and_order_independence(binding, oracle, monkeypatch):
         assert int(res2["n_u"][k]) == nu and int(res2["n_v"][k]) == nv
         assert np.array_equal(res2["u"][res2["u_off"][k]:res2["u_off"][k] + nu], res["u"][res["u_off"][r]:res["u_off"][r] + nu])
         assert np.array_equal(res2["b"][res2["b_off"][k]:res2["b_off"][k] + nv], res["b"][res["b_off"][r]:res["b_off"][r] + nv])
+
+
+def test_kernel_cell_tally_equals_oracle(binding, oracle, pkg):
+    """GCUPS is quoted on reference-semantics cells; the kernel's own tally of them must equal the instrumented oracle's."""
+    wl = pkg("workload")
+    off, a = wl.synth_anchor_batch(300, seed=11)
+    ref = oracle.replay(oracle.Params(), off, a, n_threads=4)
+    res = binding.chain_batch(binding.Params(), off, a)
+    _compare_batch(res, ref, off, "synth")
+    assert res["stats"].cells_ref == ref["stats"].cells
+    assert res["stats"].cells_issued >= res["stats"].cells_ref
+    off, a = fuzz.mixed_batch(31, n_reads=48)
+    for kw in (dict(), dict(max_skip=2, max_iter=40)):
+        ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=4)
+        res = binding.chain_batch(binding.Params(**kw), off, a)
+        assert res["stats"].cells_ref == ref["stats"].cells, kw
