@@ -3,11 +3,12 @@
 // Design (B200-first, not a translation of the FPGA shift-register kernel or of the CPU loop):
 //   * one WARP per read, persistent CTAs (8 warps, 4 CTAs/SM = 32 warps/SM) pulling reads longest-first from a
 //     global work counter, so 148 SMs x 32 warps chain 4736 reads concurrently;
-//   * anchors stream in 32 at a time with one coalesced 16-byte load per lane; the most recent 256 anchors'
-//     (x_lo, y_lo, f, p, v, t) live in a per-warp shared-memory ring (6 KB), deeper look-back (rare) reads L2;
+//   * anchors stream in 32 at a time with one coalesced 16-byte load per lane; each lane binary-searches its own
+//     anchor's window start, anchors with an empty window are finished in parallel, and the most recent 256 anchors'
+//     {x_lo, y_lo, f, p | v, t} live in a per-warp shared-memory ring (6 KB); deeper look-back (rare) reads L2;
 //   * the inner loop over predecessors j = i-1 .. st is evaluated 32 lanes at a time; the order-dependent parts of
 //     the reference loop (strict '>' running max, t[] stamps, the n_skip counter and its break, chain.c:226-233)
-//     are recovered exactly with a shuffle prefix-max, ballots and a warp-uniform walk over the record mask;
+//     are recovered exactly with a shuffle prefix-max, ballots and a closed-form (Lindley) prefix-min for n_skip;
 //   * chain ends / peaks, the descending sort, the priority backtrack and the final order by reference position
 //     (including the reference's unstable radix-sort tie order) run in the same warp right after the fill while
 //     f/p/v are still in L1/L2; a scan + gather kernel pair then packs u[]/b[] in read order.
@@ -53,27 +54,166 @@ __device__ __forceinline__ int d2i_x86(double d)
 // The saturating skip counter of chain.c:226-232 over one 32-lane chunk, visited in lane order 0,1,2,...:
 //   record lane (sc > running max):  n_skip = max(n_skip-1, 0)
 //   hit lane (t[j]==i, not a record): if (++n_skip > max_skip) break
-// Returns the break lane (32 if the loop does not break in this chunk) and updates n_skip.  All arguments are
-// warp-uniform, so this is scalar work replicated across the warp, except for one ballot that finds the k-th hit.
-__device__ __forceinline__ int skip_walk(unsigned recmask, unsigned hitmask, int &n_skip, int max_skip, int lane)
+// Returns the break lane (32 if the loop does not break in this chunk) and updates n_skip.
+// The counter is a Lindley recursion x_t = max(x_{t-1} + d_t, 0) with d = +1 (hit), -1 (record), 0 (other), whose closed
+// form is x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum_{u<=t} d_u: one popc-based prefix sum and one shuffle
+// prefix-min instead of a serial walk.  Two warp-uniform shortcuts cover most chunks (no hits; no records).
+__device__ __forceinline__ int kth_set_lane(unsigned mask, int k, int lane)     // lane index of the k-th (1-based) set bit
 {
-	int x = n_skip, lo = 0;
-	unsigned rm = recmask;
-	for (;;) {
-		const int r = rm ? __ffs(rm) - 1 : 32;
-		const unsigned seg = hitmask & bits_below(r) & ~bits_below(lo);
-		const int c = __popc(seg);
-		if (x + c > max_skip) {
-			int k = max_skip + 1 - x;
-			if (k < 1) k = 1;
-			const bool mine = ((seg >> lane) & 1u) && __popc(seg & (lanemask_lt(lane) | (1u << lane))) == k;
-			return __ffs(__ballot_sync(FULL, mine)) - 1;
+	const bool mine = ((mask >> lane) & 1u) && __popc(mask & (lanemask_lt(lane) | (1u << lane))) == k;
+	return __ffs(__ballot_sync(FULL, mine)) - 1;
+}
+__device__ __forceinline__ int skip_update(unsigned recmask, unsigned hitmask, int &n_skip, int max_skip, int lane)
+{
+	if (hitmask == 0) {                                       // only decrements: saturating subtraction
+		const int x = n_skip - __popc(recmask);
+		n_skip = x > 0 ? x : 0;
+		return 32;
+	}
+	if (recmask == 0) {                                       // only increments: the break is at the k-th hit
+		const int c = __popc(hitmask);
+		if (n_skip + c <= max_skip) { n_skip += c; return 32; }
+		const int k = max_skip + 1 - n_skip;
+		return kth_set_lane(hitmask, k < 1 ? 1 : k, lane);
+	}
+	const unsigned le = lanemask_lt(lane) | (1u << lane);
+	const int S = n_skip + __popc(hitmask & le) - __popc(recmask & le);
+	int m = S;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int o = __shfl_up_sync(FULL, m, d);             // lanes < d read their own value: min is a no-op
+		m = m < o ? m : o;
+	}
+	const int x = S - (m < 0 ? m : 0);
+	const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > max_skip);
+	if (over) return __ffs(over) - 1;
+	n_skip = __shfl_sync(FULL, x, 31);
+	return 32;
+}
+
+// Per-warp shared-memory ring: the most recent RING anchors, one slot each.
+//   slotA[s] = {x_lo, y_lo, f, p}   read with one 16-byte LDS per lane
+//   slotB[s] = {v, t}               v = peak score on the path (chain.c:237), t = visit stamp (chain.c:229,233)
+struct Ring {
+	int4 *a;
+	int2 *b;
+};
+
+struct DpConst {
+	int max_dist_x, max_dist_y, bw, max_skip, max_iter, max_dq_same;
+	bool cap_dr, is_cdna;
+	float avg;
+	double gap_scale;
+};
+
+// One anchor's scan over its predecessors j = i-1 .. st in 32-lane chunks (chain.c:197-235).
+// DEEP=false: the whole window [st, i) is resident in the ring, so every access is shared memory.
+// DEEP=true : the window reaches below the ring; lanes pick ring or global (L1/L2) per element.
+template <bool GENERAL, bool DEEP>
+__device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo,
+                                                  int32_t xi, int32_t qi, int32_t q_span, int32_t sidi,
+                                                  int32_t &max_f, int32_t &max_j, int32_t &v_best, unsigned &n_chunks, unsigned &n_cells)
+{
+	int n_skip = 0;
+	for (int jt = i - 1; jt >= st; jt -= 32) {
+		++n_chunks;
+		const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
+		const bool act = lane < n_act;
+		const int j = jt - lane;
+		const int s = j & (RING - 1);
+		int32_t xj, yj, fj, pj, vj, sidj = sidi;
+		if (!DEEP) {
+			const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
+			xj = q.x, yj = q.y, fj = q.z, pj = q.w;
+			vj = ring.b[s].x;
+			if (GENERAL) sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
+		} else {
+			xj = 0, yj = 0, fj = 0, pj = -1, vj = 0;
+			if (act) {
+				if (j >= ring_lo) {
+					const int4 q = ring.a[s];
+					xj = q.x, yj = q.y, fj = q.z, pj = q.w;
+					vj = ring.b[s].x;
+					if (GENERAL) sidj = (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff);
+				} else {                                           // deep look-back: L1/L2
+					const ulonglong2 t = __ldg(rc.A + j);
+					xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j], vj = rc.V[j];
+					sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
+				}
+			}
 		}
-		x += c;
-		if (r == 32) { n_skip = x; return 32; }
-		x = x > 0 ? x - 1 : 0;
-		rm &= rm - 1;
-		lo = r + 1;
+		// inside the window 0 <= dr <= max_dist_x, so the low words give dr exactly (chain.c:199)
+		const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)xj);
+		const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)yj);                // chain.c:200
+		const int32_t diff = dr - dq;
+		const int32_t dd = diff < 0 ? -diff : diff;                              // chain.c:204
+		bool valid;
+		int32_t sc;
+		if (!GENERAL) {
+			valid = act && dr != 0 && dq > 0 && dq <= c.max_dq_same && dd <= c.bw && !(c.cap_dr && dr > c.max_dist_y);
+			const int32_t md = dq < dr ? dq : dr;
+			sc = md < q_span ? md : q_span;                                       // chain.c:207-208
+			const int c_lin = __float2int_rz(__fmul_rn(__int2float_rn(dd), c.avg)); // chain.c:218 (dd <= bw: exact, in range)
+			const int lg = 31 - __clz(dd | 1);                                    // ilog2_32(dd), 0 for dd == 0 (chain.c:209)
+			sc = sc - (c_lin + (lg >> 1)) + fj;
+		} else {
+			const bool same = sidi == sidj;
+			valid = act && !((same && dr == 0) || dq <= 0)                        // chain.c:202
+			            && !((same && dq > c.max_dist_y) || dq > c.max_dist_x)     // chain.c:203
+			            && !(same && dd > c.bw)                                    // chain.c:205
+			            && !(c.cap_dr && same && dr > c.max_dist_y);               // chain.c:206
+			const int32_t md = dq < dr ? dq : dr;
+			sc = md > q_span ? q_span : md;
+			const int lg = dd ? 31 - __clz(dd) : 0;
+			int gap = 0;
+			if (c.is_cdna || !same) {                                             // chain.c:211-217
+				const int c_lin = f2i_x86(__fmul_rn(__int2float_rn(dd), c.avg));
+				if (!same && dr == 0) ++sc;
+				else if (dr > dq || !same) gap = c_lin < lg ? c_lin : lg;
+				else gap = c_lin + (lg >> 1);
+			} else gap = f2i_x86(__fmul_rn(__int2float_rn(dd), c.avg)) + (lg >> 1);
+			sc -= d2i_x86(__dadd_rn(__dmul_rn((double)gap, c.gap_scale), .499));  // chain.c:219
+			sc += fj;
+		}
+		if (!valid) sc = INT_MIN;
+		const unsigned vmask = __ballot_sync(FULL, valid);
+		if (vmask == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
+
+		// running max BEFORE each lane (lanes are visited in order 0..31): inclusive prefix max, shifted by one
+		int32_t m = sc;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int32_t o = __shfl_up_sync(FULL, m, d);   // lanes < d get their own value back: max is a no-op
+			m = m > o ? m : o;
+		}
+		int32_t before = __shfl_up_sync(FULL, m, 1);
+		if (lane == 0) before = INT_MIN;
+		if (before < max_f) before = max_f;
+		const bool rec = valid && sc > before;                                    // chain.c:226
+
+		// chain.c:233 — every visited (non-`continue`d) cell stamps its predecessor.  Stamps from lanes past the
+		// break lane are harmless: they carry the value i, which is never compared again once this anchor is done,
+		// and a stamp can only land on a smaller index than the lane that writes it.  Stamps below st are never read.
+		if (valid && pj >= st) {
+			if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i;
+			else rc.T[pj] = i;
+		}
+		__syncwarp();
+		int32_t tj;
+		if (!DEEP) tj = ring.b[s].y;
+		else tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
+		const unsigned recmask = __ballot_sync(FULL, rec);
+		const unsigned hitmask = __ballot_sync(FULL, valid && !rec && tj == i);    // chain.c:229
+		const int brk = skip_update(recmask, hitmask, n_skip, c.max_skip, lane);
+		const unsigned take = recmask & bits_below(brk);
+		if (take) {          // records are strictly increasing, so the last one before the break is the max,
+			const int last = 31 - __clz(take);   // and ties went to the nearest j (strict '>')
+			max_f = __shfl_sync(FULL, sc, last);
+			v_best = __shfl_sync(FULL, vj, last);
+			max_j = jt - last;
+		}
+		n_cells += brk < 32 ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
+		if (brk < 32) break;                                                      // chain.c:230-231
 	}
 }
 
@@ -81,159 +221,88 @@ __device__ __forceinline__ int skip_walk(unsigned recmask, unsigned hitmask, int
 // DP fill: f[], p[], v[] for one read (chain.c:184-238).  GENERAL=false is the map-ont / asm20 shape
 // (one segment id, !is_cdna, gap_scale == 1) with a pure-integer + one float-multiply cost; GENERAL=true carries
 // the full cost switch of chain.c:211-219 (cross-segment, cDNA, gap_scale in double).
+//
+// Anchors are taken 32 at a time.  For a block, every lane first finds its own anchor's window start st (chain.c:192-193)
+// by binary search — st_i = max(lower_bound{s : x_s + max_dist_x >= x_i}, i - max_iter) since the input is sorted by x —
+// and publishes {x_lo, y_lo, f = q_span, p = -1, v = q_span, t = -1} to the ring.  Anchors whose window is empty
+// (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool GENERAL>
-__device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, int32_t *ring, int lane,
-                        unsigned long long &n_chunks, unsigned long long &n_cells, int32_t *dbg_fpv, int64_t dbg_stride, int64_t dbg_off)
+__device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, int32_t *smem, int lane,
+                        unsigned long long &n_chunks64, unsigned long long &n_cells64)
 {
-	int32_t *rx = ring, *ry = ring + RING, *rf = ring + 2 * RING, *rp = ring + 3 * RING, *rv = ring + 4 * RING, *rt = ring + 5 * RING;
+	Ring ring;
+	ring.a = (int4*)smem, ring.b = (int2*)(smem + 4 * RING);
 	const ulonglong2 *A = rc.A;
 	const int n = rc.n;
-	const int max_dist_x = par.max_dist_x, max_dist_y = par.max_dist_y, bw = par.bw, max_skip = par.max_skip, max_iter = par.max_iter;
-	const int max_dq_same = max_dist_x < max_dist_y ? max_dist_x : max_dist_y;          // chain.c:203, same segment
-	const bool cap_dr = par.n_segs > 1 && !par.is_cdna;                                 // chain.c:206
-	const uint64_t win = (uint64_t)(int64_t)max_dist_x;
-	const double gap_scale = (double)par.gap_scale;
-	int st = 0;
+	DpConst c;
+	c.max_dist_x = par.max_dist_x, c.max_dist_y = par.max_dist_y, c.bw = par.bw, c.max_skip = par.max_skip, c.max_iter = par.max_iter;
+	c.max_dq_same = par.max_dist_x < par.max_dist_y ? par.max_dist_x : par.max_dist_y;   // chain.c:203, same segment
+	c.cap_dr = par.n_segs > 1 && !par.is_cdna;                                           // chain.c:206
+	c.is_cdna = par.is_cdna != 0, c.avg = avg, c.gap_scale = (double)par.gap_scale;
+	const uint64_t win = (uint64_t)(int64_t)par.max_dist_x;
+	unsigned n_chunks = 0, n_cells = 0;
+	int st_carry = 0;           // window start of the previous block's last anchor (window starts never move backwards)
 
 	for (int base = 0; base < n; base += 32) {
 		const int k = base + lane;
+		const bool in = k < n;
 		uint64_t x = 0, y = 0;
-		if (k < n) {
+		if (in) {
 			const ulonglong2 t = __ldg(A + k);
 			x = t.x, y = t.y;
-			const int s = k & (RING - 1);
-			rx[s] = (int32_t)x, ry[s] = (int32_t)y, rt[s] = -1;
 		}
+		// chain.c:192: first s in [st_carry, k] with !(x > a[s].x + max_dist_x); full 64-bit compare (strand/rid are in the high word)
+		int lo = st_carry, hi = in ? k : st_carry;
+		while (__any_sync(FULL, lo < hi)) {
+			const int mid = (lo + hi) >> 1;
+			if (lo < hi) {
+				if (x > __ldg(&A[mid].x) + win) lo = mid + 1;
+				else hi = mid;
+			}
+		}
+		int st_k = lo;
+		if (k - st_k > c.max_iter) st_k = k - c.max_iter;                                // chain.c:193
+		const int32_t xlo = (int32_t)x, ylo = (int32_t)y;
+		const int32_t meta = (int32_t)(y >> 32 & 0xff) | (int32_t)(y >> SEG_SHIFT & 0xff) << 8;
+		if (in) {
+			const int s = k & (RING - 1);
+			const int32_t q_span = meta & 0xff;
+			ring.a[s] = make_int4(xlo, ylo, q_span, -1);
+			ring.b[s] = make_int2(q_span, -1);
+		}
+		unsigned todo = __ballot_sync(FULL, in && st_k < k);
+		st_carry = __shfl_sync(FULL, st_k, (n - base < 32 ? n - base : 32) - 1);
 		__syncwarp();
 		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
-		const int cnt = n - base < 32 ? n - base : 32;
 
-		for (int ii = 0; ii < cnt; ++ii) {
+		while (todo) {
+			const int ii = __ffs(todo) - 1;
+			todo &= todo - 1;
 			const int i = base + ii;
-			const uint64_t ri = __shfl_sync(FULL, x, ii);
-			const uint64_t yi = __shfl_sync(FULL, y, ii);
-			const int32_t xi = (int32_t)ri, qi = (int32_t)yi, q_span = (int32_t)(yi >> 32 & 0xff);
-			const int32_t sidi = (int32_t)(yi >> SEG_SHIFT & 0xff);
-
-			// chain.c:192 — slide the window start; full 64-bit compare (strand/rid live in the high word of x)
-			for (;;) {
-				const int s = st + lane;
-				bool out = false;
-				if (s < i) out = ri > __ldg(&A[s].x) + win;
-				const unsigned m = __ballot_sync(FULL, out);
-				if (m == FULL) { st += 32; continue; }
-				st += __ffs(~m) - 1;
-				break;
-			}
-			if (i - st > max_iter) st = i - max_iter;                                    // chain.c:193
-
+			const int32_t xi = __shfl_sync(FULL, xlo, ii), qi = __shfl_sync(FULL, ylo, ii), mi = __shfl_sync(FULL, meta, ii);
+			const int st = __shfl_sync(FULL, st_k, ii);
+			const int32_t q_span = mi & 0xff, sidi = mi >> 8;
 			int32_t max_f = q_span, max_j = -1, v_best = 0;
-			int n_skip = 0;
-			for (int jt = i - 1; jt >= st; jt -= 32) {
-				++n_chunks;
-				const int j = jt - lane;
-				const bool act = j >= st;
-				int32_t xj = 0, yj = 0, fj = 0, pj = -1, vj = 0, sidj = sidi;
-				if (act) {
-					if (j >= ring_lo) {
-						const int s = j & (RING - 1);
-						xj = rx[s], yj = ry[s], fj = rf[s], pj = rp[s], vj = rv[s];
-						if (GENERAL) sidj = (int32_t)(__ldg(&A[j].y) >> SEG_SHIFT & 0xff);
-					} else {                                                             // deep look-back: L1/L2
-						const ulonglong2 t = __ldg(A + j);
-						xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j], vj = rc.V[j];
-						sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
-					}
-				}
-				// inside the window 0 <= dr <= max_dist_x, so the low words give dr exactly (chain.c:199)
-				const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)xj);
-				const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)yj);                // chain.c:200
-				const int32_t diff = dr - dq;
-				const int32_t dd = diff < 0 ? -diff : diff;                              // chain.c:204
-				bool valid;
-				int32_t sc;
-				if (!GENERAL) {
-					valid = act && dr != 0 && dq > 0 && dq <= max_dq_same && dd <= bw && !(cap_dr && dr > max_dist_y);
-					const int32_t md = dq < dr ? dq : dr;
-					sc = md < q_span ? md : q_span;                                       // chain.c:207-208
-					const int c_lin = __float2int_rz(__fmul_rn(__int2float_rn(dd), avg)); // chain.c:218 (dd <= bw: exact, in range)
-					const int lg = 31 - __clz(dd | 1);                                    // ilog2_32(dd), 0 for dd == 0 (chain.c:209)
-					sc = sc - (c_lin + (lg >> 1)) + fj;
-				} else {
-					const bool same = sidi == sidj;
-					valid = act && !((same && dr == 0) || dq <= 0)                        // chain.c:202
-					            && !((same && dq > max_dist_y) || dq > max_dist_x)         // chain.c:203
-					            && !(same && dd > bw)                                      // chain.c:205
-					            && !(cap_dr && same && dr > max_dist_y);                   // chain.c:206
-					const int32_t md = dq < dr ? dq : dr;
-					sc = md > q_span ? q_span : md;
-					const int lg = dd ? 31 - __clz(dd) : 0;
-					int gap = 0;
-					if (par.is_cdna || !same) {                                           // chain.c:211-217
-						const int c_lin = f2i_x86(__fmul_rn(__int2float_rn(dd), avg));
-						if (!same && dr == 0) ++sc;
-						else if (dr > dq || !same) gap = c_lin < lg ? c_lin : lg;
-						else gap = c_lin + (lg >> 1);
-					} else gap = f2i_x86(__fmul_rn(__int2float_rn(dd), avg)) + (lg >> 1);
-					sc -= d2i_x86(__dadd_rn(__dmul_rn((double)gap, gap_scale), .499));    // chain.c:219
-					sc += fj;
-				}
-				if (!valid) sc = INT_MIN;
-				const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
-				const unsigned vmask = __ballot_sync(FULL, valid);
-				if (vmask == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
-
-				// running max BEFORE each lane (lanes are visited in order 0..31): inclusive prefix max, shifted by one
-				int32_t m = sc;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					const int32_t o = __shfl_up_sync(FULL, m, d);   // lanes < d get their own value back: max is a no-op
-					m = m > o ? m : o;
-				}
-				int32_t before = __shfl_up_sync(FULL, m, 1);
-				if (lane == 0) before = INT_MIN;
-				if (before < max_f) before = max_f;
-				const bool rec = valid && sc > before;                                    // chain.c:226
-
-				// chain.c:233 — every visited (non-`continue`d) cell stamps its predecessor.  Stamps from lanes past the
-				// break lane are harmless: they carry the value i, which is never compared again once this anchor is done,
-				// and a stamp can only land on a smaller index than the lane that writes it.
-				if (valid && pj >= st) {
-					if (pj >= ring_lo) rt[pj & (RING - 1)] = i;
-					else rc.T[pj] = i;
+			if (st >= ring_lo) scan_predecessors<GENERAL, false>(c, rc, ring, lane, i, st, ring_lo, xi, qi, q_span, sidi, max_f, max_j, v_best, n_chunks, n_cells);
+			else scan_predecessors<GENERAL, true>(c, rc, ring, lane, i, st, ring_lo, xi, qi, q_span, sidi, max_f, max_j, v_best, n_chunks, n_cells);
+			if (max_j >= 0) {
+				if (lane == 0) {
+					const int s = i & (RING - 1);
+					*(int2*)&ring.a[s].z = make_int2(max_f, max_j);
+					ring.b[s].x = v_best > max_f ? v_best : max_f;                         // chain.c:237
 				}
 				__syncwarp();
-				int32_t tj = -1;
-				if (valid && !rec) tj = j >= ring_lo ? rt[j & (RING - 1)] : rc.T[j];
-				const unsigned recmask = __ballot_sync(FULL, rec);
-				const unsigned hitmask = __ballot_sync(FULL, tj == i);                     // chain.c:229
-				const int brk = skip_walk(recmask, hitmask, n_skip, max_skip, lane);
-				const unsigned take = recmask & bits_below(brk);
-				if (take) {          // records are strictly increasing, so the last one before the break is the max,
-					const int last = 31 - __clz(take);   // and ties went to the nearest j (strict '>')
-					max_f = __shfl_sync(FULL, sc, last);
-					v_best = __shfl_sync(FULL, vj, last);
-					max_j = jt - last;
-				}
-				n_cells += brk < 32 ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
-				if (brk < 32) break;                                                      // chain.c:230-231
 			}
-			if (lane == 0) {
-				const int s = i & (RING - 1);
-				rf[s] = max_f, rp[s] = max_j;
-				rv[s] = (max_j >= 0 && v_best > max_f) ? v_best : max_f;                  // chain.c:237
-			}
-			__syncwarp();
 		}
-		if (k < n) {             // one coalesced write of the block's f/p/v (needed by deep look-back and by the backtrack)
+		if (in) {                // one coalesced write of the block's f/p/v (needed by deep look-back and by the backtrack)
 			const int s = k & (RING - 1);
-			const int32_t f = rf[s], p = rp[s], v = rv[s];
-			rc.F[k] = f, rc.P[k] = p, rc.V[k] = v;
-			if (dbg_fpv) {
-				dbg_fpv[dbg_off + k] = f, dbg_fpv[dbg_stride + dbg_off + k] = p, dbg_fpv[2 * dbg_stride + dbg_off + k] = v;
-			}
+			const int2 fp = *(const int2*)&ring.a[s].z;
+			const int32_t v = ring.b[s].x;
+			rc.F[k] = fp.x, rc.P[k] = fp.y, rc.V[k] = v;
 		}
+		n_chunks64 += n_chunks, n_cells64 += n_cells;
+		n_chunks = 0, n_cells = 0;
 	}
 	__syncwarp();
 }
@@ -505,7 +574,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 chain_reads_kernel(const BatchArgs args)
 {
-	__shared__ int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * RING];
+	__shared__ __align__(16) int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * RING];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int32_t *ring = smem_ring[warp];
 	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0;
@@ -551,9 +620,14 @@ chain_reads_kernel(const BatchArgs args)
 		__syncwarp();
 		if (general) {
 			++n_general;
-			dp_fill<true>(args.par, rc, avg, ring, lane, n_chunks, n_cells, args.dbg_fpv, args.n_anchors, o);
+			dp_fill<true>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
 		} else {
-			dp_fill<false>(args.par, rc, avg, ring, lane, n_chunks, n_cells, args.dbg_fpv, args.n_anchors, o);
+			dp_fill<false>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
+		}
+		if (args.dbg_fpv) {      // test hook (MM2B_KEEP_FPV=1): keep f/p/v as they are at chain.c:238, before the extraction reuses v
+			int32_t *d = args.dbg_fpv + o;
+			for (int k = lane; k < rc.n; k += 32) d[k] = rc.F[k], d[args.n_anchors + k] = rc.P[k], d[2 * args.n_anchors + k] = rc.V[k];
+			__syncwarp();
 		}
 		int n_u = 0, n_v = 0, status = MM2B_READ_OK;
 		extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
