@@ -51,17 +51,20 @@ __device__ __forceinline__ int d2i_x86(double d)
 	return (d >= -2147483648.0 && d < 2147483648.0) ? __double2int_rz(d) : INT_MIN;
 }
 
+// Lowest set bit of a non-zero mask as a lane index.
+__device__ __forceinline__ int lowest_lane(unsigned m) { return __popc((m - 1u) & ~m); }
+
 // The saturating skip counter of chain.c:226-232 over one 32-lane chunk, visited in lane order 0,1,2,...:
 //   record lane (sc > running max):  n_skip = max(n_skip-1, 0)
 //   hit lane (t[j]==i, not a record): if (++n_skip > max_skip) break
 // Returns the break lane (32 if the loop does not break in this chunk) and updates n_skip.
 // The counter is a Lindley recursion x_t = max(x_{t-1} + d_t, 0) with d = +1 (hit), -1 (record), 0 (other), whose closed
-// form is x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum_{u<=t} d_u: one popc-based prefix sum and one shuffle
-// prefix-min instead of a serial walk.  Two warp-uniform shortcuts cover most chunks (no hits; no records).
+// form is x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum_{u<=t} d_u.  S only decreases at records, so the running
+// minimum is a minimum over the (few) record lanes: a warp-uniform loop over the record mask, no shuffles.
 __device__ __forceinline__ int kth_set_lane(unsigned mask, int k, int lane)     // lane index of the k-th (1-based) set bit
 {
 	const bool mine = ((mask >> lane) & 1u) && __popc(mask & (lanemask_lt(lane) | (1u << lane))) == k;
-	return __ffs(__ballot_sync(FULL, mine)) - 1;
+	return lowest_lane(__ballot_sync(FULL, mine));
 }
 __device__ __forceinline__ int skip_update(unsigned recmask, unsigned hitmask, int &n_skip, int max_skip, int lane)
 {
@@ -76,18 +79,18 @@ __device__ __forceinline__ int skip_update(unsigned recmask, unsigned hitmask, i
 		const int k = max_skip + 1 - n_skip;
 		return kth_set_lane(hitmask, k < 1 ? 1 : k, lane);
 	}
-	const unsigned le = lanemask_lt(lane) | (1u << lane);
-	const int S = n_skip + __popc(hitmask & le) - __popc(recmask & le);
-	int m = S;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const int o = __shfl_up_sync(FULL, m, d);             // lanes < d read their own value: min is a no-op
-		m = m < o ? m : o;
+	int corr = 0, floor_all = 0, done = 0;                    // corr: min(0, min S over records at or before this lane)
+	for (unsigned rm = recmask; rm; rm &= rm - 1) {
+		const unsigned below = (rm - 1u) & ~rm;               // lanes before this record
+		const int S_r = n_skip + __popc(hitmask & below) - (++done);
+		floor_all = S_r < floor_all ? S_r : floor_all;
+		if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;   // this lane is at or after the record
 	}
-	const int x = S - (m < 0 ? m : 0);
+	const unsigned le = lanemask_lt(lane) | (1u << lane);
+	const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
 	const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > max_skip);
-	if (over) return __ffs(over) - 1;
-	n_skip = __shfl_sync(FULL, x, 31);
+	if (over) return lowest_lane(over);
+	n_skip = n_skip + __popc(hitmask) - done - floor_all;
 	return 32;
 }
 
@@ -153,8 +156,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			valid = act && dr != 0 && dq > 0 && dq <= c.max_dq_same && dd <= c.bw && !(c.cap_dr && dr > c.max_dist_y);
 			const int32_t md = dq < dr ? dq : dr;
 			sc = md < q_span ? md : q_span;                                       // chain.c:207-208
-			const int c_lin = __float2int_rz(__fmul_rn(__int2float_rn(dd), c.avg)); // chain.c:218 (dd <= bw: exact, in range)
-			const int lg = 31 - __clz(dd | 1);                                    // ilog2_32(dd), 0 for dd == 0 (chain.c:209)
+			const float fdd = __int2float_rn(dd);                                 // exact: dd <= bw < 2^24 on this path
+			const int c_lin = __float2int_rz(__fmul_rn(fdd, c.avg));              // chain.c:218
+			int lg = (__float_as_int(fdd) >> 23) - 127;                           // ilog2_32(dd) read off the float exponent (chain.c:209) ...
+			lg = lg < 0 ? 0 : lg;                                                 // ... and 0 for dd == 0
 			sc = sc - (c_lin + (lg >> 1)) + fj;
 		} else {
 			const bool same = sidi == sidj;
@@ -179,17 +184,20 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		const unsigned vmask = __ballot_sync(FULL, valid);
 		if (vmask == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
 
-		// running max BEFORE each lane (lanes are visited in order 0..31): inclusive prefix max, shifted by one
-		int32_t m = sc;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const int32_t o = __shfl_up_sync(FULL, m, d);   // lanes < d get their own value back: max is a no-op
-			m = m > o ? m : o;
+		// Records (chain.c:226): lanes, in visiting order 0..31, whose score beats everything seen before them.  The first
+		// lane above max_f is one; each further record is the first later lane above the previous record's score.  Chunks
+		// hold 0-2 records in practice, so this warp-uniform loop is cheaper than a 5-step shuffle prefix-max.
+		unsigned recmask = 0;
+		{
+			unsigned cand = __ballot_sync(FULL, sc > max_f);     // invalid lanes carry INT_MIN
+			while (cand) {
+				const int r = lowest_lane(cand);
+				recmask |= 1u << r;
+				const int32_t top = __shfl_sync(FULL, sc, r);
+				cand = __ballot_sync(FULL, sc > top) & ~bits_below(r + 1);
+			}
 		}
-		int32_t before = __shfl_up_sync(FULL, m, 1);
-		if (lane == 0) before = INT_MIN;
-		if (before < max_f) before = max_f;
-		const bool rec = valid && sc > before;                                    // chain.c:226
+		const bool rec = (recmask >> lane) & 1u;
 
 		// chain.c:233 — every visited (non-`continue`d) cell stamps its predecessor.  Stamps from lanes past the
 		// break lane are harmless: they carry the value i, which is never compared again once this anchor is done,
@@ -202,7 +210,6 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		int32_t tj;
 		if (!DEEP) tj = ring.b[s].y;
 		else tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
-		const unsigned recmask = __ballot_sync(FULL, rec);
 		const unsigned hitmask = __ballot_sync(FULL, valid && !rec && tj == i);    // chain.c:229
 		const int brk = skip_update(recmask, hitmask, n_skip, c.max_skip, lane);
 		const unsigned take = recmask & bits_below(brk);
