@@ -126,9 +126,11 @@ double mm2b_measure_int32_peak(int device);
 /* Drop-in for chain.c:29.  Takes ownership of `a` (kfree(km, a) on every path); returns b and *_u allocated with
  * kmalloc(km, ...).  Re-entrant; called concurrently from the kt_for worker threads (map.c:561).  Initialises the backend
  * on first use if mm2b_init was not called.  Fatal CUDA errors print to stderr and exit(1), as checkError does. */
+#ifndef MM2B_HOST_DECLARES_MM_CHAIN_DP   /* hosts that include mmpriv.h already have the prototype (with mm128_t) */
 mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
                            float gap_scale, int is_cdna, int n_segs, int64_t n, mm2b_anchor_t *a, int *n_u_, uint64_t **_u,
                            void *km, int tid);
+#endif
 
 #ifdef __cplusplus
 }

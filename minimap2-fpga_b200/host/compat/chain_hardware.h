@@ -1,0 +1,47 @@
+/* Replacement for the reference's chain_hardware.h (/root/reference/chain_hardware.h:1-75) when minimap2 is built against
+ * the B200 backend instead of the OpenCL/FPGA one.  The three host files that include it keep compiling unchanged:
+ *
+ *   main.c:367   if (!hardware_init(BUFFER_N, XCLBIN_FILE)) return -1;     -> mm2b_init()      (CUDA devices, streams, workers)
+ *   main.c:430   cleanup();                                                -> mm2b_shutdown()
+ *   options.c:95-99,118-122   K1_HW = ONT_K1_HW; ...                       -> the learned HW/SW split is gone: constants are 0
+ *   chain.c      is NOT compiled; mm_chain_dp comes from libmm2chain_b200 (same signature, mmpriv.h:65)
+ *
+ * Like the original, this header is C++ (the reference compiles every .c with $(CXX), Makefile:184-185).
+ */
+#ifndef MM2B_COMPAT_CHAIN_HARDWARE_H
+#define MM2B_COMPAT_CHAIN_HARDWARE_H
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "minimap.h"
+#define MM2B_HOST_DECLARES_MM_CHAIN_DP     /* mmpriv.h:65 declares it with mm128_t; same C symbol */
+#include "mm2chain_b200.h"
+
+/* learned HW/SW split (chain_hardware.h:18-30): removed — every read is chained on the GPU */
+#define ONT_K1_HW 0.0f
+#define ONT_K2_HW 0.0f
+#define ONT_C_HW 0.0f
+#define ONT_K_SW 0.0f
+#define ONT_C_SW 0.0f
+#define PBCCS_K1_HW 0.0f
+#define PBCCS_K2_HW 0.0f
+#define PBCCS_C_HW 0.0f
+#define PBCCS_K_SW 0.0f
+#define PBCCS_C_SW 0.0f
+
+#define XCLBIN_FILE ((char*)"")    /* no bitstream: kernels are compiled into the library */
+#define BUFFER_N 0                 /* no fixed device buffer: workspaces grow with the largest read seen */
+
+static inline bool hardware_init(long buf_size, char *binary_name)
+{
+	(void)buf_size; (void)binary_name;
+	if (mm2b_init(0, 0) != MM2B_OK) {
+		fprintf(stderr, "[ERROR] B200 chaining backend: %s\n", mm2b_last_error());
+		return false;
+	}
+	return true;
+}
+static inline void cleanup(void) { mm2b_shutdown(); }
+
+#endif
