@@ -2,7 +2,7 @@
  *
  * CPU restatement of the reference's *software* chaining, the parity target for the CUDA path:
  * minimap2 v2.18 mm_chain_dp (/root/reference/chain.c:29-423) with ENABLE_MAX_SKIP_ON_SW and
- * the HW/SW predictor removed.  Parity status: PINNED — tests/test_oracle_vs_reference.py checks
+ * the HW/SW predictor removed.  Parity status: PINNED — tests/test_oracle.py checks
  * this file against the reference's own compiled chain.c (oracle/_ref/libmm2ref.so, built in place
  * from /root/reference by oracle/Makefile) and against tests/golden/ fixtures captured from the
  * reference CLI (f/p/v per anchor, u[] and b[] per read).  The reference tree itself stores no
