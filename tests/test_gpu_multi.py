@@ -1,0 +1,73 @@
+"""GPU test of the host backend's sub-batch pipeline and device sharding: many small sub-batches (MM2B_SUB_ANCHORS) pulled by
+one worker thread per visible device, three slots in flight each, results gathered in input order.  With one GPU this
+exercises the pipeline; with several (gpurun --gpus N) it also exercises read sharding across devices."""
+import os
+
+import numpy as np
+import pytest
+
+import fuzz
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def binding(pkg):
+    b = pkg("binding")
+    L = b.load()
+    assert L.mm2b_cuda_device_count() > 0
+    os.environ["MM2B_SUB_ANCHORS"] = "20000"
+    b.init()                       # all visible devices
+    yield b
+    b.shutdown()
+    os.environ.pop("MM2B_SUB_ANCHORS", None)
+
+
+def test_many_subbatches_all_devices(binding, oracle, pkg):
+    wl = pkg("workload")
+    n_dev = binding.load().mm2b_num_devices()
+    assert n_dev >= 1
+    off, a = wl.synth_anchor_batch(1500, seed=5)
+    assert len(a) > 30 * 20000          # dozens of sub-batches
+    ref = oracle.replay(oracle.Params(), off, a, n_threads=8)
+    for _ in range(2):                  # second call reuses grown slots
+        res = binding.chain_batch(binding.Params(), off, a)
+        assert np.array_equal(res["n_u"], ref["n_u"]) and np.array_equal(res["n_v"], ref["n_v"].astype(np.int32))
+        for r in range(len(off) - 1):
+            o, nu, nv = int(off[r]), int(ref["n_u"][r]), int(ref["n_v"][r])
+            assert np.array_equal(res["u"][res["u_off"][r]:res["u_off"][r] + nu], ref["u"][o:o + nu]), r
+            assert np.array_equal(res["b"][res["b_off"][r]:res["b_off"][r] + nv], ref["b"][o:o + nv]), r
+        assert res["stats"].cells_ref == ref["stats"].cells
+
+
+def test_concurrent_callers(binding, oracle):
+    """mm2b_chain_batch and mm_chain_dp are thread-safe: several host threads at once (ctypes releases the GIL)."""
+    import threading
+    off, a = fuzz.mixed_batch(9, n_reads=60, scale=0.5)
+    ref = oracle.replay(oracle.Params(), off, a, n_threads=4)
+    errs = []
+
+    def batch_caller():
+        try:
+            res = binding.chain_batch(binding.Params(), off, a)
+            assert np.array_equal(res["n_u"], ref["n_u"])
+            assert res["stats"].n_chained == int(ref["n_v"].sum())
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    def read_caller(lo, hi):
+        try:
+            for r in range(lo, hi):
+                u, b, _, _ = binding.chain_read(binding.Params(), a[off[r]:off[r + 1]])
+                o, nu, nv = int(off[r]), int(ref["n_u"][r]), int(ref["n_v"][r])
+                assert np.array_equal(u, ref["u"][o:o + nu]) and np.array_equal(b, ref["b"][o:o + nv]), r
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=batch_caller) for _ in range(3)] + \
+         [threading.Thread(target=read_caller, args=(k * 15, k * 15 + 15)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
