@@ -54,49 +54,11 @@ __device__ __forceinline__ int d2i_x86(double d)
 // Lowest set bit of a non-zero mask as a lane index.
 __device__ __forceinline__ int lowest_lane(unsigned m) { return __popc((m - 1u) & ~m); }
 
-// The saturating skip counter of chain.c:226-232 over one 32-lane chunk, visited in lane order 0,1,2,...:
-//   record lane (sc > running max):  n_skip = max(n_skip-1, 0)
-//   hit lane (t[j]==i, not a record): if (++n_skip > max_skip) break
-// Returns the break lane (32 if the loop does not break in this chunk) and updates n_skip.
-// The counter is a Lindley recursion x_t = max(x_{t-1} + d_t, 0) with d = +1 (hit), -1 (record), 0 (other), whose closed
-// form is x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum_{u<=t} d_u.  S only decreases at records, so the running
-// minimum is a minimum over the (few) record lanes: a warp-uniform loop over the record mask, no shuffles.
-__device__ __forceinline__ int kth_set_lane(unsigned mask, int k, int lane)     // lane index of the k-th (1-based) set bit
-{
-	const bool mine = ((mask >> lane) & 1u) && __popc(mask & (lanemask_lt(lane) | (1u << lane))) == k;
-	return lowest_lane(__ballot_sync(FULL, mine));
-}
-__device__ __forceinline__ int skip_update(unsigned recmask, unsigned hitmask, int &n_skip, int max_skip, int lane)
-{
-	if (hitmask == 0) {                                       // only decrements: saturating subtraction
-		const int x = n_skip - __popc(recmask);
-		n_skip = x > 0 ? x : 0;
-		return 32;
-	}
-	if (recmask == 0) {                                       // only increments: the break is at the k-th hit
-		const int c = __popc(hitmask);
-		if (n_skip + c <= max_skip) { n_skip += c; return 32; }
-		const int k = max_skip + 1 - n_skip;
-		return kth_set_lane(hitmask, k < 1 ? 1 : k, lane);
-	}
-	int corr = 0, floor_all = 0, done = 0;                    // corr: min(0, min S over records at or before this lane)
-	for (unsigned rm = recmask; rm; rm &= rm - 1) {
-		const unsigned below = (rm - 1u) & ~rm;               // lanes before this record
-		const int S_r = n_skip + __popc(hitmask & below) - (++done);
-		floor_all = S_r < floor_all ? S_r : floor_all;
-		if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;   // this lane is at or after the record
-	}
-	const unsigned le = lanemask_lt(lane) | (1u << lane);
-	const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
-	const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > max_skip);
-	if (over) return lowest_lane(over);
-	n_skip = n_skip + __popc(hitmask) - done - floor_all;
-	return 32;
-}
-
 // Per-warp shared-memory ring: the most recent RING anchors, one slot each.
-//   slotA[s] = {x_lo, y_lo, f, p}   read with one 16-byte LDS per lane
-//   slotB[s] = {v, t}               v = peak score on the path (chain.c:237), t = visit stamp (chain.c:229,233)
+//   slotA[s] = {x_lo, y_lo, f, p}   one 16-byte LDS fetches a predecessor
+//   slotB[s] = {v, t}               v = peak score on the path (chain.c:237); t = visit stamp (chain.c:229,233).  Until its
+//                                   anchor is processed, t holds that anchor's window start st (< its index, so it can
+//                                   never equal a later stamp) — the sequential step reads it back with a broadcast LDS.
 struct Ring {
 	int4 *a;
 	int2 *b;
@@ -109,13 +71,24 @@ struct DpConst {
 	double gap_scale;
 };
 
-// One anchor's scan over its predecessors j = i-1 .. st in 32-lane chunks (chain.c:197-235).
+// One anchor's scan over its predecessors j = i-1 .. st in 32-lane chunks, nearest first (chain.c:197-235).
 // DEEP=false: the whole window [st, i) is resident in the ring, so every access is shared memory.
 // DEEP=true : the window reaches below the ring; lanes pick ring or global (L1/L2) per element.
+//
+// The order-dependent parts of the reference loop are recovered exactly from warp votes:
+//  * records (chain.c:226, strict '>' running max): the first lane above max_f, then the first later lane above that, ...
+//    — chunks hold 0-2 records in practice, so a warp-uniform loop beats a 5-step shuffle prefix-max;
+//  * stamps (chain.c:233): every visited cell writes t[p[j]] = i, then all lanes read t[j] back.  A stamp only lands on an
+//    index smaller than its writer's, so "all write, then all read" is order-safe; stamps from lanes past the break carry
+//    a value (i) that is never compared again; stamps below st are never read;
+//  * n_skip (chain.c:228-231) is a Lindley recursion x_t = max(x_{t-1} + d_t, 0), d = +1 (hit), -1 (record), 0 (other),
+//    with closed form x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum d.  S only drops at records, so the running
+//    minimum is a minimum over the record lanes: scalar work on the two vote masks, no shuffles;
+//  * the loop breaks at the first hit lane with x > max_skip; the new (max_f, max_j) is the last record before it.
 template <bool GENERAL, bool DEEP>
 __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo,
                                                   int32_t xi, int32_t qi, int32_t q_span, int32_t sidi,
-                                                  int32_t &max_f, int32_t &max_j, int32_t &v_best, unsigned &n_chunks, unsigned &n_cells)
+                                                  int32_t &max_f, int32_t &max_j, unsigned &n_chunks, unsigned &n_cells)
 {
 	int n_skip = 0;
 	for (int jt = i - 1; jt >= st; jt -= 32) {
@@ -124,23 +97,21 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		const bool act = lane < n_act;
 		const int j = jt - lane;
 		const int s = j & (RING - 1);
-		int32_t xj, yj, fj, pj, vj, sidj = sidi;
+		int32_t xj, yj, fj, pj, sidj = sidi;
 		if (!DEEP) {
 			const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
 			xj = q.x, yj = q.y, fj = q.z, pj = q.w;
-			vj = ring.b[s].x;
 			if (GENERAL) sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
 		} else {
-			xj = 0, yj = 0, fj = 0, pj = -1, vj = 0;
+			xj = 0, yj = 0, fj = 0, pj = -1;
 			if (act) {
 				if (j >= ring_lo) {
 					const int4 q = ring.a[s];
 					xj = q.x, yj = q.y, fj = q.z, pj = q.w;
-					vj = ring.b[s].x;
 					if (GENERAL) sidj = (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff);
 				} else {                                           // deep look-back: L1/L2
 					const ulonglong2 t = __ldg(rc.A + j);
-					xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j], vj = rc.V[j];
+					xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j];
 					sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
 				}
 			}
@@ -153,7 +124,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		bool valid;
 		int32_t sc;
 		if (!GENERAL) {
-			valid = act && dr != 0 && dq > 0 && dq <= c.max_dq_same && dd <= c.bw && !(c.cap_dr && dr > c.max_dist_y);
+			valid = act && dr != 0 && (uint32_t)(dq - 1) < (uint32_t)c.max_dq_same && dd <= c.bw;   // chain.c:202-205
 			const int32_t md = dq < dr ? dq : dr;
 			sc = md < q_span ? md : q_span;                                       // chain.c:207-208
 			const float fdd = __int2float_rn(dd);                                 // exact: dd <= bw < 2^24 on this path
@@ -181,27 +152,22 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			sc += fj;
 		}
 		if (!valid) sc = INT_MIN;
-		const unsigned vmask = __ballot_sync(FULL, valid);
-		if (vmask == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
 
-		// Records (chain.c:226): lanes, in visiting order 0..31, whose score beats everything seen before them.  The first
-		// lane above max_f is one; each further record is the first later lane above the previous record's score.  Chunks
-		// hold 0-2 records in practice, so this warp-uniform loop is cheaper than a 5-step shuffle prefix-max.
-		unsigned recmask = 0;
-		{
-			unsigned cand = __ballot_sync(FULL, sc > max_f);     // invalid lanes carry INT_MIN
-			while (cand) {
-				const int r = lowest_lane(cand);
-				recmask |= 1u << r;
-				const int32_t top = __shfl_sync(FULL, sc, r);
-				cand = __ballot_sync(FULL, sc > top) & ~bits_below(r + 1);
-			}
+		// records
+		unsigned recmask = 0, cand = __ballot_sync(FULL, sc > max_f);
+		int32_t top = max_f;
+		int last = 0;
+		if (cand == 0) {
+			if (__ballot_sync(FULL, valid) == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
+		} else {
+			do {
+				last = lowest_lane(cand);
+				recmask |= 1u << last;
+				top = __shfl_sync(FULL, sc, last);
+				cand = __ballot_sync(FULL, sc > top) & (0xfffffffeu << last);
+			} while (cand);
 		}
-		const bool rec = (recmask >> lane) & 1u;
-
-		// chain.c:233 — every visited (non-`continue`d) cell stamps its predecessor.  Stamps from lanes past the
-		// break lane are harmless: they carry the value i, which is never compared again once this anchor is done,
-		// and a stamp can only land on a smaller index than the lane that writes it.  Stamps below st are never read.
+		// stamps, then hits
 		if (valid && pj >= st) {
 			if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i;
 			else rc.T[pj] = i;
@@ -210,14 +176,55 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		int32_t tj;
 		if (!DEEP) tj = ring.b[s].y;
 		else tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
-		const unsigned hitmask = __ballot_sync(FULL, valid && !rec && tj == i);    // chain.c:229
-		const int brk = skip_update(recmask, hitmask, n_skip, c.max_skip, lane);
-		const unsigned take = recmask & bits_below(brk);
-		if (take) {          // records are strictly increasing, so the last one before the break is the max,
-			const int last = 31 - __clz(take);   // and ties went to the nearest j (strict '>')
-			max_f = __shfl_sync(FULL, sc, last);
-			v_best = __shfl_sync(FULL, vj, last);
-			max_j = jt - last;
+		const unsigned hitmask = __ballot_sync(FULL, valid && tj == i) & ~recmask;   // chain.c:229
+		// n_skip and the break lane
+		int brk = 32;
+		if (hitmask == 0) {                                   // only decrements: saturating subtraction
+			n_skip -= __popc(recmask);
+			n_skip = n_skip > 0 ? n_skip : 0;
+		} else if ((recmask & (recmask - 1u)) == 0) {         // at most one record (the usual case): two runs of hits, scalar
+			const unsigned before = recmask ? (recmask - 1u) : FULL;           // lanes visited before the record
+			const unsigned h1 = hitmask & before, h2 = hitmask & ~before;
+			const int x1 = n_skip + __popc(h1);
+			unsigned run = h1;                                // the run of hits in which the counter first exceeds max_skip
+			int k = c.max_skip + 1 - n_skip;                  // ... at its k-th hit
+			bool brk_here = x1 > c.max_skip;
+			if (!brk_here) {
+				const int x2 = recmask ? (x1 > 0 ? x1 - 1 : 0) : x1;
+				n_skip = x2 + __popc(h2);
+				brk_here = n_skip > c.max_skip;
+				run = h2, k = c.max_skip + 1 - x2;
+			}
+			if (brk_here) {
+				k = k < 1 ? 1 : k;
+				const unsigned le = lanemask_lt(lane) | (1u << lane);
+				brk = lowest_lane(__ballot_sync(FULL, ((run >> lane) & 1u) && __popc(run & le) == k));
+			}
+		} else {
+			int corr = 0, floor_all = 0, done = 0;            // corr: min(0, min S over the records at or before this lane)
+			for (unsigned rm = recmask; rm; rm &= rm - 1) {
+				const unsigned below = (rm - 1u) & ~rm;       // lanes before this record
+				const int S_r = n_skip + __popc(hitmask & below) - (++done);
+				floor_all = S_r < floor_all ? S_r : floor_all;
+				if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
+			}
+			const unsigned le = lanemask_lt(lane) | (1u << lane);
+			const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
+			const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > c.max_skip);
+			if (over) brk = lowest_lane(over);
+			else n_skip = n_skip + __popc(hitmask) - done - floor_all;
+		}
+		// new running max: the last record before the break (records are strictly increasing; ties went to the nearest j)
+		if (recmask) {
+			if (brk > last) max_f = top, max_j = jt - last;
+			else {
+				const unsigned take = recmask & bits_below(brk);
+				if (take) {
+					const int l2 = 31 - __clz(take);
+					max_f = __shfl_sync(FULL, sc, l2);
+					max_j = jt - l2;
+				}
+			}
 		}
 		n_cells += brk < 32 ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
 		if (brk < 32) break;                                                      // chain.c:230-231
@@ -231,7 +238,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 //
 // Anchors are taken 32 at a time.  For a block, every lane first finds its own anchor's window start st (chain.c:192-193)
 // by binary search — st_i = max(lower_bound{s : x_s + max_dist_x >= x_i}, i - max_iter) since the input is sorted by x —
-// and publishes {x_lo, y_lo, f = q_span, p = -1, v = q_span, t = -1} to the ring.  Anchors whose window is empty
+// and publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = st} to the ring.  Anchors whose window is empty
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool GENERAL>
@@ -270,34 +277,38 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 		}
 		int st_k = lo;
 		if (k - st_k > c.max_iter) st_k = k - c.max_iter;                                // chain.c:193
-		const int32_t xlo = (int32_t)x, ylo = (int32_t)y;
-		const int32_t meta = (int32_t)(y >> 32 & 0xff) | (int32_t)(y >> SEG_SHIFT & 0xff) << 8;
+		const int32_t seg = (int32_t)(y >> SEG_SHIFT & 0xff);
 		if (in) {
 			const int s = k & (RING - 1);
-			const int32_t q_span = meta & 0xff;
-			ring.a[s] = make_int4(xlo, ylo, q_span, -1);
-			ring.b[s] = make_int2(q_span, -1);
+			const int32_t q_span = (int32_t)(y >> 32 & 0xff);
+			ring.a[s] = make_int4((int32_t)x, (int32_t)y, q_span, -1);
+			ring.b[s] = make_int2(q_span, st_k);
 		}
 		unsigned todo = __ballot_sync(FULL, in && st_k < k);
+		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
+		const bool deep_block = __any_sync(FULL, in && st_k < ring_lo);    // some window in this block reaches below the ring
 		st_carry = __shfl_sync(FULL, st_k, (n - base < 32 ? n - base : 32) - 1);
 		__syncwarp();
-		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
 
 		while (todo) {
-			const int ii = __ffs(todo) - 1;
+			const int ii = lowest_lane(todo);
 			todo &= todo - 1;
 			const int i = base + ii;
-			const int32_t xi = __shfl_sync(FULL, xlo, ii), qi = __shfl_sync(FULL, ylo, ii), mi = __shfl_sync(FULL, meta, ii);
-			const int st = __shfl_sync(FULL, st_k, ii);
-			const int32_t q_span = mi & 0xff, sidi = mi >> 8;
-			int32_t max_f = q_span, max_j = -1, v_best = 0;
-			if (st >= ring_lo) scan_predecessors<GENERAL, false>(c, rc, ring, lane, i, st, ring_lo, xi, qi, q_span, sidi, max_f, max_j, v_best, n_chunks, n_cells);
-			else scan_predecessors<GENERAL, true>(c, rc, ring, lane, i, st, ring_lo, xi, qi, q_span, sidi, max_f, max_j, v_best, n_chunks, n_cells);
-			if (max_j >= 0) {
-				if (lane == 0) {
-					const int s = i & (RING - 1);
-					*(int2*)&ring.a[s].z = make_int2(max_f, max_j);
-					ring.b[s].x = v_best > max_f ? v_best : max_f;                         // chain.c:237
+			const int si = i & (RING - 1);
+			const int4 me = ring.a[si];                    // broadcast reads: this anchor's own slot still holds its defaults
+			const int st = ring.b[si].y;
+			const int32_t q_span = me.z;
+			const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
+			int32_t max_f = q_span, max_j = -1;
+			if (!deep_block) scan_predecessors<GENERAL, false>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
+			else scan_predecessors<GENERAL, true>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
+			{	// f[i], p[i], v[i] (chain.c:236-237): one lane publishes them to the anchor's slot; untouched if no predecessor won
+				int32_t v_prev;
+				if (deep_block && max_j < ring_lo) v_prev = max_j >= 0 ? rc.V[max_j] : 0;
+				else v_prev = ring.b[max_j & (RING - 1)].x;
+				if (lane == 0 && max_j >= 0) {
+					*(int2*)&ring.a[si].z = make_int2(max_f, max_j);
+					ring.b[si].x = v_prev > max_f ? v_prev : max_f;
 				}
 				__syncwarp();
 			}
@@ -623,7 +634,8 @@ chain_reads_kernel(const BatchArgs args)
 		}
 		// `.01 * (float)sum_qspan / n` — double arithmetic on a float-rounded sum, rounded once more to float
 		const float avg = __double2float_rn(__ddiv_rn(__dmul_rn(.01, (double)__ull2float_rn(sum)), (double)n64));
-		const bool general = seg_diff != 0 || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24);
+		const bool general = seg_diff != 0 || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24) || args.par.bw < 0
+		                  || args.par.n_segs > 1 || args.par.max_dist_x <= 0 || args.par.max_dist_y <= 0;
 		__syncwarp();
 		if (general) {
 			++n_general;
