@@ -57,6 +57,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per pipeline stream (see chain_backend.cpp)
     if not os.path.exists(LIB_PATH):
         raise Mm2bError("native library %s not built: run `python __graft_entry__.py` (there is no CPU fallback)" % LIB_PATH)
     L = C.CDLL(LIB_PATH)

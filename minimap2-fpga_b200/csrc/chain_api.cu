@@ -104,6 +104,7 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 }
 
 size_t mm2b_ws_bytes(const mm2b_workspace_t *ws) { return ws ? ws->bytes : 0; }
+const unsigned long long *mm2b_ws_counters_dev(const mm2b_workspace_t *ws) { return ws ? ws->counters : 0; }
 
 int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
                             const int64_t *d_off, const mm2b_anchor_t *d_a,

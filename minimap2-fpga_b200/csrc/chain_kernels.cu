@@ -1,7 +1,7 @@
 // Hand-written sm_100a kernels for minimap2's chaining hot path (mm_chain_dp, /root/reference/chain.c:29-423).
 //
 // Design (B200-first, not a translation of the FPGA shift-register kernel or of the CPU loop):
-//   * one WARP per read, persistent CTAs (8 warps, 4 CTAs/SM = 32 warps/SM) pulling reads longest-first from a
+//   * one WARP per read, persistent CTAs (2 warps, 16 CTAs/SM = 32 warps/SM) pulling reads longest-first from a
 //     global work counter, so 148 SMs x 32 warps chain 4736 reads concurrently;
 //   * anchors stream in 32 at a time with one coalesced 16-byte load per lane; each lane binary-searches its own
 //     anchor's window start, anchors with an empty window are finished in parallel, and the most recent 256 anchors'
@@ -23,8 +23,13 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int RING = 256;               // ring slots per warp (power of two)
 constexpr int RING_ARRAYS = 6;          // x_lo, y_lo, f, p, v, t
-constexpr int WARPS_PER_CTA = 8;
-constexpr int CTAS_PER_SM = 4;
+// 2 warps per CTA, 16 CTAs per SM (32 warps/SM, 64 registers): small CTAs retire as soon as their reads are done, so when
+// several sub-batch kernels share the GPU (the host-buffer pipeline) SM slots are handed on at 2-read granularity.
+#ifndef MM2B_WARPS_PER_CTA
+#define MM2B_WARPS_PER_CTA 2
+#endif
+constexpr int WARPS_PER_CTA = MM2B_WARPS_PER_CTA;
+constexpr int CTAS_PER_SM = 32 / WARPS_PER_CTA;
 constexpr int32_t MARK_SUCC = 0x7ffffffe;   // "has a successor" (chain.c:351); DP stamps are anchor indices < 2^31-2
 constexpr int32_t MARK_USED = 0x7fffffff;   // "already on a chain" (chain.c:381)
 constexpr int SEG_SHIFT = 48;               // MM_SEED_SEG_SHIFT, mmpriv.h:22

@@ -7,3 +7,6 @@ void set_error(const char *fmt, const char *a, const char *b);   // thread-local
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launches(int n);
 }
+struct mm2b_workspace;
+// device address of a workspace's counters: [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells
+extern "C" const unsigned long long *mm2b_ws_counters_dev(const struct mm2b_workspace *ws);

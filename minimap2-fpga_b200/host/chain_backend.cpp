@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "mm2chain_b200.h"
 #include "../csrc/shim_internal.h"
@@ -35,7 +36,7 @@ namespace {
 using mm2b::cuda_ok;
 using mm2b::set_error;
 
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 6;
 
 template <class T> cudaError_t dmalloc(T **p, size_t bytes) { return cudaMalloc((void**)p, bytes ? bytes : 1); }
 template <class T> cudaError_t hmalloc(T **p, size_t bytes, unsigned flags) { return cudaHostAlloc((void**)p, bytes ? bytes : 1, flags); }
@@ -65,6 +66,7 @@ struct Slot {
 	uint64_t *d_u = nullptr;
 	int32_t *d_n_u = nullptr, *d_n_v = nullptr, *d_status = nullptr;
 	int64_t *h_off = nullptr, *h_u_off = nullptr, *h_b_off = nullptr;   // pinned
+	unsigned long long *h_cnt = nullptr;                                // pinned copy of the workspace counters
 	// the sub-batch currently occupying the slot
 	int sub = -1;
 	int stage = 0;              // 0 free, 1 kernels + counts in flight, 2 outputs in flight
@@ -84,7 +86,8 @@ struct Slot {
 		mm2b_ws_destroy(ws), ws = nullptr;
 		cudaFree(d_off), cudaFree(d_u_off), cudaFree(d_b_off), cudaFree(d_a), cudaFree(d_b), cudaFree(d_u);
 		cudaFree(d_n_u), cudaFree(d_n_v), cudaFree(d_status);
-		cudaFreeHost(h_off), cudaFreeHost(h_u_off), cudaFreeHost(h_b_off);
+		cudaFreeHost(h_off), cudaFreeHost(h_u_off), cudaFreeHost(h_b_off), cudaFreeHost(h_cnt);
+		h_cnt = nullptr;
 		d_off = d_u_off = d_b_off = nullptr, d_a = d_b = nullptr, d_u = nullptr, d_n_u = d_n_v = d_status = nullptr;
 		h_off = h_u_off = h_b_off = nullptr;
 		cap_anchors = cap_reads = 0;
@@ -113,7 +116,8 @@ struct Slot {
 		       && cuda_ok(dmalloc(&d_status, nr * 4), "cudaMalloc")
 		       && cuda_ok(hmalloc(&h_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
 		       && cuda_ok(hmalloc(&h_u_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
-		       && cuda_ok(hmalloc(&h_b_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc");
+		       && cuda_ok(hmalloc(&h_b_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_cnt, 32, cudaHostAllocPortable), "cudaHostAlloc");
 		if (!ok) return false;
 		cap_anchors = na, cap_reads = nr;
 		return true;
@@ -157,8 +161,10 @@ struct Backend {
 	std::vector<Device*> devs;
 	std::mutex mu;              // guards init/shutdown
 	bool up = false;
-	int64_t sub_anchors = 4 << 20;
+	int64_t sub_anchors = 2 << 20;
 	bool want_stats = true;
+	bool trace = false;
+	cudaEvent_t trace_ev0[64] = {};
 } g;
 
 void job_fail(Job *job)
@@ -188,6 +194,7 @@ bool stage_issue(Slot &s, Job *job, int si)
 	  && cuda_ok(cudaMemcpyAsync(job->status + sb.r0, s.d_status, nr * 4, cudaMemcpyDeviceToHost, st), "D2H status")
 	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
 	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
+	  && cuda_ok(cudaMemcpyAsync(s.h_cnt, mm2b_ws_counters_dev(s.ws), 24, cudaMemcpyDeviceToHost, st), "D2H counters")
 	  && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord");
 	s.sub = si, s.stage = 1;
 	return ok;
@@ -215,12 +222,18 @@ bool stage_outputs(Slot &s, Job *job)
 bool stage_finish(Slot &s, Job *job)
 {
 	if (!cuda_ok(cudaEventSynchronize(s.ev[5]), "cudaEventSynchronize")) return false;
+	if (g.trace) {              // MM2B_TRACE=1: timeline of this sub-batch relative to the first event of the job on this slot's device
+		float t[6];
+		for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], g.trace_ev0[s.device], s.ev[i]);
+		const SubBatch sb = job->subs[s.sub];
+		fprintf(stderr, "[mm2b trace] dev %d sub %3d reads %6lld anchors %8lld | start %8.3f h2d_done %8.3f kern_done %8.3f cnt_done %8.3f out_start %8.3f out_done %8.3f ms\n",
+		        s.device, s.sub, (long long)(sb.r1 - sb.r0), (long long)(job->off[sb.r1] - job->off[sb.r0]), t[0], t[1], t[2], t[3], t[4], t[5]);
+	}
 	if (g.want_stats) {
 		float h2d = 0, ker = 0, d2h0 = 0, d2h1 = 0;
 		cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]), cudaEventElapsedTime(&ker, s.ev[1], s.ev[2]);
 		cudaEventElapsedTime(&d2h0, s.ev[2], s.ev[3]), cudaEventElapsedTime(&d2h1, s.ev[4], s.ev[5]);
-		mm2b_stats_t st;
-		if (mm2b_ws_stats(s.ws, s.stream, &st) == MM2B_OK) job->cells_issued += st.cells_issued, job->cells_ref += st.cells_ref, job->n_general += st.n_general_reads;
+		job->cells_issued += (int64_t)s.h_cnt[0] * 32, job->n_general += (int64_t)s.h_cnt[1], job->cells_ref += (int64_t)s.h_cnt[2];
 		std::lock_guard<std::mutex> lk(job->mu);
 		job->h2d_ms += h2d, job->kernel_ms += ker, job->d2h_ms += d2h0 + d2h1;
 	}
@@ -231,29 +244,45 @@ bool stage_finish(Slot &s, Job *job)
 void run_job_on_device(Device *d, Job *job)
 {
 	cudaSetDevice(d->id);
-	std::deque<int> fifo;       // slot indices in issue order
+	if (g.trace) {
+		if (!g.trace_ev0[d->id]) cudaEventCreate(&g.trace_ev0[d->id]);
+		cudaEventRecord(g.trace_ev0[d->id], d->slots[0].stream);
+	}
 	const int n_subs = (int)job->subs.size();
 	bool more = true;
+	int in_flight = 0;
 	for (;;) {
-		// fill free slots
-		while (more && (int)fifo.size() < NSLOT && !job->failed.load()) {
+		bool progressed = false;
+		// advance whatever is ready, oldest sub-batch first, without blocking: a finished count copy turns into the output
+		// copies, a finished output copy frees the slot
+		for (int k = 0; k < NSLOT; ++k) {
+			Slot &s = d->slots[k];
+			if (s.stage == 0) continue;
+			if (job->failed.load()) { cudaStreamSynchronize(s.stream); s.stage = 0, --in_flight, progressed = true; continue; }
+			const cudaError_t q = cudaEventQuery(s.stage == 1 ? s.ev[3] : s.ev[5]);
+			if (q == cudaErrorNotReady) continue;
+			if (q != cudaSuccess) { mm2b::cuda_ok(q, "cudaEventQuery"); job_fail(job); s.stage = 0, --in_flight; continue; }
+			progressed = true;
+			if (s.stage == 1) {
+				if (!stage_outputs(s, job)) { job_fail(job); s.stage = 0, --in_flight; }
+			} else {
+				if (!stage_finish(s, job)) job_fail(job);
+				s.stage = 0, --in_flight;
+			}
+		}
+		// keep the copy engines fed: every free slot gets the next sub-batch right away
+		while (more && in_flight < NSLOT && !job->failed.load()) {
 			const int si = job->next.fetch_add(1);
 			if (si >= n_subs) { more = false; break; }
 			int k = 0;
 			while (d->slots[k].stage != 0) ++k;
 			if (!stage_issue(d->slots[k], job, si)) { job_fail(job); d->slots[k].stage = 0; break; }
-			fifo.push_back(k);
+			++in_flight, progressed = true;
 		}
-		if (fifo.empty()) break;
-		const int k = fifo.front();
-		fifo.pop_front();
-		Slot &s = d->slots[k];
-		if (job->failed.load()) { cudaStreamSynchronize(s.stream); s.stage = 0; continue; }
-		if (s.stage == 1) {
-			if (!stage_outputs(s, job)) { job_fail(job); s.stage = 0; continue; }
-			fifo.push_back(k);      // comes round again once younger sub-batches have been looked at
-		} else {
-			if (!stage_finish(s, job)) { job_fail(job); s.stage = 0; }
+		if (in_flight == 0 && (!more || job->failed.load())) break;
+		if (!progressed) {          // nothing ready yet: events of different slots complete in no fixed order, so poll all of them
+			struct timespec ts = {0, 20000};                                   // 20 us
+			nanosleep(&ts, nullptr);
 		}
 	}
 }
@@ -332,6 +361,10 @@ int mm2b_init(int n_devices, const int *devices)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (g.up) return MM2B_OK;
+	// Each in-flight sub-batch (and each mm_chain_dp caller thread) owns a stream; with the default of 8 hardware queues
+	// streams alias and pick up false dependencies (measured: copies stalled behind other sub-batches' kernels).  Only takes
+	// effect if the CUDA context does not exist yet, which is the case for the minimap2 CLI and for binding.load().
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 	int visible = 0;
 	if (!cuda_ok(cudaGetDeviceCount(&visible), "cudaGetDeviceCount") || visible <= 0) {
 		if (visible <= 0) set_error("%s%s", "mm2b_init: no CUDA device visible", "");
@@ -342,6 +375,7 @@ int mm2b_init(int n_devices, const int *devices)
 	else if (n_devices > 0) for (int i = 0; i < n_devices; ++i) ids.push_back(i);
 	else if (!parse_device_list(getenv("MM2B_DEVICES"), ids)) for (int i = 0; i < visible; ++i) ids.push_back(i);
 	for (int id : ids) if (id < 0 || id >= visible) { set_error("%s%s", "mm2b_init: device id out of range", ""); return MM2B_ERR_ARG; }
+	if (const char *s = getenv("MM2B_TRACE")) g.trace = atoi(s) > 0;
 	if (const char *s = getenv("MM2B_SUB_ANCHORS")) { const long long v = atoll(s); if (v > 0) g.sub_anchors = v; }
 	for (int id : ids) {
 		Device *d = new Device();
