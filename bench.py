@@ -84,10 +84,17 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(n_reads, seed):
+WORKLOADS = {
+    "map-ont": "map-ont (BASELINE configs[1]): %d synthetic ONT reads per GPU (10 kb mean, ~10%% error) vs 100 Mbp random reference",
+    "asm20": "asm20 (BASELINE configs[2]): %d synthetic CCS-like reads per GPU (15 kb mean, ~1%% error) vs 100 Mbp random reference",
+    "ultralong": "ultra-long map-ont (BASELINE configs[3]): %d synthetic ONT reads per GPU (120 kb mean, ~10%% error) vs 100 Mbp random reference",
+}
+
+
+def make_workload(name, n_reads, seed):
     wl = load_package("workload")
     t0 = time.time()
-    off, a = wl.synth_anchor_batch(n_reads, seed=seed)
+    off, a = wl.preset_batch(name, n_reads, seed=seed)
     return off, a, time.time() - t0
 
 
@@ -117,17 +124,21 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=100000, help="reads per GPU (weak scaling)")
+    ap.add_argument("--workload", default="map-ont", choices=sorted(WORKLOADS), help="map-ont is the configuration the metric is quoted on")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (weak scaling); default 100000 / 50000 / 2000 by workload")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.reads <= 0:
+        args.reads = {"map-ont": 100000, "asm20": 50000, "ultralong": 2000}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "map-ont: %d synthetic ONT reads per GPU (10 kb mean, ~10%% error) vs 100 Mbp random reference; "
-                          "chaining parameters of -x map-ont (max_dist 5000, bw 500, max_skip 25, max_iter 5000, min_cnt 3, min_sc 40)" % args.reads,
+    config = {"workload": WORKLOADS[args.workload] % args.reads + "; anchors drawn from the seed-hit model in workload.py (calibrated against real "
+                          "minimap2 seeding, tests/golden/workload_calibration.json); chaining parameters of the preset "
+                          "(max_dist 5000, bw 500, max_skip 25, max_iter 5000, min_cnt 3, min_sc 40)",
               "reads_per_gpu": args.reads, "l2": "inputs (anchors + 40 B/anchor scratch) exceed the 126 MB L2, no flush needed",
               "parallelism": "read-sharded, %d GPU(s), no collective" % world}
 
@@ -135,7 +146,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        off, a, _ = make_workload(args.reads, seed=1000)
+        off, a, _ = make_workload(args.workload, args.reads, seed=1000)
         cores = os.cpu_count() or 1
         r = cpu_arm(off, a, cores, max(args.steps, 1), max(args.warmup, 0))
         line = {"impl": "reference", "metric": "chain_dp_gcups", "value": r["value"], "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
@@ -177,7 +188,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    off, a, gen_s = make_workload(args.reads, seed=1000 + rank)
+    off, a, gen_s = make_workload(args.workload, args.reads, seed=1000 + rank)
     n_reads, n_anchors = len(off) - 1, int(off[-1])
     par = binding.Params()
     binding.init([local_rank])

@@ -78,7 +78,8 @@ struct DpConst {
 
 // One anchor's scan over its predecessors j = i-1 .. st in 32-lane chunks, nearest first (chain.c:197-235).
 // DEEP=false: the whole window [st, i) is resident in the ring, so every access is shared memory.
-// DEEP=true : the window reaches below the ring; lanes pick ring or global (L1/L2) per element.
+// DEEP=true : the window reaches below the ring (CCS reads, repeats); chunks that still lie inside the ring — the nearest
+//             ones, where the loop usually ends — take the same shared-memory path, only deeper chunks read L1/L2.
 //
 // The order-dependent parts of the reference loop are recovered exactly from warp votes:
 //  * records (chain.c:226, strict '>' running max): the first lane above max_f, then the first later lane above that, ...
@@ -103,7 +104,8 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		const int j = jt - lane;
 		const int s = j & (RING - 1);
 		int32_t xj, yj, fj, pj, sidj = sidi;
-		if (!DEEP) {
+		const bool in_ring = !DEEP || jt - n_act + 1 >= ring_lo;   // warp-uniform: the whole chunk is resident in the ring
+		if (in_ring) {
 			const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
 			xj = q.x, yj = q.y, fj = q.z, pj = q.w;
 			if (GENERAL) sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
@@ -179,7 +181,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		}
 		__syncwarp();
 		int32_t tj;
-		if (!DEEP) tj = ring.b[s].y;
+		if (in_ring) tj = ring.b[s].y;
 		else tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
 		const unsigned hitmask = __ballot_sync(FULL, valid && tj == i) & ~recmask;   // chain.c:229
 		// n_skip and the break lane

@@ -42,3 +42,19 @@ def synth_anchor_batch(n_reads, seed=0, mean_len=10000, min_len=500, **kw):
     off = np.zeros(n_reads + 1, np.int64)
     np.cumsum([len(r) for r in reads], out=off[1:])
     return off, (np.concatenate(reads) if reads else np.empty(0, ANCHOR))
+
+
+# BASELINE.json configs at the anchor level.  Model constants are calibrated against real minimap2 seeding of simulated reads
+# (SURVEY.md 8d probe: ONT 588 anchors/read, 15.9 cells/anchor, 61 % chained; CCS 2,248 anchors/read, 26.8 cells/anchor,
+# 99.9 % chained; ultra-long 7.5 k anchors/read); tests/test_workload_model.py re-checks the statistics with the oracle.
+PRESETS = {
+    # name: (mean read length, generator keyword arguments, chaining preset)
+    "map-ont": (10000, dict(k=15, keep=0.2, err_indel=0.067, noise_rate=0.023), "map-ont"),
+    "asm20": (15000, dict(k=19, keep=0.826, err_indel=0.0067, noise_rate=0.0002), "asm20"),
+    "ultralong": (120000, dict(k=15, keep=0.2, err_indel=0.067, noise_rate=0.023), "map-ont"),
+}
+
+
+def preset_batch(name, n_reads, seed=0):
+    mean_len, kw, _ = PRESETS[name]
+    return synth_anchor_batch(n_reads, seed=seed, mean_len=mean_len, **kw)
