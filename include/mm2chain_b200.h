@@ -55,9 +55,9 @@ enum { MM2B_OK = 0, MM2B_ERR_CUDA = -1, MM2B_ERR_ARG = -2, MM2B_ERR_CAPACITY = -
 typedef struct {
 	int64_t n_reads, n_anchors;
 	int64_t n_chains, n_chained;     /* totals: sum n_u, sum n_v */
-	int64_t cells_issued;            /* GPU lanes evaluated (32 per chunk) */
+	int64_t cells_issued;            /* GPU lanes evaluated (32 per chunk); 0 unless counting is on */
 	int64_t cells_ref;               /* iterations of the reference's inner j loop (chain.c:197) these reads take, `continue`d ones
-	                                    included, up to the max_skip break: the "cell" of the GCUPS metric */
+	                                    included, up to the max_skip break: the "cell" of the GCUPS metric; 0 unless counting is on */
 	int64_t n_general_reads;         /* reads that took the general (multi-segment / cDNA / gap_scale != 1) scoring path */
 	double  h2d_ms, kernel_ms, d2h_ms; /* device-side timings of the last host-buffer call (CUDA events), 0 for device calls */
 } mm2b_stats_t;
@@ -69,6 +69,7 @@ typedef struct {
 int mm2b_init(int n_devices, const int *devices);
 void mm2b_shutdown(void);
 int mm2b_num_devices(void);                 /* devices bound by mm2b_init (0 before) */
+void mm2b_set_counting(int on);             /* the same statistics switch for mm2b_chain_batch / mm_chain_dp (all internal workspaces) */
 int mm2b_cuda_device_count(void);           /* devices visible to the CUDA runtime; <= 0 when there is no usable GPU */
 const char *mm2b_last_error(void);          /* thread-local text of the last failure */
 int mm2b_abi_version(void);
@@ -98,6 +99,9 @@ typedef struct mm2b_workspace mm2b_workspace_t;
 mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_reads);
 void mm2b_ws_destroy(mm2b_workspace_t *ws);
 size_t mm2b_ws_bytes(const mm2b_workspace_t *ws);
+/* Statistics switch: when on, batches run on this workspace also tally cells_ref / cells_issued (mm2b_stats_t).  Off by default
+ * (the tally costs kernel time and is not part of the result); also switched on by the environment variable MM2B_COUNT_CELLS=1. */
+void mm2b_ws_set_counting(mm2b_workspace_t *ws, int on);
 
 /* All d_* pointers are device memory on the workspace's device; `stream` is a cudaStream_t passed as void* (NULL = default
  * stream).  Asynchronous: work is enqueued on `stream` and the call returns.  `n_anchors` == off[n_reads] (known to the host).

@@ -13,12 +13,13 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmm2chain_b200.so")
+LIB_PATH = os.environ.get("MM2B_LIB") or os.path.join(HERE, "libmm2chain_b200.so")      # MM2B_LIB: tuning experiments only
 ANCHOR = np.dtype([("x", "<u8"), ("y", "<u8")])
 READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 
 EXPORTS = ["mm2b_init", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
+           "mm2b_ws_set_counting", "mm2b_set_counting",
            "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_measure_int32_peak",
            "mm_chain_dp"]
 
@@ -77,6 +78,8 @@ def load():
     L.mm2b_ws_create.restype, L.mm2b_ws_create.argtypes = vp, [i32, i64, i64]
     L.mm2b_ws_destroy.restype, L.mm2b_ws_destroy.argtypes = None, [vp]
     L.mm2b_ws_bytes.restype, L.mm2b_ws_bytes.argtypes = C.c_size_t, [vp]
+    L.mm2b_ws_set_counting.restype, L.mm2b_ws_set_counting.argtypes = None, [vp, i32]
+    L.mm2b_set_counting.restype, L.mm2b_set_counting.argtypes = None, [i32]
     L.mm2b_chain_batch_device.restype = i32
     L.mm2b_chain_batch_device.argtypes = [vp, C.POINTER(Params), i64, i64] + [vp] * 9 + [vp]
     L.mm2b_ws_stats.restype, L.mm2b_ws_stats.argtypes = i32, [vp, vp, C.POINTER(Stats)]
@@ -109,6 +112,11 @@ def init(devices=None):
 
 def shutdown():
     load().mm2b_shutdown()
+
+
+def set_counting(on):
+    """Statistics switch for chain_batch()/chain_read(): tally reference-semantics cells (stats.cells_ref); off by default."""
+    load().mm2b_set_counting(1 if on else 0)
 
 
 class PinnedArray:
@@ -241,6 +249,9 @@ class DeviceBatch:
         st = Stats()
         _check(self.L.mm2b_ws_stats(self.ws, self._stream(), C.byref(st)), "mm2b_ws_stats")
         return st
+
+    def set_counting(self, on):
+        self.L.mm2b_ws_set_counting(self.ws, 1 if on else 0)
 
     def chain_kernel_ms(self):
         return float(self.L.mm2b_ws_chain_kernel_ms(self.ws))

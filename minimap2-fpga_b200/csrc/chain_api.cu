@@ -39,6 +39,7 @@ struct mm2b_workspace {
 	int32_t *dbg_fpv;           // 3 * max_anchors when MM2B_KEEP_FPV=1
 	size_t bytes;
 	cudaEvent_t ev_k1[2];       // around the chaining kernel of the last batch
+	int count_cells;
 	int64_t last_reads, last_anchors;
 	const int32_t *last_n_u, *last_n_v;
 	const int64_t *last_u_off, *last_b_off;
@@ -72,6 +73,7 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return 0;
 	mm2b_workspace_t *ws = (mm2b_workspace_t*)calloc(1, sizeof(*ws));
 	ws->device = device, ws->max_anchors = max_anchors, ws->max_reads = max_reads;
+	{ const char *e = getenv("MM2B_COUNT_CELLS"); ws->count_cells = e && atoi(e) > 0; }
 	cudaDeviceGetAttribute(&ws->n_sms, cudaDevAttrMultiProcessorCount, device);
 	const size_t sz_scratch = (size_t)max_anchors * SCRATCH_BYTES_PER_ANCHOR;
 	const size_t sz_order = (size_t)max_reads * sizeof(int32_t);
@@ -104,6 +106,7 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 }
 
 size_t mm2b_ws_bytes(const mm2b_workspace_t *ws) { return ws ? ws->bytes : 0; }
+void mm2b_ws_set_counting(mm2b_workspace_t *ws, int on) { if (ws) ws->count_cells = on != 0; }
 const unsigned long long *mm2b_ws_counters_dev(const mm2b_workspace_t *ws) { return ws ? ws->counters : 0; }
 
 int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
@@ -126,7 +129,7 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	memset(&ba, 0, sizeof(ba));
 	ba.par = *par, ba.n_reads = n_reads, ba.off = d_off, ba.a = d_a, ba.scratch = ws->scratch;
 	ba.n_u = d_n_u, ba.n_v = d_n_v, ba.status = d_status, ba.order = ws->order, ba.work_counter = ws->small;
-	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors;
+	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors, ba.count_cells = ws->count_cells;
 	cudaEventRecord(ws->ev_k1[0], stream);
 	launches += launch_chain(ba, ws->n_sms, stream);
 	cudaEventRecord(ws->ev_k1[1], stream);

@@ -29,7 +29,10 @@ constexpr int RING_ARRAYS = 6;          // x_lo, y_lo, f, p, v, t
 #define MM2B_WARPS_PER_CTA 2
 #endif
 constexpr int WARPS_PER_CTA = MM2B_WARPS_PER_CTA;
-constexpr int CTAS_PER_SM = 32 / WARPS_PER_CTA;
+#ifndef MM2B_WARPS_PER_SM
+#define MM2B_WARPS_PER_SM 32
+#endif
+constexpr int CTAS_PER_SM = MM2B_WARPS_PER_SM / WARPS_PER_CTA;
 constexpr int32_t MARK_SUCC = 0x7ffffffe;   // "has a successor" (chain.c:351); DP stamps are anchor indices < 2^31-2
 constexpr int32_t MARK_USED = 0x7fffffff;   // "already on a chain" (chain.c:381)
 constexpr int SEG_SHIFT = 48;               // MM_SEED_SEG_SHIFT, mmpriv.h:22
@@ -91,14 +94,14 @@ struct DpConst {
 //    with closed form x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum d.  S only drops at records, so the running
 //    minimum is a minimum over the record lanes: scalar work on the two vote masks, no shuffles;
 //  * the loop breaks at the first hit lane with x > max_skip; the new (max_f, max_j) is the last record before it.
-template <bool GENERAL, bool DEEP>
+template <bool GENERAL, bool DEEP, bool COUNT>
 __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo,
                                                   int32_t xi, int32_t qi, int32_t q_span, int32_t sidi,
                                                   int32_t &max_f, int32_t &max_j, unsigned &n_chunks, unsigned &n_cells)
 {
 	int n_skip = 0;
 	for (int jt = i - 1; jt >= st; jt -= 32) {
-		++n_chunks;
+		if (COUNT) ++n_chunks;
 		const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
 		const bool act = lane < n_act;
 		const int j = jt - lane;
@@ -160,19 +163,26 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		}
 		if (!valid) sc = INT_MIN;
 
-		// records
-		unsigned recmask = 0, cand = __ballot_sync(FULL, sc > max_f);
+		// records: the largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane
+		// above max_f, i.e. the only one.  Otherwise walk from the first candidate up to it.
+		unsigned recmask = 0;
+		const unsigned cand = __ballot_sync(FULL, sc > max_f);
 		int32_t top = max_f;
 		int last = 0;
 		if (cand == 0) {
-			if (__ballot_sync(FULL, valid) == 0) { n_cells += n_act; continue; }   // every cell `continue`d: no stamps, no n_skip change
+			if (__ballot_sync(FULL, valid) == 0) {       // every cell `continue`d: no stamps, no n_skip change
+				if (COUNT) n_cells += n_act;
+				continue;
+			}
 		} else {
-			do {
-				last = lowest_lane(cand);
-				recmask |= 1u << last;
-				top = __shfl_sync(FULL, sc, last);
-				cand = __ballot_sync(FULL, sc > top) & (0xfffffffeu << last);
-			} while (cand);
+			top = __reduce_max_sync(FULL, sc);
+			last = lowest_lane(__ballot_sync(FULL, sc == top));
+			recmask = 1u << last;
+			for (int r = lowest_lane(cand); r != last;) {
+				recmask |= 1u << r;
+				const int32_t t = __shfl_sync(FULL, sc, r);
+				r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
+			}
 		}
 		// stamps, then hits
 		if (valid && pj >= st) {
@@ -184,8 +194,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		if (in_ring) tj = ring.b[s].y;
 		else tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
 		const unsigned hitmask = __ballot_sync(FULL, valid && tj == i) & ~recmask;   // chain.c:229
-		// n_skip and the break lane
-		int brk = 32;
+		// n_skip, whether the loop breaks in this chunk, and which records come before the break
+		bool broke = false;
+		int brk = 32;                                         // break lane; only tracked exactly when it is needed
+		unsigned take = recmask;                              // records visited before the break
 		if (hitmask == 0) {                                   // only decrements: saturating subtraction
 			n_skip -= __popc(recmask);
 			n_skip = n_skip > 0 ? n_skip : 0;
@@ -193,16 +205,16 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			const unsigned before = recmask ? (recmask - 1u) : FULL;           // lanes visited before the record
 			const unsigned h1 = hitmask & before, h2 = hitmask & ~before;
 			const int x1 = n_skip + __popc(h1);
-			unsigned run = h1;                                // the run of hits in which the counter first exceeds max_skip
+			unsigned run = h1;                                // the run of hits in which the counter first exceeds max_skip ...
 			int k = c.max_skip + 1 - n_skip;                  // ... at its k-th hit
-			bool brk_here = x1 > c.max_skip;
-			if (!brk_here) {
+			if (x1 > c.max_skip) broke = true, take = 0;      // the loop ends before it reaches the record
+			else {
 				const int x2 = recmask ? (x1 > 0 ? x1 - 1 : 0) : x1;
 				n_skip = x2 + __popc(h2);
-				brk_here = n_skip > c.max_skip;
+				broke = n_skip > c.max_skip;
 				run = h2, k = c.max_skip + 1 - x2;
 			}
-			if (brk_here) {
+			if (COUNT && broke) {                             // the exact lane only matters for the cell tally
 				k = k < 1 ? 1 : k;
 				const unsigned le = lanemask_lt(lane) | (1u << lane);
 				brk = lowest_lane(__ballot_sync(FULL, ((run >> lane) & 1u) && __popc(run & le) == k));
@@ -218,23 +230,20 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			const unsigned le = lanemask_lt(lane) | (1u << lane);
 			const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
 			const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > c.max_skip);
-			if (over) brk = lowest_lane(over);
+			if (over) broke = true, brk = lowest_lane(over), take = recmask & bits_below(brk);
 			else n_skip = n_skip + __popc(hitmask) - done - floor_all;
 		}
 		// new running max: the last record before the break (records are strictly increasing; ties went to the nearest j)
-		if (recmask) {
-			if (brk > last) max_f = top, max_j = jt - last;
+		if (take) {
+			if ((take >> last) & 1u) max_f = top, max_j = jt - last;
 			else {
-				const unsigned take = recmask & bits_below(brk);
-				if (take) {
-					const int l2 = 31 - __clz(take);
-					max_f = __shfl_sync(FULL, sc, l2);
-					max_j = jt - l2;
-				}
+				const int l2 = 31 - __clz(take);
+				max_f = __shfl_sync(FULL, sc, l2);
+				max_j = jt - l2;
 			}
 		}
-		n_cells += brk < 32 ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
-		if (brk < 32) break;                                                      // chain.c:230-231
+		if (COUNT) n_cells += broke ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
+		if (broke) break;                                                         // chain.c:230-231
 	}
 }
 
@@ -248,7 +257,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 // and publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = st} to the ring.  Anchors whose window is empty
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool GENERAL>
+template <bool GENERAL, bool COUNT>
 __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, int32_t *smem, int lane,
                         unsigned long long &n_chunks64, unsigned long long &n_cells64)
 {
@@ -307,8 +316,8 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 			const int32_t q_span = me.z;
 			const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
 			int32_t max_f = q_span, max_j = -1;
-			if (!deep_block) scan_predecessors<GENERAL, false>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
-			else scan_predecessors<GENERAL, true>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
+			if (!deep_block) scan_predecessors<GENERAL, false, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
+			else scan_predecessors<GENERAL, true, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
 			{	// f[i], p[i], v[i] (chain.c:236-237): one lane publishes them to the anchor's slot; untouched if no predecessor won
 				int32_t v_prev;
 				if (deep_block && max_j < ring_lo) v_prev = max_j >= 0 ? rc.V[max_j] : 0;
@@ -596,6 +605,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 // ---------------------------------------------------------------------------------------------------------------
 // K1: persistent warp-per-read kernel
 // ---------------------------------------------------------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 chain_reads_kernel(const BatchArgs args)
 {
@@ -646,9 +656,9 @@ chain_reads_kernel(const BatchArgs args)
 		__syncwarp();
 		if (general) {
 			++n_general;
-			dp_fill<true>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
+			dp_fill<true, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
 		} else {
-			dp_fill<false>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
+			dp_fill<false, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
 		}
 		if (args.dbg_fpv) {      // test hook (MM2B_KEEP_FPV=1): keep f/p/v as they are at chain.c:238, before the extraction reuses v
 			int32_t *d = args.dbg_fpv + o;
@@ -835,7 +845,8 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 	int64_t ctas = (args.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const int64_t resident = (int64_t)n_sms * CTAS_PER_SM;
 	if (ctas > resident) ctas = resident;
-	chain_reads_kernel<<<(int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args);
+	if (args.count_cells) chain_reads_kernel<true><<<(int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args);
+	else chain_reads_kernel<false><<<(int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args);
 	return 1;
 }
 

@@ -26,6 +26,7 @@ struct BatchArgs {
 	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells
 	int32_t *dbg_fpv;               // optional 3 x n_anchors int32 (f, p, v) copy for tests, or nullptr
 	int64_t n_anchors;
+	int count_cells;                // tally reference-semantics cells / issued chunks (statistics only; costs kernel time)
 };
 
 struct EmitArgs {

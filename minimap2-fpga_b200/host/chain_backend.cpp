@@ -164,6 +164,7 @@ struct Backend {
 	int64_t sub_anchors = 2 << 20;
 	bool want_stats = true;
 	bool trace = false;
+	std::atomic<int> count_cells{0};
 	cudaEvent_t trace_ev0[64] = {};
 } g;
 
@@ -179,6 +180,7 @@ bool stage_issue(Slot &s, Job *job, int si)
 	const SubBatch sb = job->subs[si];
 	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0], na = job->off[sb.r1] - a0;
 	if (!s.ensure(na, nr)) return false;
+	mm2b_ws_set_counting(s.ws, g.count_cells.load());
 	for (int64_t r = 0; r <= nr; ++r) s.h_off[r] = job->off[sb.r0 + r] - a0;
 	cudaStream_t st = s.stream;
 	bool ok = cuda_ok(cudaEventRecord(s.ev[0], st), "cudaEventRecord")
@@ -376,6 +378,7 @@ int mm2b_init(int n_devices, const int *devices)
 	else if (!parse_device_list(getenv("MM2B_DEVICES"), ids)) for (int i = 0; i < visible; ++i) ids.push_back(i);
 	for (int id : ids) if (id < 0 || id >= visible) { set_error("%s%s", "mm2b_init: device id out of range", ""); return MM2B_ERR_ARG; }
 	if (const char *s = getenv("MM2B_TRACE")) g.trace = atoi(s) > 0;
+	if (const char *s = getenv("MM2B_COUNT_CELLS")) g.count_cells.store(atoi(s) > 0);
 	if (const char *s = getenv("MM2B_SUB_ANCHORS")) { const long long v = atoll(s); if (v > 0) g.sub_anchors = v; }
 	for (int id : ids) {
 		Device *d = new Device();
@@ -415,6 +418,7 @@ void mm2b_shutdown(void)
 }
 
 int mm2b_num_devices(void) { return g.up ? (int)g.devs.size() : 0; }
+void mm2b_set_counting(int on) { g.count_cells.store(on != 0); }
 
 int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
                      int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,

@@ -37,7 +37,11 @@ def test_full_size_batches_bit_exact(binding, oracle, pkg, name, n_reads):
     ref = oracle.replay(oracle.Params(), off, a, n_threads=16)
     res = binding.chain_batch(binding.Params(), off, a)
     b = _compare_all(res, ref, off)
-    assert res["stats"].cells_ref == ref["stats"].cells
+    binding.set_counting(True)                  # the statistics variant of the kernel must give the same chains and the oracle's cell count
+    res_c = binding.chain_batch(binding.Params(), off, a)
+    binding.set_counting(False)
+    _compare_all(res_c, ref, off)
+    assert res_c["stats"].cells_ref == ref["stats"].cells
     # properties that hold at any size
     n_v = res["n_v"].astype(np.int64)
     cnt_from_u = np.add.reduceat((res["u"] & np.uint64(0xffffffff)).astype(np.int64), np.minimum(res["u_off"][:-1], len(res["u"]) - 1))

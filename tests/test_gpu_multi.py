@@ -30,6 +30,7 @@ def test_many_subbatches_all_devices(binding, oracle, pkg):
     off, a = wl.synth_anchor_batch(1500, seed=5)
     assert len(a) > 30 * 20000          # dozens of sub-batches
     ref = oracle.replay(oracle.Params(), off, a, n_threads=8)
+    binding.set_counting(True)
     for _ in range(2):                  # second call reuses grown slots
         res = binding.chain_batch(binding.Params(), off, a)
         assert np.array_equal(res["n_u"], ref["n_u"]) and np.array_equal(res["n_v"], ref["n_v"].astype(np.int32))
@@ -38,6 +39,7 @@ def test_many_subbatches_all_devices(binding, oracle, pkg):
             assert np.array_equal(res["u"][res["u_off"][r]:res["u_off"][r] + nu], ref["u"][o:o + nu]), r
             assert np.array_equal(res["b"][res["b_off"][r]:res["b_off"][r] + nv], ref["b"][o:o + nv]), r
         assert res["stats"].cells_ref == ref["stats"].cells
+    binding.set_counting(False)
 
 
 def test_concurrent_callers(binding, oracle):

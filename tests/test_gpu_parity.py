@@ -127,6 +127,9 @@ def test_kernel_cell_tally_equals_oracle(binding, oracle, pkg):
     off, a = wl.synth_anchor_batch(300, seed=11)
     ref = oracle.replay(oracle.Params(), off, a, n_threads=4)
     res = binding.chain_batch(binding.Params(), off, a)
+    assert res["stats"].cells_ref == 0          # the tally is a statistics option, off by default
+    binding.set_counting(True)
+    res = binding.chain_batch(binding.Params(), off, a)
     _compare_batch(res, ref, off, "synth")
     assert res["stats"].cells_ref == ref["stats"].cells
     assert res["stats"].cells_issued >= res["stats"].cells_ref
@@ -135,3 +138,5 @@ def test_kernel_cell_tally_equals_oracle(binding, oracle, pkg):
         ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=4)
         res = binding.chain_batch(binding.Params(**kw), off, a)
         assert res["stats"].cells_ref == ref["stats"].cells, kw
+        _compare_batch(res, ref, off, kw)
+    binding.set_counting(False)
