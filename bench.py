@@ -31,6 +31,17 @@ INT_OPS_PER_CELL = 30          # INT32-equivalent ops per refere
 BYTES_PER_ANCHOR = 40          # unavoidable device traffic per anchor (16 in, <=16 b out, <=8 u/indices)
 
 
+def captured_traffic(workload, reads):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this same workload, else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        if t["workload"] == workload and t["reads_per_gpu"] == reads:
+            return t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -49,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -221,7 +232,6 @@ def main():
         db.run()
         k1.append(db.chain_kernel_ms())
     k1_avg = sum(k1) / len(k1)
-    clocks = sampler.stop() if rank == 0 else None
     tot_cells = sum_over_ranks(cells)
     tot_reads = sum_over_ranks(n_reads)
     tot_anchors = sum_over_ranks(n_anchors)
@@ -252,6 +262,7 @@ def main():
                "api": "mm2b_chain_batch (pinned host anchors in, u[]/b[] out)", "stage_ms_sum_over_subbatches": {"h2d": est.h2d_ms, "kernels": est.kernel_ms, "d2h": est.d2h_ms}}
     finally:
         pin["a"] = h_a
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (value and e2e)
 
     # ---- CPU baseline on rank 0, N=1 only -------------------------------------------------------------------------
     cpu = None
@@ -271,7 +282,7 @@ def main():
                 "cells_per_step": int(tot_cells), "cells_issued_per_step_rank0": int(st.cells_issued), "anchors_per_step": int(tot_anchors),
                 "e2e": e2e, "gpu_launches": int(launches_value), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "chain_reads_kernel", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                             "frac": hbm_ach / peaks["hbm_gbs"], "traffic": captured_traffic(args.workload, args.reads), "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                              "algorithmic_bytes_per_launch": BYTES_PER_ANCHOR * n_anchors, "kernel_ms": k1_avg,
                              "note": "the path is INT32-issue bound, not HBM bound (SURVEY.md 8d): see roofline_int32"},
                 "roofline_int32": {"bound": "int32_issue", "achieved": int_ach, "peak": int_peak, "unit": "Gop/s", "frac": int_ach / int_peak if int_peak > 0 else None,

@@ -21,7 +21,10 @@ namespace mm2b {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int RING = 256;               // ring slots per warp (power of two)
+#ifndef MM2B_RING
+#define MM2B_RING 256
+#endif
+constexpr int RING = MM2B_RING;          // ring slots per warp (power of two)
 constexpr int RING_ARRAYS = 6;          // x_lo, y_lo, f, p, v, t
 // 2 warps per CTA, 16 CTAs per SM (32 warps/SM, 64 registers): small CTAs retire as soon as their reads are done, so when
 // several sub-batch kernels share the GPU (the host-buffer pipeline) SM slots are handed on at 2-read granularity.
