@@ -37,7 +37,6 @@ constexpr int WARPS_PER_CTA = MM2B_WARPS_PER_CTA;
 #endif
 constexpr int CTAS_PER_SM = MM2B_WARPS_PER_SM / WARPS_PER_CTA;
 constexpr int32_t MARK_SUCC = 0x7ffffffe;   // "has a successor" (chain.c:351); DP stamps are anchor indices < 2^31-2
-constexpr int32_t MARK_USED = 0x7fffffff;   // "already on a chain" (chain.c:381)
 constexpr int SEG_SHIFT = 48;               // MM_SEED_SEG_SHIFT, mmpriv.h:22
 
 struct W16 { uint64_t x, y; };          // (first-anchor x, start-in-PATH << 32 | chain index); 8-byte aligned on purpose
@@ -250,6 +249,34 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 	}
 }
 
+// The sequential step for one block of 32 anchors: the anchors flagged in `todo` (non-empty window), in index order.
+template <bool GENERAL, bool DEEP, bool COUNT>
+__device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int base, int ring_lo,
+                                            unsigned todo, int32_t seg, unsigned &n_chunks, unsigned &n_cells)
+{
+	while (todo) {
+		const int ii = lowest_lane(todo);
+		todo &= todo - 1;
+		const int i = base + ii;
+		const int si = i & (RING - 1);
+		const int4 me = ring.a[si];                    // broadcast reads: this anchor's own slot still holds its defaults
+		const int st = ring.b[si].y;
+		const int32_t q_span = me.z;
+		const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
+		int32_t max_f = q_span, max_j = -1;
+		scan_predecessors<GENERAL, DEEP, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
+		// f[i], p[i], v[i] (chain.c:236-237): one lane publishes them to the anchor's slot; untouched if no predecessor won
+		int32_t v_prev;
+		if (DEEP && max_j < ring_lo) v_prev = max_j >= 0 ? rc.V[max_j] : 0;
+		else v_prev = ring.b[max_j & (RING - 1)].x;
+		if (lane == 0 && max_j >= 0) {
+			*(int2*)&ring.a[si].z = make_int2(max_f, max_j);
+			ring.b[si].x = v_prev > max_f ? v_prev : max_f;
+		}
+		__syncwarp();
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // DP fill: f[], p[], v[] for one read (chain.c:184-238).  GENERAL=false is the map-ont / asm20 shape
 // (one segment id, !is_cdna, gap_scale == 1) with a pure-integer + one float-multiply cost; GENERAL=true carries
@@ -309,29 +336,8 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 		st_carry = __shfl_sync(FULL, st_k, (n - base < 32 ? n - base : 32) - 1);
 		__syncwarp();
 
-		while (todo) {
-			const int ii = lowest_lane(todo);
-			todo &= todo - 1;
-			const int i = base + ii;
-			const int si = i & (RING - 1);
-			const int4 me = ring.a[si];                    // broadcast reads: this anchor's own slot still holds its defaults
-			const int st = ring.b[si].y;
-			const int32_t q_span = me.z;
-			const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
-			int32_t max_f = q_span, max_j = -1;
-			if (!deep_block) scan_predecessors<GENERAL, false, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
-			else scan_predecessors<GENERAL, true, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
-			{	// f[i], p[i], v[i] (chain.c:236-237): one lane publishes them to the anchor's slot; untouched if no predecessor won
-				int32_t v_prev;
-				if (deep_block && max_j < ring_lo) v_prev = max_j >= 0 ? rc.V[max_j] : 0;
-				else v_prev = ring.b[max_j & (RING - 1)].x;
-				if (lane == 0 && max_j >= 0) {
-					*(int2*)&ring.a[si].z = make_int2(max_f, max_j);
-					ring.b[si].x = v_prev > max_f ? v_prev : max_f;
-				}
-				__syncwarp();
-			}
-		}
+		if (!deep_block) chain_block<GENERAL, false, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, n_chunks, n_cells);
+		else chain_block<GENERAL, true, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, n_chunks, n_cells);
 		if (in) {                // one coalesced write of the block's f/p/v (needed by deep look-back and by the backtrack)
 			const int s = k & (RING - 1);
 			const int2 fp = *(const int2*)&ring.a[s].z;
@@ -459,8 +465,8 @@ __device__ void flag_sort_by_x_lane0(W16 *w, int n, int *sm /* >= 768 ints */, i
 __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int32_t *smem, int lane, int &n_u_out, int &n_v_out, int &status)
 {
 	const int n = rc.n;
-	const int32_t *F = rc.F, *P = rc.P;
-	int32_t *V = rc.V, *T = rc.T;
+	const int32_t *F = rc.F;
+	int32_t *P = rc.P, *V = rc.V, *T = rc.T;
 	uint64_t *U = rc.U;
 
 	// chain.c:349-351: mark anchors that have a successor
@@ -519,12 +525,20 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 		for (int i = 0; i < n_u; ++i) {
 			const uint64_t key = U[i];
 			const int n_v0 = n_v;
+			// The used-mark of an anchor (t[j] = 1 at chain.c:381) is folded into its p[] word — a used anchor stores -3 - p,
+			// i.e. a value <= -2 — so each step of the walk is ONE dependent load (the next anchor's word gives both its
+			// mark and its own predecessor) instead of two.  p[] has no reader after the backtrack.
 			int j = (int32_t)key;
-			do {
+			int32_t w = P[j];
+			for (;;) {                                       // do-while of chain.c:379-383: the first anchor is taken unconditionally
 				PATH[n_v++] = j;
-				T[j] = MARK_USED;
-				j = P[j];
-			} while (j >= 0 && T[j] != MARK_USED);
+				const int32_t pj = w <= -2 ? -3 - w : w;
+				if (w >= -1) P[j] = -3 - w;
+				j = pj;
+				if (j < 0) break;
+				w = P[j];
+				if (w <= -2) break;                          // already on a better chain
+			}
 			const int len = n_v - n_v0;
 			bool keep = false;
 			uint64_t sc = key >> 32;
