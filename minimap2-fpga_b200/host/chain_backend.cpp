@@ -165,6 +165,7 @@ struct Backend {
 	bool want_stats = true;
 	bool trace = false;
 	std::atomic<int> count_cells{0};
+	bool use_batcher = true;       // MM2B_BATCHER=0: every mm_chain_dp caller drives its own stream instead
 	cudaEvent_t trace_ev0[64] = {};
 } g;
 
@@ -355,6 +356,157 @@ ThreadCtx *thread_ctx()
 	exit(EXIT_FAILURE);
 }
 
+// ---- cross-thread batcher behind mm_chain_dp ------------------------------------------------------------------------
+// mm_chain_dp is a synchronous per-read call made by n_threads kt_for workers (map.c:561).  One GPU launch per read would
+// be dominated by launch/sync latency, so concurrent callers are aggregated: each caller copies its anchors into the open
+// flight's pinned buffer and sleeps; a dispatcher thread per device closes the flight as soon as the GPU is free, runs it as
+// ONE device batch and wakes the callers, which copy their own results out.  While a flight is on the GPU the next one fills,
+// so the batch size adapts to the load (1 read with -t 1, hundreds with an oversubscribed -t).  This is the CUDA counterpart
+// of the reference's hw_queue / mutex arbitration (chain_hardware.cpp:45-98), which admitted ONE read at a time.
+struct Req {
+	int64_t n = 0, a_off = 0;
+	int32_t n_u = 0, n_v = 0, status = 0;
+	int64_t u_off = 0, b_off = 0;
+};
+
+struct Flight {
+	Slot slot;
+	mm2b_anchor_t *h_a = nullptr, *h_b = nullptr;
+	uint64_t *h_u = nullptr;
+	int32_t *h_cnt = nullptr;       // 3 x max_reqs: n_u, n_v, status
+	int64_t cap = 0;                // anchors
+	mm2b_params_t par;
+	std::vector<Req*> reqs;
+	int64_t used = 0;
+	int copies_pending = 0, consumers_pending = 0;
+	int state = 0;                  // 0 filling, 1 closed / on the GPU, 2 results ready
+	uint64_t epoch = 0;
+};
+
+constexpr int FLIGHT_MAX_REQS = 4096;
+
+struct Batcher {
+	int dev = -1;
+	std::mutex mu;
+	std::condition_variable cv_callers, cv_disp;
+	Flight fl[2];
+	int open = 0;
+	bool stop = false;
+	std::thread th;
+	std::atomic<int64_t> n_flights{0}, n_reqs{0};
+};
+std::vector<Batcher*> g_batchers;
+std::atomic<int> g_batcher_rr{0};
+
+bool flight_grow(Flight &f, int dev, int64_t need)
+{
+	const int64_t cap = std::max<int64_t>(need + need / 4, 1 << 21);
+	cudaSetDevice(dev);
+	cudaFreeHost(f.h_a), cudaFreeHost(f.h_b), cudaFreeHost(f.h_u);
+	f.h_a = f.h_b = nullptr, f.h_u = nullptr;
+	if (!cuda_ok(hmalloc(&f.h_a, cap * 16, cudaHostAllocPortable), "cudaHostAlloc") || !cuda_ok(hmalloc(&f.h_b, cap * 16, cudaHostAllocPortable), "cudaHostAlloc") ||
+	    !cuda_ok(hmalloc(&f.h_u, cap * 8, cudaHostAllocPortable), "cudaHostAlloc")) return false;
+	if (!f.h_cnt && !cuda_ok(hmalloc(&f.h_cnt, FLIGHT_MAX_REQS * 12, cudaHostAllocPortable), "cudaHostAlloc")) return false;
+	f.cap = cap;
+	return true;
+}
+
+bool same_par(const mm2b_params_t &a, const mm2b_params_t &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+void flight_run(Batcher *bt, Flight &f)          // dispatcher thread, no lock held
+{
+	Slot &s = f.slot;
+	cudaSetDevice(bt->dev);
+	const int64_t nr = (int64_t)f.reqs.size(), na = f.used;
+	if (!s.ensure(na, nr)) fatal("workspace allocation");
+	mm2b_ws_set_counting(s.ws, 0);
+	for (int64_t r = 0; r < nr; ++r) s.h_off[r] = f.reqs[r]->a_off;
+	s.h_off[nr] = na;
+	cudaStream_t st = s.stream;
+	bool ok = cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off")
+	       && cuda_ok(cudaMemcpyAsync(s.d_a, f.h_a, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
+	if (!ok || mm2b_chain_batch_device(s.ws, &f.par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st) != MM2B_OK)
+		fatal("enqueue");
+	ok = cuda_ok(cudaMemcpyAsync(f.h_cnt, s.d_n_u, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_u")
+	  && cuda_ok(cudaMemcpyAsync(f.h_cnt + FLIGHT_MAX_REQS, s.d_n_v, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_v")
+	  && cuda_ok(cudaMemcpyAsync(f.h_cnt + 2 * FLIGHT_MAX_REQS, s.d_status, nr * 4, cudaMemcpyDeviceToHost, st), "D2H status")
+	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
+	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
+	  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+	if (!ok) fatal("chain");
+	const int64_t tot_u = s.h_u_off[nr], tot_b = s.h_b_off[nr];
+	ok = (tot_u == 0 || cuda_ok(cudaMemcpyAsync(f.h_u, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"))
+	  && (tot_b == 0 || cuda_ok(cudaMemcpyAsync(f.h_b, s.d_b, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st), "D2H b"))
+	  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+	if (!ok) fatal("copy back");
+	for (int64_t r = 0; r < nr; ++r) {
+		Req *q = f.reqs[r];
+		q->n_u = f.h_cnt[r], q->n_v = f.h_cnt[FLIGHT_MAX_REQS + r], q->status = f.h_cnt[2 * FLIGHT_MAX_REQS + r];
+		q->u_off = s.h_u_off[r], q->b_off = s.h_b_off[r];
+	}
+	bt->n_flights += 1, bt->n_reqs += nr;
+}
+
+void batcher_loop(Batcher *bt)
+{
+	cudaSetDevice(bt->dev);
+	std::unique_lock<std::mutex> lk(bt->mu);
+	for (;;) {
+		bt->cv_disp.wait(lk, [&] { return bt->stop || (bt->fl[bt->open].state == 0 && !bt->fl[bt->open].reqs.empty()); });
+		if (bt->stop) return;
+		Flight &f = bt->fl[bt->open];
+		f.state = 1;                    // closed: later callers go to the other flight (and wait there if it is still being read out)
+		bt->open ^= 1;
+		bt->cv_callers.notify_all();
+		bt->cv_disp.wait(lk, [&] { return f.copies_pending == 0; });
+		lk.unlock();
+		flight_run(bt, f);
+		lk.lock();
+		f.consumers_pending = (int)f.reqs.size();
+		f.state = 2;
+		bt->cv_callers.notify_all();
+	}
+}
+
+// one synchronous read through the batcher; returns the flight holding the results (caller must release it)
+Flight *batcher_submit(Batcher *bt, const mm2b_params_t &par, int64_t n, const mm2b_anchor_t *a, Req &req)
+{
+	std::unique_lock<std::mutex> lk(bt->mu);
+	Flight *f = nullptr;
+	for (;;) {
+		f = &bt->fl[bt->open];
+		if (f->state == 0) {
+			if (f->reqs.empty() && n > f->cap) { if (!flight_grow(*f, bt->dev, n)) fatal("pinned staging"); }
+			if ((f->reqs.empty() || same_par(f->par, par)) && f->used + n <= f->cap && (int)f->reqs.size() < FLIGHT_MAX_REQS) break;
+		}
+		bt->cv_disp.notify_one();
+		bt->cv_callers.wait(lk);
+	}
+	req.n = n, req.a_off = f->used;
+	f->used += n, f->par = par;
+	f->reqs.push_back(&req);
+	++f->copies_pending;
+	const uint64_t epoch = f->epoch;
+	lk.unlock();
+	bt->cv_disp.notify_one();
+	memcpy(f->h_a + req.a_off, a, (size_t)n * 16);
+	lk.lock();
+	if (--f->copies_pending == 0) bt->cv_disp.notify_one();
+	bt->cv_callers.wait(lk, [&] { return f->state == 2 && f->epoch == epoch; });
+	return f;
+}
+
+void batcher_release(Batcher *bt, Flight *f)
+{
+	std::lock_guard<std::mutex> lk(bt->mu);
+	if (--f->consumers_pending == 0) {
+		f->reqs.clear();
+		f->used = 0, f->state = 0, ++f->epoch;
+		bt->cv_callers.notify_all();
+		bt->cv_disp.notify_one();
+	}
+}
+
 }  // namespace
 
 extern "C" {
@@ -378,6 +530,7 @@ int mm2b_init(int n_devices, const int *devices)
 	else if (!parse_device_list(getenv("MM2B_DEVICES"), ids)) for (int i = 0; i < visible; ++i) ids.push_back(i);
 	for (int id : ids) if (id < 0 || id >= visible) { set_error("%s%s", "mm2b_init: device id out of range", ""); return MM2B_ERR_ARG; }
 	if (const char *s = getenv("MM2B_TRACE")) g.trace = atoi(s) > 0;
+	if (const char *s = getenv("MM2B_BATCHER")) g.use_batcher = atoi(s) != 0;
 	if (const char *s = getenv("MM2B_COUNT_CELLS")) g.count_cells.store(atoi(s) > 0);
 	if (const char *s = getenv("MM2B_SUB_ANCHORS")) { const long long v = atoll(s); if (v > 0) g.sub_anchors = v; }
 	for (int id : ids) {
@@ -387,6 +540,15 @@ int mm2b_init(int n_devices, const int *devices)
 		g.devs.push_back(d);
 	}
 	for (Device *d : g.devs) d->worker = std::thread(device_worker, d);
+	if (g.use_batcher) {
+		for (Device *d : g.devs) {
+			Batcher *bt = new Batcher();
+			bt->dev = d->id;
+			for (auto &f : bt->fl) if (!f.slot.create(d->id)) return MM2B_ERR_CUDA;
+			bt->th = std::thread(batcher_loop, bt);
+			g_batchers.push_back(bt);
+		}
+	}
 	g.up = true;
 	return MM2B_OK;
 }
@@ -405,6 +567,18 @@ void mm2b_shutdown(void)
 		delete d;
 	}
 	g.devs.clear();
+	for (Batcher *bt : g_batchers) {
+		{ std::lock_guard<std::mutex> l2(bt->mu); bt->stop = true; }
+		bt->cv_disp.notify_all();
+		if (bt->th.joinable()) bt->th.join();
+		if (g.trace) fprintf(stderr, "[mm2b trace] batcher dev %d: %lld reads in %lld flights\n", bt->dev, (long long)bt->n_reqs.load(), (long long)bt->n_flights.load());
+		for (auto &f : bt->fl) {
+			f.slot.destroy();
+			cudaFreeHost(f.h_a), cudaFreeHost(f.h_b), cudaFreeHost(f.h_u), cudaFreeHost(f.h_cnt);
+		}
+		delete bt;
+	}
+	g_batchers.clear();
 	{
 		std::lock_guard<std::mutex> l3(g_tctx_mu);
 		for (ThreadCtx *t : g_tctx) {
@@ -476,6 +650,25 @@ mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
 		return 0;
 	}
 	if (!g.up && mm2b_init(0, nullptr) != MM2B_OK) fatal("mm2b_init");
+	if (g.use_batcher) {
+		static thread_local int my_batcher = -1;
+		if (my_batcher < 0 || my_batcher >= (int)g_batchers.size()) my_batcher = g_batcher_rr.fetch_add(1) % (int)g_batchers.size();
+		Batcher *bt = g_batchers[my_batcher];
+		const mm2b_params_t par = {max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
+		Req req;
+		Flight *f = batcher_submit(bt, par, n, a, req);
+		host_kfree(km, a);                                            // chain.c:356 / :421 — `a` is consumed on every path
+		mm2b_anchor_t *b = nullptr;
+		if (req.status == MM2B_READ_OK) {                             // otherwise chain.c:355-358: NULL, *_u = NULL, *n_u_ = 0
+			uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(req.n_u, 1) * 8);
+			b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)req.n_v * 16);   // kmalloc(km, 0) == NULL, as at chain.c:397
+			if (req.n_u > 0) memcpy(u, f->h_u + req.u_off, (size_t)req.n_u * 8);
+			if (req.n_v > 0) memcpy(b, f->h_b + req.b_off, (size_t)req.n_v * 16);
+			*n_u_ = req.n_u, *_u = u;
+		}
+		batcher_release(bt, f);
+		return b;
+	}
 	ThreadCtx *t = thread_ctx();
 	Slot &s = t->slot;
 	cudaSetDevice(s.device);

@@ -73,3 +73,29 @@ def test_concurrent_callers(binding, oracle):
     for t in th:
         t.join()
     assert not errs, errs
+
+
+def test_batcher_aggregates_many_mm_chain_dp_callers(binding, oracle, pkg):
+    """64 host threads call the per-read drop-in at once (an oversubscribed `-t`): the cross-thread batcher must hand every
+    caller its own read's result, bit-exact, whatever flight it ended up in."""
+    import threading
+    wl = pkg("workload")
+    off, a = wl.synth_anchor_batch(640, seed=21)
+    ref = oracle.replay(oracle.Params(), off, a, n_threads=8)
+    errs, n_threads = [], 64
+
+    def caller(t):
+        try:
+            for r in range(t, len(off) - 1, n_threads):
+                u, b, u_null, b_null = binding.chain_read(binding.Params(), a[off[r]:off[r + 1]])
+                o, nu, nv = int(off[r]), int(ref["n_u"][r]), int(ref["n_v"][r])
+                assert np.array_equal(u, ref["u"][o:o + nu]) and np.array_equal(b, ref["b"][o:o + nv]), r
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=caller, args=(t,)) for t in range(n_threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs[:3]
