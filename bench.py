@@ -22,7 +22,7 @@ import time
 
 import numpy as np
 
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context exists: one hardware queue per pipeline stream
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "16")   # before any CUDA context exists: one hardware queue per pipeline stream
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402

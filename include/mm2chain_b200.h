@@ -67,6 +67,9 @@ typedef struct {
 /* Bind the backend to `n_devices` CUDA devices (ids in `devices`, or NULL for 0..n_devices-1; n_devices <= 0 means
  * "all visible", or the MM2B_DEVICES environment variable if set).  Creates per-device streams and worker threads. */
 int mm2b_init(int n_devices, const int *devices);
+/* Same, but returns at once and brings the devices up on a background thread (only "no GPU at all" is reported immediately);
+ * the first call that needs the backend waits for it.  Lets a host overlap CUDA start-up with its own (e.g. index loading). */
+int mm2b_init_async(int n_devices, const int *devices);
 void mm2b_shutdown(void);
 int mm2b_num_devices(void);                 /* devices bound by mm2b_init (0 before) */
 void mm2b_set_counting(int on);             /* the same statistics switch for mm2b_chain_batch / mm_chain_dp (all internal workspaces) */

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("MM2B_LIB") or os.path.join(HERE, "libmm2chain_b200.so
 ANCHOR = np.dtype([("x", "<u8"), ("y", "<u8")])
 READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 
-EXPORTS = ["mm2b_init", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
+EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
            "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_measure_int32_peak",
@@ -58,7 +58,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per pipeline stream (see chain_backend.cpp)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "16")   # one hardware queue per pipeline stream (see chain_backend.cpp)
     if not os.path.exists(LIB_PATH):
         raise Mm2bError("native library %s not built: run `python __graft_entry__.py` (there is no CPU fallback)" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
@@ -66,6 +66,7 @@ def load():
         getattr(L, name)        # AttributeError if the C ABI is incomplete
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     L.mm2b_init.restype, L.mm2b_init.argtypes = i32, [i32, vp]
+    L.mm2b_init_async.restype, L.mm2b_init_async.argtypes = i32, [i32, vp]
     L.mm2b_shutdown.restype, L.mm2b_shutdown.argtypes = None, []
     L.mm2b_num_devices.restype = i32
     L.mm2b_cuda_device_count.restype = i32

@@ -515,15 +515,26 @@ int mm2b_init(int n_devices, const int *devices)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (g.up) return MM2B_OK;
-	// Each in-flight sub-batch (and each mm_chain_dp caller thread) owns a stream; with the default of 8 hardware queues
-	// streams alias and pick up false dependencies (measured: copies stalled behind other sub-batches' kernels).  Only takes
+	// Each in-flight sub-batch owns a stream (6 pipeline slots + 2 batcher flights per device); with the default of 8 hardware
+	// queues streams alias and pick up false dependencies (measured: copies stalled behind other sub-batches' kernels).  16 is
+	// enough and keeps context creation fast (measured on this pool: 0.3 s at 8, 0.5 s at 16, 1.5-3.4 s at 32).  Only takes
 	// effect if the CUDA context does not exist yet, which is the case for the minimap2 CLI and for binding.load().
-	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0);
+	if (const char *s = getenv("MM2B_TRACE")) g.trace = atoi(s) > 0;
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	auto lap = [&](const char *what) {
+		if (!g.trace) return;
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		fprintf(stderr, "[mm2b trace] init: %-28s %.3f s\n", what, (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+		t0 = t1;
+	};
 	int visible = 0;
 	if (!cuda_ok(cudaGetDeviceCount(&visible), "cudaGetDeviceCount") || visible <= 0) {
 		if (visible <= 0) set_error("%s%s", "mm2b_init: no CUDA device visible", "");
 		return MM2B_ERR_CUDA;
 	}
+	lap("cudaGetDeviceCount");
 	std::vector<int> ids;
 	if (n_devices > 0 && devices) ids.assign(devices, devices + n_devices);
 	else if (n_devices > 0) for (int i = 0; i < n_devices; ++i) ids.push_back(i);
@@ -539,6 +550,7 @@ int mm2b_init(int n_devices, const int *devices)
 		for (auto &s : d->slots) if (!s.create(id)) return MM2B_ERR_CUDA;
 		g.devs.push_back(d);
 	}
+	lap("contexts, streams, events");
 	for (Device *d : g.devs) d->worker = std::thread(device_worker, d);
 	if (g.use_batcher) {
 		for (Device *d : g.devs) {
@@ -549,12 +561,49 @@ int mm2b_init(int n_devices, const int *devices)
 			g_batchers.push_back(bt);
 		}
 	}
+	lap("worker + batcher threads");
 	g.up = true;
 	return MM2B_OK;
 }
 
+// hardware_init() replacement for hosts that do other start-up work next (the minimap2 CLI loads its index right after,
+// main.c:367-371): bring the devices up on a background thread; the first call that needs them waits for it.
+static std::thread g_init_thread;
+static std::mutex g_init_mu;
+static int g_init_rc = MM2B_OK;
+
+int mm2b_init_async(int n_devices, const int *devices)
+{
+	std::lock_guard<std::mutex> lk(g_init_mu);
+	if (g.up || g_init_thread.joinable()) return MM2B_OK;
+	int visible = 0;
+	if (!cuda_ok(cudaGetDeviceCount(&visible), "cudaGetDeviceCount") || visible <= 0) {      // fail now, loudly, if there is no GPU at all
+		if (visible <= 0) set_error("%s%s", "mm2b_init: no CUDA device visible", "");
+		return MM2B_ERR_CUDA;
+	}
+	std::vector<int> ids;
+	if (n_devices > 0 && devices) ids.assign(devices, devices + n_devices);
+	g_init_thread = std::thread([n_devices, ids] { g_init_rc = mm2b_init(n_devices, ids.empty() ? nullptr : ids.data()); });
+	return MM2B_OK;
+}
+
+static int ensure_up(void)
+{
+	{
+		std::lock_guard<std::mutex> lk(g_init_mu);
+		if (g_init_thread.joinable()) g_init_thread.join();
+	}
+	if (g.up) return MM2B_OK;
+	if (g_init_rc != MM2B_OK) return g_init_rc;
+	return mm2b_init(0, nullptr);
+}
+
 void mm2b_shutdown(void)
 {
+	{
+		std::lock_guard<std::mutex> lk0(g_init_mu);
+		if (g_init_thread.joinable()) g_init_thread.join();
+	}
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.up) return;
 	for (Device *d : g.devs) {
@@ -599,7 +648,7 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
                      uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats)
 {
 	if (!g.up) {
-		const int rc = mm2b_init(0, nullptr);
+		const int rc = ensure_up();
 		if (rc != MM2B_OK) return rc;
 	}
 	if (!par || n_reads < 0 || !off || !n_u || !n_v || !status || !u_off || !b_off) { set_error("%s%s", "mm2b_chain_batch: NULL argument", ""); return MM2B_ERR_ARG; }
@@ -649,7 +698,7 @@ mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
 		host_kfree(km, a);
 		return 0;
 	}
-	if (!g.up && mm2b_init(0, nullptr) != MM2B_OK) fatal("mm2b_init");
+	if (!g.up && ensure_up() != MM2B_OK) fatal("mm2b_init");
 	if (g.use_batcher) {
 		static thread_local int my_batcher = -1;
 		if (my_batcher < 0 || my_batcher >= (int)g_batchers.size()) my_batcher = g_batcher_rr.fetch_add(1) % (int)g_batchers.size();

@@ -1,7 +1,7 @@
 /* Replacement for the reference's chain_hardware.h (/root/reference/chain_hardware.h:1-75) when minimap2 is built against
  * the B200 backend instead of the OpenCL/FPGA one.  The three host files that include it keep compiling unchanged:
  *
- *   main.c:367   if (!hardware_init(BUFFER_N, XCLBIN_FILE)) return -1;     -> mm2b_init()      (CUDA devices, streams, workers)
+ *   main.c:367   if (!hardware_init(BUFFER_N, XCLBIN_FILE)) return -1;     -> mm2b_init_async() (CUDA devices, streams, workers)
  *   main.c:430   cleanup();                                                -> mm2b_shutdown()
  *   options.c:95-99,118-122   K1_HW = ONT_K1_HW; ...                       -> the learned HW/SW split is gone: constants are 0
  *   chain.c      is NOT compiled; mm_chain_dp comes from libmm2chain_b200 (same signature, mmpriv.h:65)
@@ -36,7 +36,7 @@
 static inline bool hardware_init(long buf_size, char *binary_name)
 {
 	(void)buf_size; (void)binary_name;
-	if (mm2b_init(0, 0) != MM2B_OK) {
+	if (mm2b_init_async(0, 0) != MM2B_OK) {      /* devices come up while main() loads the index (main.c:371) */
 		fprintf(stderr, "[ERROR] B200 chaining backend: %s\n", mm2b_last_error());
 		return false;
 	}
