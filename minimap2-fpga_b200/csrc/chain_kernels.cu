@@ -200,27 +200,26 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		bool broke = false;
 		int brk = 32;                                         // break lane; only tracked exactly when it is needed
 		unsigned take = recmask;                              // records visited before the break
-		if (hitmask == 0) {                                   // only decrements: saturating subtraction
-			n_skip -= __popc(recmask);
-			n_skip = n_skip > 0 ? n_skip : 0;
-		} else if ((recmask & (recmask - 1u)) == 0) {         // at most one record (the usual case): two runs of hits, scalar
+		if ((recmask & (recmask - 1u)) == 0) {                // at most one record (the usual case): two runs of hits, branch-free
 			const unsigned before = recmask ? (recmask - 1u) : FULL;           // lanes visited before the record
 			const unsigned h1 = hitmask & before, h2 = hitmask & ~before;
-			const int x1 = n_skip + __popc(h1);
-			unsigned run = h1;                                // the run of hits in which the counter first exceeds max_skip ...
-			int k = c.max_skip + 1 - n_skip;                  // ... at its k-th hit
-			if (x1 > c.max_skip) broke = true, take = 0;      // the loop ends before it reaches the record
-			else {
-				const int x2 = recmask ? (x1 > 0 ? x1 - 1 : 0) : x1;
-				n_skip = x2 + __popc(h2);
-				broke = n_skip > c.max_skip;
-				run = h2, k = c.max_skip + 1 - x2;
-			}
+			const int x1 = n_skip + __popc(h1);                                // counter when the record is reached
+			const int x2 = x1 - (recmask != 0 && x1 > 0);                      // ... after it
+			const int x3 = x2 + __popc(h2);                                    // ... at the end of the chunk
+			const bool early = x1 > c.max_skip;                                // the loop ends before it reaches the record
+			broke = early || x3 > c.max_skip;
+			if (early) take = 0;
 			if (COUNT && broke) {                             // the exact lane only matters for the cell tally
+				const unsigned run = early ? h1 : h2;         // the run of hits in which the counter first exceeds max_skip ...
+				int k = c.max_skip + 1 - (early ? n_skip : x2);                // ... at its k-th hit
 				k = k < 1 ? 1 : k;
 				const unsigned le = lanemask_lt(lane) | (1u << lane);
 				brk = lowest_lane(__ballot_sync(FULL, ((run >> lane) & 1u) && __popc(run & le) == k));
 			}
+			n_skip = x3;
+		} else if (hitmask == 0) {                            // only decrements: saturating subtraction
+			n_skip -= __popc(recmask);
+			n_skip = n_skip > 0 ? n_skip : 0;
 		} else {
 			int corr = 0, floor_all = 0, done = 0;            // corr: min(0, min S over the records at or before this lane)
 			for (unsigned rm = recmask; rm; rm &= rm - 1) {
