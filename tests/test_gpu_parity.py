@@ -140,3 +140,44 @@ def test_kernel_cell_tally_equals_oracle(binding, oracle, pkg):
         assert res["stats"].cells_ref == ref["stats"].cells, kw
         _compare_batch(res, ref, off, kw)
     binding.set_counting(False)
+
+
+def test_edge_shapes(binding, oracle):
+    """Read lengths around the 32-anchor block and 256-slot ring boundaries, windows that end exactly at the ring edge, extreme
+    field values (q_span 255, reverse strand, rid 2^31-1, positions near 2^31), duplicate anchors, degenerate thresholds."""
+    rng = np.random.default_rng(99)
+    reads = []
+    for n in (1, 2, 3, 31, 32, 33, 63, 64, 65, 95, 96, 97, 223, 224, 225, 255, 256, 257, 287, 288, 289, 511, 512, 513, 1023, 1025):
+        reads.append(fuzz.dense_repeat(rng, n, width=max(4, n // 2), qwidth=max(4, n // 2)))        # everything in one window
+        reads.append(fuzz.collinear(rng, n, 0, step=(1, 30)))
+        reads.append(fuzz.lattice(rng, max(n, 4)))
+    # windows whose start falls exactly on / just below the ring edge: uniform spacing s so that 5000 / s sweeps past 224..256
+    for spacing in (19, 20, 21, 22, 23):
+        k = np.arange(1500)
+        a = np.empty(len(k), binding.ANCHOR)
+        a["x"] = (np.uint64(1) << np.uint64(63)) | (np.uint64(2 ** 31 - 1) << np.uint64(32)) | (np.uint64(2 ** 31 - 40000) + (k * spacing).astype(np.uint64))
+        a["y"] = (np.uint64(255) << np.uint64(32)) | (np.uint64(300) + (k * spacing).astype(np.uint64))
+        reads.append(a)
+    dup = fuzz.collinear(rng, 200, 20)
+    reads.append(np.sort(np.concatenate([dup, dup, dup[:50]]), order="x", kind="stable"))          # duplicate anchors (dr == 0 and dq == 0)
+    off, a = fuzz.batch(reads)
+    for kw in (dict(), dict(max_skip=0), dict(max_skip=1, max_iter=1), dict(min_cnt=0, min_sc=-5), dict(min_cnt=1, min_sc=0, bw=0),
+               dict(max_dist_x=0, max_dist_y=0), dict(max_iter=0), dict(bw=100000, max_dist_x=100000, max_dist_y=100000, max_iter=100000)):
+        ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=8)
+        binding.set_counting(True)
+        res = binding.chain_batch(binding.Params(**kw), off, a)
+        binding.set_counting(False)
+        _compare_batch(res, ref, off, kw)
+        assert res["stats"].cells_ref == ref["stats"].cells, kw
+        res = binding.chain_batch(binding.Params(**kw), off, a)          # the non-counting kernel variant
+        _compare_batch(res, ref, off, kw)
+
+
+def test_one_very_long_read(binding, oracle):
+    """A single 300k-anchor read with a window that stays at the max_iter clamp (int32 indices, deep look-back throughout)."""
+    rng = np.random.default_rng(3)
+    off, a = fuzz.batch([fuzz.dense_repeat(rng, 300000, width=200000, qwidth=200000)])
+    for kw in (dict(max_iter=400), dict(max_iter=5000, max_skip=3)):
+        ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=1)
+        res = binding.chain_batch(binding.Params(**kw), off, a)
+        _compare_batch(res, ref, off, kw)
