@@ -125,6 +125,10 @@ int64_t mm2b_launch_count(void);
  * Only valid when the workspace was created with the environment variable MM2B_KEEP_FPV=1 (costs 12 B/anchor extra). */
 int mm2b_ws_copy_fpv(mm2b_workspace_t *ws, void *stream, int64_t n_anchors, int32_t *h_f, int32_t *h_p, int32_t *h_v);
 
+/* Range-check violations recorded by the debug build of the library (libmm2chain_b200_dbg.so, -DMM2B_DEBUG_CHECKS): bit 31 set means
+ * "this is the checking build", the low bits are violation codes.  Always 0 in the release build. */
+unsigned mm2b_debug_flags(void);
+
 /* Measured INT32 issue peak of `device` in G int-ops/s (IADD3/LOP3/IMNMX mix, all SMs), for the roofline. */
 double mm2b_measure_int32_peak(int device);
 

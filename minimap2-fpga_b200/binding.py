@@ -20,7 +20,7 @@ READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
-           "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_measure_int32_peak",
+           "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
            "mm_chain_dp"]
 
 
@@ -87,6 +87,7 @@ def load():
     L.mm2b_ws_chain_kernel_ms.restype, L.mm2b_ws_chain_kernel_ms.argtypes = C.c_double, [vp]
     L.mm2b_launch_count.restype = i64
     L.mm2b_ws_copy_fpv.restype, L.mm2b_ws_copy_fpv.argtypes = i32, [vp, vp, i64, vp, vp, vp]
+    L.mm2b_debug_flags.restype, L.mm2b_debug_flags.argtypes = C.c_uint, []
     L.mm2b_measure_int32_peak.restype, L.mm2b_measure_int32_peak.argtypes = C.c_double, [i32]
     L.mm_chain_dp.restype = vp
     L.mm_chain_dp.argtypes = [i32] * 7 + [C.c_float, i32, i32, i64, vp, C.POINTER(i32), C.POINTER(vp), vp, i32]

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libmm2chain_b200.so")
+LIB_DBG = os.path.join(HERE, "libmm2chain_b200_dbg.so")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -54,6 +55,13 @@ def build_all(verbose=False, force=False):
         objs.append(o)
     if force or _newer(LIB, objs):
         _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-lpthread"], verbose)
+    # range-checking twin of the library (same sources, kernels compiled with -DMM2B_DEBUG_CHECKS); used only by tests
+    dbg_obj = os.path.join(OBJ, "chain_kernels_dbg.cu.o")
+    ksrc = os.path.join(HERE, "csrc/chain_kernels.cu")
+    if force or _newer(dbg_obj, [ksrc] + hdrs):
+        _run([NVCC] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-DMM2B_DEBUG_CHECKS"] + INC + ["-c", ksrc, "-o", dbg_obj], verbose)
+    if force or _newer(LIB_DBG, [dbg_obj] + objs[1:]):
+        _run([NVCC] + ARCH + ["-shared", "-o", LIB_DBG, dbg_obj] + objs[1:] + ["-cudart", "static", "-lpthread"], verbose)
     return LIB
 
 

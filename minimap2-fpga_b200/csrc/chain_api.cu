@@ -194,6 +194,8 @@ double mm2b_ws_chain_kernel_ms(mm2b_workspace_t *ws)
 	return (double)ms;
 }
 
+unsigned mm2b_debug_flags(void) { return debug_flags(); }
+
 double mm2b_measure_int32_peak(int device)
 {
 	count_launches(6);

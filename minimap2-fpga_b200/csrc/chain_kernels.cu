@@ -39,6 +39,16 @@ constexpr int CTAS_PER_SM = MM2B_WARPS_PER_SM / WARPS_PER_CTA;
 constexpr int32_t MARK_SUCC = 0x7ffffffe;   // "has a successor" (chain.c:351); DP stamps are anchor indices < 2^31-2
 constexpr int SEG_SHIFT = 48;               // MM_SEED_SEG_SHIFT, mmpriv.h:22
 
+// Debug build (-DMM2B_DEBUG_CHECKS, libmm2chain_b200_dbg.so): every index into the per-read scratch is range-checked and
+// violations are OR-ed into a device flag word (mm2b_debug_flags()).  compute-sanitizer is closed on this GPU pool, so this is
+// the memory-safety net the tests use (tests/test_gpu_debug_build.py).  The release build compiles the checks away.
+#ifdef MM2B_DEBUG_CHECKS
+__device__ unsigned g_dbg_flags = 0;
+#define MM2B_CHK(cond, code) do { if (!(cond)) atomicOr(&g_dbg_flags, (code)); } while (0)
+#else
+#define MM2B_CHK(cond, code) do { } while (0)
+#endif
+
 struct W16 { uint64_t x, y; };          // (first-anchor x, start-in-PATH << 32 | chain index); 8-byte aligned on purpose
 
 struct ReadCtx {
@@ -122,6 +132,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 					xj = q.x, yj = q.y, fj = q.z, pj = q.w;
 					if (GENERAL) sidj = (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff);
 				} else {                                           // deep look-back: L1/L2
+					MM2B_CHK(j >= 0 && j < i, 0x1);
 					const ulonglong2 t = __ldg(rc.A + j);
 					xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j];
 					sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
@@ -188,6 +199,8 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		}
 		// stamps, then hits
 		if (valid && pj >= st) {
+			MM2B_CHK(pj < j && pj > i - RING - 32 - 5000000, 0x2);
+			MM2B_CHK(DEEP || pj >= ring_lo, 0x4);
 			if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i;
 			else rc.T[pj] = i;
 		}
@@ -266,6 +279,7 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 		scan_predecessors<GENERAL, DEEP, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
 		// f[i], p[i], v[i] (chain.c:236-237): one lane publishes them to the anchor's slot; untouched if no predecessor won
 		int32_t v_prev;
+		MM2B_CHK(max_j < i && max_j >= -1 && (max_j < 0 || max_j >= st) && (DEEP || max_j < 0 || max_j >= ring_lo), 0x8);
 		if (DEEP && max_j < ring_lo) v_prev = max_j >= 0 ? rc.V[max_j] : 0;
 		else v_prev = ring.b[max_j & (RING - 1)].x;
 		if (lane == 0 && max_j >= 0) {
@@ -424,6 +438,7 @@ __device__ void flag_sort_by_x_lane0(W16 *w, int n, int *sm /* >= 768 ints */, i
 {
 	int *head = sm, *tail = sm + 256, *cnt = sm + 512;
 	int n_work = 0;
+	MM2B_CHK(work_cap >= 1, 0x10);
 	work[n_work++] = make_int3(0, n, 56);
 	while (n_work > 0) {
 		const int3 job = work[--n_work];
@@ -450,6 +465,7 @@ __device__ void flag_sort_by_x_lane0(W16 *w, int n, int *sm /* >= 768 ints */, i
 			for (int k = 0; k < 256; ++k) {
 				const int beg = tail[k] - cnt[k];
 				if (cnt[k] > 64) {
+					MM2B_CHK(n_work < work_cap, 0x10);
 					if (n_work < work_cap) work[n_work++] = make_int3(job.x + beg, cnt[k], next);
 					else insertion_by_x(a + beg, cnt[k]);   // unreachable: work_cap >= n/65 + 1 pending ranges always fit
 				} else if (cnt[k] > 1) insertion_by_x(a + beg, cnt[k]);
@@ -488,6 +504,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 			key = (uint64_t)(uint32_t)F[j] << 32 | (uint32_t)j;
 		}
 		const unsigned m = __ballot_sync(FULL, is_end);
+		MM2B_CHK(n_u + __popc(m) <= n, 0x20);
 		if (is_end) U[n_u + __popc(m & lanemask_lt(lane))] = key;
 		n_u += __popc(m);
 	}
@@ -530,6 +547,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 			int j = (int32_t)key;
 			int32_t w = P[j];
 			for (;;) {                                       // do-while of chain.c:379-383: the first anchor is taken unconditionally
+				MM2B_CHK(n_v < n && j >= 0 && j < n, 0x40);
 				PATH[n_v++] = j;
 				const int32_t pj = w <= -2 ? -3 - w : w;
 				if (w >= -1) P[j] = -3 - w;
@@ -612,6 +630,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 		const uint64_t uu = U[src];
 		const int len = (int32_t)uu;
 		if (lane == 0) rc.UF[i] = uu;
+		MM2B_CHK(src >= 0 && src < n_u && k0 >= 0 && len >= 1 && k0 + len <= n_v && pos + len <= n_v, 0x80);
 		for (int j = lane; j < len; j += 32) OUTIDX[pos + j] = PATH[k0 + (len - 1 - j)];
 		pos += len;
 	}
@@ -889,6 +908,18 @@ int launch_emit(const EmitArgs &args, int n_sms, cudaStream_t stream)
 	if (blocks > cap) blocks = cap;
 	emit_kernel<<<(int)blocks, 256, 0, stream>>>(args);
 	return 1;
+}
+
+unsigned debug_flags()
+{
+#ifdef MM2B_DEBUG_CHECKS
+	unsigned f = 0;
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(&f, g_dbg_flags, sizeof(f));
+	return f | 0x80000000u;         // top bit: this IS the checking build
+#else
+	return 0;
+#endif
 }
 
 double measure_int32_peak(int device)

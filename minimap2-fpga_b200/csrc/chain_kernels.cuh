@@ -47,5 +47,6 @@ int launch_offsets(int64_t n_reads, const int32_t *n_u, const int32_t *n_v, int6
                    int64_t *tile_scratch, cudaStream_t stream);
 int launch_emit(const EmitArgs &args, int n_sms, cudaStream_t stream);
 double measure_int32_peak(int device);
+unsigned debug_flags();          // range-check violations seen so far (0x80000000 | codes) in the -DMM2B_DEBUG_CHECKS build, else 0
 
 }  // namespace mm2b
