@@ -102,6 +102,30 @@ WORKLOADS = {
 }
 
 
+def bind_near_gpu(torch, device_index):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the CPUs of the GPU's NUMA node, so that
+    eight ranks do not push all their H2D/D2H traffic through one socket.  Best effort: silently skipped where sysfs says nothing."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/" % (dom, bus, dev)
+        cpus = open(path + "local_cpulist").read().strip()
+        node = open(path + "numa_node").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        if ids and len(ids) < (os.cpu_count() or 1):
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": cpus}
+    except Exception as e:      # noqa: BLE001
+        return {"numa_node": None, "error": repr(e)[:80]}
+
+
 def make_workload(name, n_reads, seed):
     wl = load_package("workload")
     t0 = time.time()
@@ -176,6 +200,7 @@ def main():
     if not torch.cuda.is_available() or L.mm2b_cuda_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = bind_near_gpu(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -287,7 +312,7 @@ def main():
                              "note": "the path is INT32-issue bound, not HBM bound (SURVEY.md 8d): see roofline_int32"},
                 "roofline_int32": {"bound": "int32_issue", "achieved": int_ach, "peak": int_peak, "unit": "Gop/s", "frac": int_ach / int_peak if int_peak > 0 else None,
                                    "ops_per_cell": INT_OPS_PER_CELL, "peak_source": "measured live: mm2b_measure_int32_peak (IADD/LOP3/IMNMX mix on all SMs)"},
-                "cpu_baseline": cpu, "workload_gen_s": gen_s}
+                "cpu_baseline": cpu, "workload_gen_s": gen_s, "host_affinity_rank0": affinity}
         print(json.dumps(line), flush=True)
     for v in pin.values():
         v.free()
