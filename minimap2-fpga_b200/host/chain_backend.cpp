@@ -658,8 +658,16 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
 	Job job;
 	job.par = par, job.n_reads = n_reads, job.off = off, job.a = a;
 	job.n_u = n_u, job.n_v = n_v, job.status = status, job.u_off = u_off, job.b_off = b_off, job.u = u, job.b = b;
-	for (int64_t r0 = 0; r0 < n_reads;) {       // cut into sub-batches of <= sub_anchors anchors (a larger single read stands alone)
-		const int64_t lim = off[r0] + g.sub_anchors;
+	// Cut into sub-batches of <= sub_anchors anchors (a larger single read stands alone).  The first and last few are smaller:
+	// the first copy and the last kernel + copy-back are the only stages nothing overlaps with, so they should be short.
+	for (int64_t r0 = 0; r0 < n_reads;) {
+		int64_t size = g.sub_anchors;
+		const int64_t done = off[r0], left = n_anchors - off[r0];
+		if (n_anchors > 6 * g.sub_anchors) {
+			if (done < g.sub_anchors / 4 || left <= g.sub_anchors / 2) size = g.sub_anchors / 4;
+			else if (done < g.sub_anchors || left <= 3 * g.sub_anchors / 2) size = g.sub_anchors / 2;
+		}
+		const int64_t lim = off[r0] + size;
 		int64_t r1 = std::upper_bound(off + r0 + 1, off + n_reads + 1, lim) - off - 1;
 		if (r1 <= r0) r1 = r0 + 1;
 		if (r1 - r0 > (1 << 20)) r1 = r0 + (1 << 20);
