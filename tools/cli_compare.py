@@ -1,5 +1,5 @@
 import os, sys, time, subprocess, hashlib, tempfile
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from __graft_entry__ import load_package
 seqsim = load_package("seqsim")
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4000

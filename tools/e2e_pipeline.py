@@ -1,5 +1,5 @@
 import sys, time, os, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from __graft_entry__ import load_package
 b = load_package("binding"); wl = load_package("workload")
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
