@@ -8,7 +8,8 @@
 //     {x_lo, y_lo, f, p | v, t} live in a per-warp shared-memory ring (6 KB); deeper look-back (rare) reads L2;
 //   * the inner loop over predecessors j = i-1 .. st is evaluated 32 lanes at a time; the order-dependent parts of
 //     the reference loop (strict '>' running max, t[] stamps, the n_skip counter and its break, chain.c:226-233)
-//     are recovered exactly with a shuffle prefix-max, ballots and a closed-form (Lindley) prefix-min for n_skip;
+//     are recovered exactly from warp votes: REDUX.MAX + ballots for the records, stamp-then-read for t[], and a
+//     closed-form (Lindley) evaluation of the n_skip counter on the two vote masks;
 //   * chain ends / peaks, the descending sort, the priority backtrack and the final order by reference position
 //     (including the reference's unstable radix-sort tie order) run in the same warp right after the fill while
 //     f/p/v are still in L1/L2; a scan + gather kernel pair then packs u[]/b[] in read order.
