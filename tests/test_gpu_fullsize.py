@@ -73,3 +73,35 @@ def test_rechaining_own_output_is_idempotent(binding, oracle, pkg):
     for k, r in enumerate(single):
         assert r2["u"][r2["u_off"][k]] == r1["u"][r1["u_off"][r]]
         assert np.array_equal(r2["b"][r2["b_off"][k]:r2["b_off"][k] + r2["n_v"][k]], reads[k])
+
+
+def test_real_seeding_replay_against_reference_outputs(binding, pkg, tmp_path):
+    """The reference itself as the checker, at scale: simulate ONT reads at the sequence level against a 100 Mbp reference, let
+    the reference CLI (built in place, software chaining) seed and chain them while the capture shim records every mm_chain_dp
+    call, then replay the captured anchors through the GPU batch call and compare with the reference's OWN u[] / b[]."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from oracle import dumpio
+    cli = os.path.join(ROOT, "oracle", "_ref", "minimap2-sw")
+    if not os.path.exists(cli):
+        pytest.skip("oracle/_ref/minimap2-sw was not built (needs /root/reference at build time)")
+    seqsim = pkg("seqsim")
+    ref = seqsim.gen_reference(100_000_000, seed=1)
+    seqsim.write_fasta(str(tmp_path / "ref.fa"), [("chr1", ref)])
+    seqsim.write_fasta(str(tmp_path / "q.fa"), seqsim.gen_reads(ref, 6000, 10000, 0.10, seed=23))
+    dump = str(tmp_path / "d.bin")
+    subprocess.run([cli, "-t", "16", "-x", "map-ont", str(tmp_path / "ref.fa"), str(tmp_path / "q.fa")], env=dict(os.environ, MM2_DUMP=dump),
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    recs = dumpio.read_dump(dump)
+    assert len(recs) >= 5900
+    off, a = dumpio.to_batch(recs)
+    res = binding.chain_batch(binding.Params(**recs[0]["par"].as_dict()), off, a)
+    bad = 0
+    for r, rec in enumerate(recs):
+        nu, nv = int(res["n_u"][r]), int(res["n_v"][r])
+        ok = nu == len(rec["u"]) and nv == len(rec["b"]) and (int(res["status"][r]) == 2) == (not rec["u_null"]) \
+            and np.array_equal(res["u"][res["u_off"][r]:res["u_off"][r] + nu], rec["u"]) \
+            and np.array_equal(res["b"][res["b_off"][r]:res["b_off"][r] + nv], rec["b"])
+        bad += int(not ok)
+    assert bad == 0, "%d of %d reads differ from the reference's own output" % (bad, len(recs))
