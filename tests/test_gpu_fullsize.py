@@ -44,9 +44,11 @@ def test_full_size_batches_bit_exact(binding, oracle, pkg, name, n_reads):
     assert res_c["stats"].cells_ref == ref["stats"].cells
     # properties that hold at any size
     n_v = res["n_v"].astype(np.int64)
-    cnt_from_u = np.add.reduceat((res["u"] & np.uint64(0xffffffff)).astype(np.int64), np.minimum(res["u_off"][:-1], len(res["u"]) - 1))
-    has = res["n_u"] > 0
-    assert np.array_equal(cnt_from_u[has], n_v[has])                     # sum of chain lengths == anchors returned
+    n_u = res["n_u"].astype(np.int64)         # u[] is packed per sub-batch with gaps between sub-batches: sum exactly n_u entries per read
+    starts = np.repeat(res["u_off"][:-1] - np.concatenate([[0], np.cumsum(n_u)[:-1]]), n_u) + np.arange(int(n_u.sum()))
+    lens = (res["u"][starts] & np.uint64(0xffffffff)).astype(np.int64)
+    cnt_from_u = np.bincount(np.repeat(np.arange(len(n_u)), n_u), weights=lens, minlength=len(n_u)).astype(np.int64)
+    assert np.array_equal(cnt_from_u, n_v)                               # sum of chain lengths == anchors returned
     assert int(n_v.sum()) <= len(a) and np.all(n_v <= np.diff(off))
     # every returned anchor is an input anchor of the same read
     key = lambda arr: arr["x"].astype(np.uint64) * np.uint64(1000003) ^ arr["y"]
