@@ -304,7 +304,7 @@ def main():
         line = {"metric": "chain_dp_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": config, "reads_per_s": tot_reads / (ms_value * 1e-3), "anchors_per_s": tot_anchors / (ms_value * 1e-3),
-                "cells_per_step": int(tot_cells), "cells_issued_per_step_rank0": int(st.cells_issued), "anchors_per_step": int(tot_anchors),
+                "cells_per_step": int(tot_cells), "cells_issued_per_step_rank0": int(st.cells_issued), "window_cells_per_step_rank0": int(st.window_cells), "anchors_per_step": int(tot_anchors),
                 "e2e": e2e, "gpu_launches": int(launches_value), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "chain_reads_kernel", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": hbm_ach / peaks["hbm_gbs"], "traffic": captured_traffic(args.workload, args.reads), "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",

@@ -58,6 +58,7 @@ typedef struct {
 	int64_t cells_issued;            /* GPU lanes evaluated (32 per chunk); 0 unless counting is on */
 	int64_t cells_ref;               /* iterations of the reference's inner j loop (chain.c:197) these reads take, `continue`d ones
 	                                    included, up to the max_skip break: the "cell" of the GCUPS metric; 0 unless counting is on */
+	int64_t window_cells;            /* sum over anchors of the window size i - st after the max_iter clamp (chain.c:192-193); 0 unless counting is on */
 	int64_t n_general_reads;         /* reads that took the general (multi-segment / cDNA / gap_scale != 1) scoring path */
 	double  h2d_ms, kernel_ms, d2h_ms; /* device-side timings of the last host-buffer call (CUDA events), 0 for device calls */
 } mm2b_stats_t;

@@ -39,7 +39,7 @@ class Params(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "cells_ref", "n_general_reads")] + \
+    _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "cells_ref", "window_cells", "n_general_reads")] + \
                [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")]
 
     def as_dict(self):

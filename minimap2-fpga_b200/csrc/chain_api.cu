@@ -153,7 +153,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	int prev = -1;
 	cudaGetDevice(&prev);
 	if (prev != ws->device) cudaSetDevice(ws->device);
-	unsigned long long c[3] = {0, 0, 0};
+	unsigned long long c[4] = {0, 0, 0, 0};
 	int64_t tot[2] = {0, 0};
 	bool ok = cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize")
 	       && cuda_ok(cudaMemcpy(c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
@@ -164,7 +164,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	memset(st, 0, sizeof(*st));
 	st->n_reads = ws->last_reads, st->n_anchors = ws->last_anchors;
 	st->n_chains = tot[0], st->n_chained = tot[1];
-	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1], st->cells_ref = (int64_t)c[2];
+	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1], st->cells_ref = (int64_t)c[2], st->window_cells = (int64_t)c[3];
 	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
 	return ok ? MM2B_OK : MM2B_ERR_CUDA;
 }

@@ -303,7 +303,7 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 // ---------------------------------------------------------------------------------------------------------------
 template <bool GENERAL, bool COUNT>
 __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, int32_t *smem, int lane,
-                        unsigned long long &n_chunks64, unsigned long long &n_cells64)
+                        unsigned long long &n_chunks64, unsigned long long &n_cells64, unsigned long long &n_window64)
 {
 	Ring ring;
 	ring.a = (int4*)smem, ring.b = (int2*)(smem + 4 * RING);
@@ -344,6 +344,7 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 			ring.a[s] = make_int4((int32_t)x, (int32_t)y, q_span, -1);
 			ring.b[s] = make_int2(q_span, st_k);
 		}
+		if (COUNT && in) n_window64 += (unsigned)(k - st_k);             // per-lane partial sums of the window sizes (chain.c:192-193)
 		unsigned todo = __ballot_sync(FULL, in && st_k < k);
 		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
 		const bool deep_block = __any_sync(FULL, in && st_k < ring_lo);    // some window in this block reaches below the ring
@@ -648,7 +649,7 @@ chain_reads_kernel(const BatchArgs args)
 	__shared__ __align__(16) int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * RING];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int32_t *ring = smem_ring[warp];
-	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0;
+	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0, n_window = 0;
 
 	for (;;) {
 		int64_t slot = 0;
@@ -692,9 +693,9 @@ chain_reads_kernel(const BatchArgs args)
 		__syncwarp();
 		if (general) {
 			++n_general;
-			dp_fill<true, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
+			dp_fill<true, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells, n_window);
 		} else {
-			dp_fill<false, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells);
+			dp_fill<false, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells, n_window);
 		}
 		if (args.dbg_fpv) {      // test hook (MM2B_KEEP_FPV=1): keep f/p/v as they are at chain.c:238, before the extraction reuses v
 			int32_t *d = args.dbg_fpv + o;
@@ -705,7 +706,12 @@ chain_reads_kernel(const BatchArgs args)
 		extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
 		if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status;
 	}
+	if (COUNT) {
+#pragma unroll
+		for (int d = 16; d; d >>= 1) n_window += __shfl_xor_sync(FULL, n_window, d);
+	}
 	if (lane == 0) {
+		if (n_window) atomicAdd(&args.counters[3], n_window);
 		if (n_chunks) atomicAdd(&args.counters[0], n_chunks);
 		if (n_general) atomicAdd(&args.counters[1], n_general);
 		if (n_cells) atomicAdd(&args.counters[2], n_cells);

@@ -23,7 +23,7 @@ struct BatchArgs {
 	int32_t *n_u, *n_v, *status;
 	const int32_t *order;           // processing order (longest reads first) or nullptr
 	int *work_counter;              // persistent-warp work queue
-	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells
+	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells, [3] window cells
 	int32_t *dbg_fpv;               // optional 3 x n_anchors int32 (f, p, v) copy for tests, or nullptr
 	int64_t n_anchors;
 	int count_cells;                // tally reference-semantics cells / issued chunks (statistics only; costs kernel time)

@@ -131,13 +131,13 @@ def test_kernel_cell_tally_equals_oracle(binding, oracle, pkg):
     binding.set_counting(True)
     res = binding.chain_batch(binding.Params(), off, a)
     _compare_batch(res, ref, off, "synth")
-    assert res["stats"].cells_ref == ref["stats"].cells
+    assert res["stats"].cells_ref == ref["stats"].cells and res["stats"].window_cells == ref["stats"].window_cells
     assert res["stats"].cells_issued >= res["stats"].cells_ref
     off, a = fuzz.mixed_batch(31, n_reads=48)
     for kw in (dict(), dict(max_skip=2, max_iter=40)):
         ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=4)
         res = binding.chain_batch(binding.Params(**kw), off, a)
-        assert res["stats"].cells_ref == ref["stats"].cells, kw
+        assert res["stats"].cells_ref == ref["stats"].cells and res["stats"].window_cells == ref["stats"].window_cells, kw
         _compare_batch(res, ref, off, kw)
     binding.set_counting(False)
 
