@@ -181,3 +181,26 @@ def test_one_very_long_read(binding, oracle):
         ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=1)
         res = binding.chain_batch(binding.Params(**kw), off, a)
         _compare_batch(res, ref, off, kw)
+
+
+def test_error_codes_and_empty_batches(binding):
+    """The mm2b_* calls report misuse with return codes + mm2b_last_error() (they never exit); empty batches are fine."""
+    import ctypes as C
+    L = binding.load()
+    par = binding.Params()
+    off = np.array([0, 5, 9], np.int64)
+    a = fuzz.collinear(np.random.default_rng(0), 9, 0)
+    small_u = np.empty(3, np.uint64)
+    with pytest.raises(binding.Mm2bError, match="u_cap and b_cap"):
+        binding.chain_batch(par, off, a, out={"u": small_u})
+    rc = L.mm2b_chain_batch(C.byref(par), 2, None, None, None, None, None, None, None, None, 0, None, 0, None)
+    assert rc == -2 and b"NULL" in L.mm2b_last_error()
+    res = binding.chain_batch(par, np.zeros(1, np.int64), np.empty(0, binding.ANCHOR))          # zero reads
+    assert len(res["n_u"]) == 0 and res["u_off"][0] == 0
+    res = binding.chain_batch(par, np.zeros(4, np.int64), np.empty(0, binding.ANCHOR))          # three empty reads
+    assert list(res["n_u"]) == [0, 0, 0] and list(res["status"]) == [0, 0, 0]
+    ws = L.mm2b_ws_create(0, 100, 10)
+    assert ws and L.mm2b_ws_bytes(ws) > 0
+    rc = L.mm2b_chain_batch_device(ws, C.byref(par), 11, 50, None, None, None, None, None, None, None, None, None, None)
+    assert rc == -3 and b"capacity" in L.mm2b_last_error()
+    L.mm2b_ws_destroy(ws)
