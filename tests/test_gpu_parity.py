@@ -204,3 +204,40 @@ def test_error_codes_and_empty_batches(binding):
     rc = L.mm2b_chain_batch_device(ws, C.byref(par), 11, 50, None, None, None, None, None, None, None, None, None, None)
     assert rc == -3 and b"capacity" in L.mm2b_last_error()
     L.mm2b_ws_destroy(ws)
+
+
+def test_random_parameter_sweep(binding, oracle):
+    """24 random parameter sets (degenerate values included) x 60 small random reads each, through both kernel variants."""
+    rng = np.random.default_rng(2026)
+    dom = dict(max_dist_x=[0, 50, 500, 5000], max_dist_y=[0, 50, 500, 5000], bw=[0, 10, 100, 500], max_skip=list(range(0, 31)),
+               max_iter=[0, 1, 5, 50, 5000], min_cnt=[0, 1, 2, 3, 4], min_sc=[-5, 0, 10, 40], is_cdna=[0, 1], n_segs=[1, 2, 3], gap_scale=[0.5, 1.0, 1.7])
+    for trial in range(24):
+        kw = {k: (float if k == "gap_scale" else int)(v[rng.integers(0, len(v))]) for k, v in dom.items()}
+        reads = []
+        for _ in range(60):
+            n = int(rng.integers(0, 120))
+            style = int(rng.integers(0, 4))
+            span = [1, 15, 19, 255][int(rng.integers(0, 4))]
+            if style == 0:
+                r = 1000 + np.cumsum(rng.integers(0, 40, n)); q = span + np.cumsum(rng.integers(0, 40, n))
+            elif style == 1:
+                r = rng.integers(0, 20000, n); q = rng.integers(span, 20000, n)
+            elif style == 2:
+                r = 500 + rng.integers(0, 6, n) * 17; q = span + rng.integers(0, 6, n) * 17
+            else:
+                r = 1000 + np.cumsum(rng.integers(1, 30, n)); q = span + np.cumsum(rng.integers(1, 30, n))
+            rev = (rng.integers(0, 2, n) if style == 3 else np.zeros(n, np.int64)).astype(np.uint64)
+            seg = rng.integers(0, kw["n_segs"], n).astype(np.uint64)
+            a = np.empty(n, binding.ANCHOR)
+            a["x"] = (rev << np.uint64(63)) | np.asarray(r, np.uint64)
+            a["y"] = (seg << np.uint64(48)) | (np.uint64(span) << np.uint64(32)) | np.asarray(q, np.uint64)
+            reads.append(a[np.argsort(a["x"], kind="stable")])
+        off, a = fuzz.batch(reads)
+        ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=4)
+        for counting in (False, True):
+            binding.set_counting(counting)
+            res = binding.chain_batch(binding.Params(**kw), off, a)
+            _compare_batch(res, ref, off, kw)
+            if counting:
+                assert res["stats"].cells_ref == ref["stats"].cells, kw
+        binding.set_counting(False)
