@@ -568,7 +568,9 @@ int mm2b_init(int n_devices, const int *devices)
 
 // hardware_init() replacement for hosts that do other start-up work next (the minimap2 CLI loads its index right after,
 // main.c:367-371): bring the devices up on a background thread; the first call that needs them waits for it.
-static std::thread g_init_thread;
+// heap-allocated and never destroyed: a host that exits without cleanup() (main.c returns early on several error paths) must
+// not run a joinable std::thread's destructor (std::terminate)
+static std::thread &g_init_thread = *new std::thread();
 static std::mutex g_init_mu;
 static int g_init_rc = MM2B_OK;
 
