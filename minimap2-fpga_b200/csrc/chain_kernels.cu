@@ -77,9 +77,7 @@ __device__ __forceinline__ int lowest_lane(unsigned m) { return __popc((m - 1u) 
 
 // Per-warp shared-memory ring: the most recent RING anchors, one slot each.
 //   slotA[s] = {x_lo, y_lo, f, p}   one 16-byte LDS fetches a predecessor
-//   slotB[s] = {v, t}               v = peak score on the path (chain.c:237); t = visit stamp (chain.c:229,233).  Until its
-//                                   anchor is processed, t holds that anchor's window start st (< its index, so it can
-//                                   never equal a later stamp) — the sequential step reads it back with a broadcast LDS.
+//   slotB[s] = {v, t}               v = peak score on the path (chain.c:237); t = visit stamp (chain.c:229,233)
 struct Ring {
 	int4 *a;
 	int2 *b;
@@ -124,7 +122,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		if (in_ring) {
 			const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
 			xj = q.x, yj = q.y, fj = q.z, pj = q.w;
-			if (GENERAL) sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
+			if (GENERAL) {
+				sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
+				__syncwarp();
+			}
 		} else {
 			xj = 0, yj = 0, fj = 0, pj = -1;
 			if (act) {
@@ -139,6 +140,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 					sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
 				}
 			}
+			__syncwarp();
 		}
 		// inside the window 0 <= dr <= max_dist_x, so the low words give dr exactly (chain.c:199)
 		const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)xj);
@@ -176,6 +178,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			sc += fj;
 		}
 		if (!valid) sc = INT_MIN;
+		if (GENERAL) __syncwarp();                            // the cost switch above branches per lane
 
 		// records: the largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane
 		// above max_f, i.e. the only one.  Otherwise walk from the first candidate up to it.
@@ -208,7 +211,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		__syncwarp();
 		int32_t tj;
 		if (in_ring) tj = ring.b[s].y;
-		else tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
+		else {
+			tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
+			__syncwarp();
+		}
 		const unsigned hitmask = __ballot_sync(FULL, valid && tj == i) & ~recmask;   // chain.c:229
 		// n_skip, whether the loop breaks in this chunk, and which records come before the break
 		bool broke = false;
@@ -265,15 +271,17 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 // The sequential step for one block of 32 anchors: the anchors flagged in `todo` (non-empty window), in index order.
 template <bool GENERAL, bool DEEP, bool COUNT>
 __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int base, int ring_lo,
-                                            unsigned todo, int32_t seg, unsigned &n_chunks, unsigned &n_cells)
+                                            unsigned todo, int32_t seg, int st_k, unsigned &n_chunks, unsigned &n_cells)
 {
 	while (todo) {
 		const int ii = lowest_lane(todo);
 		todo &= todo - 1;
 		const int i = base + ii;
 		const int si = i & (RING - 1);
-		const int4 me = ring.a[si];                    // broadcast reads: this anchor's own slot still holds its defaults
-		const int st = ring.b[si].y;
+		const int4 me = ring.a[si];                    // broadcast read: this anchor's own slot still holds its defaults
+		// The window start must come through a shuffle, not through shared memory: it bounds the chunk loop, and ptxas only
+		// treats the loop as warp-uniform (no BRA.DIV guards on the collectives inside) when the bound is a shuffle/vote result.
+		const int st = __shfl_sync(FULL, st_k, ii);
 		const int32_t q_span = me.z;
 		const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
 		int32_t max_f = q_span, max_j = -1;
@@ -298,7 +306,7 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 //
 // Anchors are taken 32 at a time.  For a block, every lane first finds its own anchor's window start st (chain.c:192-193)
 // by binary search — st_i = max(lower_bound{s : x_s + max_dist_x >= x_i}, i - max_iter) since the input is sorted by x —
-// and publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = st} to the ring.  Anchors whose window is empty
+// and publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = -1} to the ring.  Anchors whose window is empty
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool GENERAL, bool COUNT>
@@ -326,6 +334,7 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 			const ulonglong2 t = __ldg(A + k);
 			x = t.x, y = t.y;
 		}
+		__syncwarp();
 		// chain.c:192: first s in [st_carry, k] with !(x > a[s].x + max_dist_x); full 64-bit compare (strand/rid are in the high word)
 		int lo = st_carry, hi = in ? k : st_carry;
 		while (__any_sync(FULL, lo < hi)) {
@@ -334,6 +343,7 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 				if (x > __ldg(&A[mid].x) + win) lo = mid + 1;
 				else hi = mid;
 			}
+			__syncwarp();
 		}
 		int st_k = lo;
 		if (k - st_k > c.max_iter) st_k = k - c.max_iter;                                // chain.c:193
@@ -342,8 +352,9 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 			const int s = k & (RING - 1);
 			const int32_t q_span = (int32_t)(y >> 32 & 0xff);
 			ring.a[s] = make_int4((int32_t)x, (int32_t)y, q_span, -1);
-			ring.b[s] = make_int2(q_span, st_k);
+			ring.b[s] = make_int2(q_span, -1);
 		}
+		__syncwarp();
 		if (COUNT && in) n_window64 += (unsigned)(k - st_k);             // per-lane partial sums of the window sizes (chain.c:192-193)
 		unsigned todo = __ballot_sync(FULL, in && st_k < k);
 		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
@@ -351,14 +362,15 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 		st_carry = __shfl_sync(FULL, st_k, (n - base < 32 ? n - base : 32) - 1);
 		__syncwarp();
 
-		if (!deep_block) chain_block<GENERAL, false, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, n_chunks, n_cells);
-		else chain_block<GENERAL, true, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, n_chunks, n_cells);
+		if (!deep_block) chain_block<GENERAL, false, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
+		else chain_block<GENERAL, true, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
 		if (in) {                // one coalesced write of the block's f/p/v (needed by deep look-back and by the backtrack)
 			const int s = k & (RING - 1);
 			const int2 fp = *(const int2*)&ring.a[s].z;
 			const int32_t v = ring.b[s].x;
 			rc.F[k] = fp.x, rc.P[k] = fp.y, rc.V[k] = v;
 		}
+		__syncwarp();            // (see the note on convergence at the top of the kernel)
 		n_chunks64 += n_chunks, n_cells64 += n_cells;
 		n_chunks = 0, n_cells = 0;
 	}
@@ -376,15 +388,22 @@ __device__ void warp_radix_sort_u64(uint64_t *keys, uint64_t *tmp, int n, int *h
 	uint64_t diff = 0;
 	const uint64_t k0 = keys[0];
 	for (int k = lane; k < n; k += 32) diff |= keys[k] ^ k0;
+	__syncwarp();
 #pragma unroll
 	for (int d = 16; d; d >>= 1) diff |= __shfl_xor_sync(FULL, diff, d);
+	diff = __shfl_sync(FULL, diff, 0);          // same value in every lane already; the broadcast makes the `continue` below provably uniform
 	uint64_t *src = keys, *dst = tmp;
 	for (int shift = 0; shift < 64; shift += 8) {
 		if (((diff >> shift) & 0xff) == 0) continue;
 		for (int b = lane; b < 256; b += 32) hist[b] = 0;
 		__syncwarp();
-		for (int k = lane; k < n; k += 32) atomicAdd(&hist[(int)(src[k] >> shift & 0xff)], 1);
-		__syncwarp();
+		for (int base = 0; base < n; base += 32) {     // histogram without atomics (shared-memory atomics compile to retry loops
+			const int k = base + lane;                   // that cost ptxas its convergence proof for the whole kernel): the first
+			const int dig = k < n ? (int)(src[k] >> shift & 0xff) : 256;      // lane of each digit group adds the group size
+			const unsigned peers = __match_any_sync(FULL, dig);
+			if (k < n && (peers & lanemask_lt(lane)) == 0) hist[dig] += __popc(peers);
+			__syncwarp();
+		}
 		{	// exclusive prefix over 256 bins: 8 consecutive bins per lane
 			int loc[8], sum = 0;
 #pragma unroll
@@ -505,9 +524,11 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 			if (j < 0) j = k;
 			key = (uint64_t)(uint32_t)F[j] << 32 | (uint32_t)j;
 		}
+		__syncwarp();
 		const unsigned m = __ballot_sync(FULL, is_end);
 		MM2B_CHK(n_u + __popc(m) <= n, 0x20);
 		if (is_end) U[n_u + __popc(m & lanemask_lt(lane))] = key;
+		__syncwarp();
 		n_u += __popc(m);
 	}
 	__syncwarp();
@@ -518,6 +539,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 	if (n_u > 1) {
 		if (n_u <= 32) {
 			const uint64_t key = lane < n_u ? U[lane] : 0;
+			__syncwarp();
 			int rank = 0;
 			for (int t = 0; t < n_u; ++t) {     // two ends can share a peak => equal keys: break ties by position
 				const uint64_t kt = __shfl_sync(FULL, key, t);
@@ -570,6 +592,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 			else n_v = n_v0;
 		}
 	}
+	__syncwarp();
 	n_v = __shfl_sync(FULL, n_v, 0);
 	n_u = __shfl_sync(FULL, n_kept, 0);
 	__syncwarp();
@@ -596,6 +619,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 				w.y = (uint64_t)(uint32_t)k0 << 32 | (uint32_t)i;
 				W[i] = w;
 			}
+			__syncwarp();
 			carry += __shfl_sync(FULL, incl, 31);
 		}
 	}
@@ -605,6 +629,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 			W16 w0 = {0, 0}, w1 = {0, 0};
 			if (lane < n_u) w0 = W[lane];
 			if (lane + 32 < n_u) w1 = W[lane + 32];
+			__syncwarp();
 			int r0 = 0, r1 = 0;
 			for (int t = 0; t < n_u; ++t) {
 				const uint64_t xt = W[t].x;
@@ -634,6 +659,7 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 		if (lane == 0) rc.UF[i] = uu;
 		MM2B_CHK(src >= 0 && src < n_u && k0 >= 0 && len >= 1 && k0 + len <= n_v && pos + len <= n_v, 0x80);
 		for (int j = lane; j < len; j += 32) OUTIDX[pos + j] = PATH[k0 + (len - 1 - j)];
+		__syncwarp();
 		pos += len;
 	}
 	__syncwarp();
@@ -642,6 +668,11 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 // ---------------------------------------------------------------------------------------------------------------
 // K1: persistent warp-per-read kernel
 // ---------------------------------------------------------------------------------------------------------------
+// Convergence note: every lane-dependent `if` / lane-strided loop in this kernel is followed by an explicit __syncwarp()
+// before the next loop back-edge or warp collective.  Without it ptxas cannot prove that the warp is converged anywhere inside
+// the persistent loop and guards EVERY shuffle/vote/redux with a `BRA.DIV` + `WARPSYNC.COLLECTIVE` slow path (2 extra
+// instructions per collective: ~16 of the ~150 per anchor).  Found by bisecting SASS; one missing __syncwarp() after the
+// `if (lane == 0) ...` at the end of a read was enough to poison the whole kernel.
 template <bool COUNT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 chain_reads_kernel(const BatchArgs args)
@@ -654,6 +685,7 @@ chain_reads_kernel(const BatchArgs args)
 	for (;;) {
 		int64_t slot = 0;
 		if (lane == 0) slot = atomicAdd(args.work_counter, 1);
+		__syncwarp();
 		slot = __shfl_sync(FULL, slot, 0);
 		if (slot >= args.n_reads) break;
 		const int64_t r = args.order ? args.order[slot] : slot;
@@ -661,6 +693,7 @@ chain_reads_kernel(const BatchArgs args)
 		const int64_t n64 = args.off[r + 1] - o;
 		if (n64 <= 0) {                                                               // chain.c:38-41
 			if (lane == 0) args.n_u[r] = 0, args.n_v[r] = 0, args.status[r] = MM2B_READ_EMPTY;
+			__syncwarp();
 			continue;
 		}
 		ReadCtx rc;
@@ -681,6 +714,7 @@ chain_reads_kernel(const BatchArgs args)
 			seg_diff |= (uint32_t)(y >> SEG_SHIFT & 0xff) ^ seg0;
 			rc.T[k] = 0;
 		}
+		__syncwarp();
 #pragma unroll
 		for (int d = 16; d; d >>= 1) {
 			sum += __shfl_xor_sync(FULL, sum, d);
@@ -688,7 +722,8 @@ chain_reads_kernel(const BatchArgs args)
 		}
 		// `.01 * (float)sum_qspan / n` — double arithmetic on a float-rounded sum, rounded once more to float
 		const float avg = __double2float_rn(__ddiv_rn(__dmul_rn(.01, (double)__ull2float_rn(sum)), (double)n64));
-		const bool general = seg_diff != 0 || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24) || args.par.bw < 0
+		// (through a vote so that ptxas sees a warp-uniform branch: see the convergence note above)
+		const bool general = __any_sync(FULL, seg_diff != 0) || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24) || args.par.bw < 0
 		                  || args.par.n_segs > 1 || args.par.max_dist_x <= 0 || args.par.max_dist_y <= 0;
 		__syncwarp();
 		if (general) {
@@ -705,6 +740,7 @@ chain_reads_kernel(const BatchArgs args)
 		int n_u = 0, n_v = 0, status = MM2B_READ_OK;
 		extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
 		if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status;
+		__syncwarp();
 	}
 	if (COUNT) {
 #pragma unroll
