@@ -286,15 +286,10 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 		const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
 		int32_t max_f = q_span, max_j = -1;
 		scan_predecessors<GENERAL, DEEP, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
-		// f[i], p[i], v[i] (chain.c:236-237): one lane publishes them to the anchor's slot; untouched if no predecessor won
-		int32_t v_prev;
+		// f[i], p[i] (chain.c:236): one lane publishes them to the anchor's slot; untouched if no predecessor won.
+		// v[i] is not needed by the scan at all; it is filled in per block afterwards (dp_fill).
 		MM2B_CHK(max_j < i && max_j >= -1 && (max_j < 0 || max_j >= st) && (DEEP || max_j < 0 || max_j >= ring_lo), 0x8);
-		if (DEEP && max_j < ring_lo) v_prev = max_j >= 0 ? rc.V[max_j] : 0;
-		else v_prev = ring.b[max_j & (RING - 1)].x;
-		if (lane == 0 && max_j >= 0) {
-			*(int2*)&ring.a[si].z = make_int2(max_f, max_j);
-			ring.b[si].x = v_prev > max_f ? v_prev : max_f;
-		}
+		if (lane == 0 && max_j >= 0) *(int2*)&ring.a[si].z = make_int2(max_f, max_j);
 		__syncwarp();
 	}
 }
@@ -364,11 +359,31 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 
 		if (!deep_block) chain_block<GENERAL, false, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
 		else chain_block<GENERAL, true, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
-		if (in) {                // one coalesced write of the block's f/p/v (needed by deep look-back and by the backtrack)
+		// Block epilogue.  v[i] = max(f[i], v[p[i]]) (chain.c:237) is the maximum of f along the chain behind i.  Inside the block
+		// it is resolved by pointer jumping over the lanes (5 rounds cover 32 anchors); a chain that leaves the block picks up the
+		// finished v of an earlier block from the ring (or from HBM when it reaches below the ring).  Then one coalesced write
+		// of the block's f/p/v (needed by deep look-back and by the backtrack).
+		{
 			const int s = k & (RING - 1);
-			const int2 fp = *(const int2*)&ring.a[s].z;
-			const int32_t v = ring.b[s].x;
-			rc.F[k] = fp.x, rc.P[k] = fp.y, rc.V[k] = v;
+			int2 fp = make_int2(0, -1);
+			if (in) fp = *(const int2*)&ring.a[s].z;
+			__syncwarp();
+			int32_t v = fp.x, pp = fp.y;
+#pragma unroll
+			for (int r = 0; r < 5; ++r) {
+				const bool inb = pp >= base;
+				const int src = inb ? pp - base : lane;
+				const int32_t vs = __shfl_sync(FULL, v, src), ps = __shfl_sync(FULL, pp, src);
+				if (inb) v = v > vs ? v : vs, pp = ps;
+			}
+			if (in) {
+				if (pp >= 0) {
+					const int32_t v_prev = pp >= ring_lo ? ring.b[pp & (RING - 1)].x : rc.V[pp];
+					v = v > v_prev ? v : v_prev;
+				}
+				ring.b[s].x = v;
+				rc.F[k] = fp.x, rc.P[k] = fp.y, rc.V[k] = v;
+			}
 		}
 		__syncwarp();            // (see the note on convergence at the top of the kernel)
 		n_chunks64 += n_chunks, n_cells64 += n_cells;
