@@ -193,12 +193,15 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			}
 		} else {
 			top = __reduce_max_sync(FULL, sc);
-			last = lowest_lane(__ballot_sync(FULL, sc == top));
+			// the nearest lane holding the maximum = the lane with the largest j among them: a second REDUX instead of vote + bit scan
+			last = jt - __reduce_max_sync(FULL, sc == top ? j : INT_MIN);
 			recmask = 1u << last;
-			for (int r = lowest_lane(cand); r != last;) {
-				recmask |= 1u << r;
-				const int32_t t = __shfl_sync(FULL, sc, r);
-				r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
+			if (cand & (recmask - 1u)) {                   // candidates before it: more than one record, walk them (rare)
+				for (int r = lowest_lane(cand); r != last;) {
+					recmask |= 1u << r;
+					const int32_t t = __shfl_sync(FULL, sc, r);
+					r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
+				}
 			}
 		}
 		// stamps, then hits
