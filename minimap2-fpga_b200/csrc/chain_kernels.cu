@@ -180,6 +180,18 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		if (!valid) sc = INT_MIN;
 		if (GENERAL) __syncwarp();                            // the cost switch above branches per lane
 
+		// Quiet tail: n_skip grows by at most one per visited cell, so once n_skip + (cells left in the window) <= max_skip the
+		// break of chain.c:230 cannot fire any more.  Then stamps, hits and n_skip cannot change the outcome and only the running
+		// maximum matters (strict '>', nearest first = the largest j among the lanes holding the chunk's maximum).  Short
+		// windows — most of a noisy read — are quiet from their first chunk.
+		if (n_skip + (jt - st + 1) <= c.max_skip) {
+			const int32_t best = __reduce_max_sync(FULL, sc);
+			const int32_t best_j = __reduce_max_sync(FULL, sc == best ? j : INT_MIN);   // unconditional: keeps the warp converged by construction
+			if (best > max_f) max_f = best, max_j = best_j;
+			if (COUNT) n_cells += n_act;
+			continue;
+		}
+
 		// records: the largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane
 		// above max_f, i.e. the only one.  Otherwise walk from the first candidate up to it.
 		unsigned recmask = 0;
@@ -575,45 +587,63 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 		__syncwarp();
 	}
 
-	// chain.c:374-391: greedy backtrack in score order.  Sequential by definition (a chain stops where a better one
-	// already passed), so one lane walks the p[] links; used-marks persist even when a candidate is dropped.
+	// chain.c:374-391: greedy backtrack in score order.  Chains are taken one after the other (a chain stops where a better
+	// one already passed; used-marks persist even when a candidate is dropped), but the walk along one chain is done 32 anchors
+	// at a time: the warp loads the aligned block of p[] that holds the next anchor of the walk, resolves the stretch of the
+	// path inside the block by pointer jumping over the lanes (links only point to smaller indices), appends it to PATH and
+	// follows the link that leaves the block.  Chains of neighbouring anchors — the bulk of all chained anchors — cost a few
+	// warp instructions per anchor instead of one dependent load each.
+	// The used-mark of an anchor (t[j] = 1 at chain.c:381) is folded into its p[] word: a used anchor stores -3 - p (<= -2).
+	// p[] has no reader after the backtrack.
 	int32_t *PATH = V;      // v[] is dead from here on, exactly like the reference reuses it (chain.c:380)
 	int n_v = 0, n_kept = 0;
-	if (lane == 0) {
-		for (int i = 0; i < n_u; ++i) {
-			const uint64_t key = U[i];
-			const int n_v0 = n_v;
-			// The used-mark of an anchor (t[j] = 1 at chain.c:381) is folded into its p[] word — a used anchor stores -3 - p,
-			// i.e. a value <= -2 — so each step of the walk is ONE dependent load (the next anchor's word gives both its
-			// mark and its own predecessor) instead of two.  p[] has no reader after the backtrack.
-			int j = (int32_t)key;
-			int32_t w = P[j];
-			for (;;) {                                       // do-while of chain.c:379-383: the first anchor is taken unconditionally
-				MM2B_CHK(n_v < n && j >= 0 && j < n, 0x40);
-				PATH[n_v++] = j;
-				const int32_t pj = w <= -2 ? -3 - w : w;
-				if (w >= -1) P[j] = -3 - w;
-				j = pj;
-				if (j < 0) break;
-				w = P[j];
-				if (w <= -2) break;                          // already on a better chain
+	for (int i = 0; i < n_u; ++i) {
+		const uint64_t key = U[i];
+		const int n_v0 = n_v;
+		int cur = __shfl_sync(FULL, (int32_t)key, 0);        // next anchor of the walk (through a shuffle: see the convergence note)
+		bool first = true;                                   // do-while of chain.c:379-383: the first anchor is taken unconditionally
+		int stop;                                            // the j the reference's loop ends with: -1 = past the head, else the first used anchor
+		for (;;) {
+			const int base = cur & ~31, e = cur & 31;
+			const int k = base + lane;
+			const int32_t w = k < n ? P[k] : -1;
+			const bool used = w <= -2;
+			const int32_t pp = used ? -3 - w : w;            // the anchor's predecessor, mark removed
+			const unsigned usedmask = __ballot_sync(FULL, used);
+			if (!first && (usedmask >> e & 1u)) { stop = cur; break; }                 // already on a better chain
+			int nxt = (pp >= base && !(usedmask >> ((pp - base) & 31) & 1u)) ? pp - base : -1;   // link followed inside the block
+			unsigned mask = 1u << lane;
+			while (__any_sync(FULL, nxt >= 0)) {             // <= 5 rounds
+				const int src = nxt >= 0 ? nxt : lane;
+				const unsigned m2 = __shfl_sync(FULL, mask, src);
+				const int n2 = __shfl_sync(FULL, nxt, src);
+				if (nxt >= 0) mask |= m2, nxt = n2;
 			}
-			const int len = n_v - n_v0;
-			bool keep = false;
-			uint64_t sc = key >> 32;
-			if (j < 0) keep = len >= par.min_cnt;
-			else if ((int32_t)(key >> 32) - F[j] >= par.min_sc) {
-				keep = len >= par.min_cnt;
-				sc = (key >> 32) - (uint64_t)(int64_t)F[j];
+			const unsigned path = __shfl_sync(FULL, mask, e);                        // this block's stretch of the walk
+			const int32_t out = __shfl_sync(FULL, pp, lowest_lane(path));              // the link that leaves it
+			MM2B_CHK(n_v + __popc(path) <= n && cur >= 0 && cur < n, 0x40);
+			if (path >> lane & 1u) {
+				PATH[n_v + __popc(path >> 1 >> lane)] = k;                           // walk order = descending index
+				if (!used) P[k] = -3 - w;
 			}
-			if (keep) U[n_kept++] = sc << 32 | (uint64_t)(uint32_t)len;
-			else n_v = n_v0;
+			__syncwarp();
+			n_v += __popc(path);
+			first = false;
+			if (out < 0 || out >= base) { stop = out; break; }                       // past the head, or an in-block link that was not followed: used
+			cur = out;
 		}
+		const int len = n_v - n_v0;
+		const int32_t f_stop = __shfl_sync(FULL, stop >= 0 ? F[stop] : 0, 0);
+		const int32_t sc = (int32_t)(key >> 32) - f_stop;                            // chain.c:385-388
+		const bool keep = len >= par.min_cnt && (stop < 0 || sc >= par.min_sc);
+		// (stored whether kept or not — slot n_kept <= i is already consumed — so that the branch stays lane-only; see the convergence note)
+		if (lane == 0) U[n_kept] = (uint64_t)(stop < 0 ? (uint32_t)(key >> 32) : (uint32_t)sc) << 32 | (uint64_t)(uint32_t)len;
+		__syncwarp();
+		n_kept += keep;
+		if (!keep) n_v = n_v0;
 	}
 	__syncwarp();
-	n_v = __shfl_sync(FULL, n_v, 0);
-	n_u = __shfl_sync(FULL, n_kept, 0);
-	__syncwarp();
+	n_u = n_kept;
 	n_u_out = n_u, n_v_out = n_v;
 	if (n_u == 0) return;
 
