@@ -111,7 +111,8 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
                                                   int32_t &max_f, int32_t &max_j, unsigned &n_chunks, unsigned &n_cells)
 {
 	int n_skip = 0;
-	for (int jt = i - 1; jt >= st; jt -= 32) {
+	int jt = i - 1;
+	do {                                                         // the caller only comes here with a non-empty window (st < i)
 		if (COUNT) ++n_chunks;
 		const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
 		const bool act = lane < n_act;
@@ -193,11 +194,11 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		}
 
 		// records: the largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane
-		// above max_f, i.e. the only one.  Otherwise walk from the first candidate up to it.
+		// above max_f, i.e. the only one.  Otherwise (`multi`) walk from the first candidate up to it.
 		unsigned recmask = 0;
 		const unsigned cand = __ballot_sync(FULL, sc > max_f);
-		int32_t top = max_f;
-		int last = 0;
+		int32_t top = max_f, top_j = -1;
+		bool multi = false;
 		if (cand == 0) {
 			if (__ballot_sync(FULL, valid) == 0) {       // every cell `continue`d: no stamps, no n_skip change
 				if (COUNT) n_cells += n_act;
@@ -206,9 +207,11 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		} else {
 			top = __reduce_max_sync(FULL, sc);
 			// the nearest lane holding the maximum = the lane with the largest j among them: a second REDUX instead of vote + bit scan
-			last = jt - __reduce_max_sync(FULL, sc == top ? j : INT_MIN);
+			top_j = __reduce_max_sync(FULL, sc == top ? j : INT_MIN);
+			const int last = jt - top_j;
 			recmask = 1u << last;
-			if (cand & (recmask - 1u)) {                   // candidates before it: more than one record, walk them (rare)
+			multi = (cand & (recmask - 1u)) != 0;          // candidates before it: more than one record (rare)
+			if (multi) {
 				for (int r = lowest_lane(cand); r != last;) {
 					recmask |= 1u << r;
 					const int32_t t = __shfl_sync(FULL, sc, r);
@@ -231,11 +234,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			__syncwarp();
 		}
 		const unsigned hitmask = __ballot_sync(FULL, valid && tj == i) & ~recmask;   // chain.c:229
-		// n_skip, whether the loop breaks in this chunk, and which records come before the break
+		// n_skip, whether the loop breaks in this chunk, and the last record before the break = the new running max
 		bool broke = false;
 		int brk = 32;                                         // break lane; only tracked exactly when it is needed
-		unsigned take = recmask;                              // records visited before the break
-		if ((recmask & (recmask - 1u)) == 0) {                // at most one record (the usual case): two runs of hits, branch-free
+		if (!multi) {                                         // at most one record (the usual case): two runs of hits, branch-free
 			const unsigned before = recmask ? (recmask - 1u) : FULL;           // lanes visited before the record
 			const unsigned h1 = hitmask & before, h2 = hitmask & ~before;
 			const int x1 = n_skip + __popc(h1);                                // counter when the record is reached
@@ -243,7 +245,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			const int x3 = x2 + __popc(h2);                                    // ... at the end of the chunk
 			const bool early = x1 > c.max_skip;                                // the loop ends before it reaches the record
 			broke = early || x3 > c.max_skip;
-			if (early) take = 0;
+			if (recmask != 0 && !early) max_f = top, max_j = top_j;
 			if (COUNT && broke) {                             // the exact lane only matters for the cell tally
 				const unsigned run = early ? h1 : h2;         // the run of hits in which the counter first exceeds max_skip ...
 				int k = c.max_skip + 1 - (early ? n_skip : x2);                // ... at its k-th hit
@@ -252,27 +254,27 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 				brk = lowest_lane(__ballot_sync(FULL, ((run >> lane) & 1u) && __popc(run & le) == k));
 			}
 			n_skip = x3;
-		} else if (hitmask == 0) {                            // only decrements: saturating subtraction
-			n_skip -= __popc(recmask);
-			n_skip = n_skip > 0 ? n_skip : 0;
 		} else {
-			int corr = 0, floor_all = 0, done = 0;            // corr: min(0, min S over the records at or before this lane)
-			for (unsigned rm = recmask; rm; rm &= rm - 1) {
-				const unsigned below = (rm - 1u) & ~rm;       // lanes before this record
-				const int S_r = n_skip + __popc(hitmask & below) - (++done);
-				floor_all = S_r < floor_all ? S_r : floor_all;
-				if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
+			unsigned take = recmask;                          // records visited before the break
+			if (hitmask == 0) {                               // only decrements: saturating subtraction
+				n_skip -= __popc(recmask);
+				n_skip = n_skip > 0 ? n_skip : 0;
+			} else {
+				int corr = 0, floor_all = 0, done = 0;        // corr: min(0, min S over the records at or before this lane)
+				for (unsigned rm = recmask; rm; rm &= rm - 1) {
+					const unsigned below = (rm - 1u) & ~rm;   // lanes before this record
+					const int S_r = n_skip + __popc(hitmask & below) - (++done);
+					floor_all = S_r < floor_all ? S_r : floor_all;
+					if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
+				}
+				const unsigned le = lanemask_lt(lane) | (1u << lane);
+				const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
+				const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > c.max_skip);
+				if (over) broke = true, brk = lowest_lane(over), take = recmask & bits_below(brk);
+				else n_skip = n_skip + __popc(hitmask) - done - floor_all;
 			}
-			const unsigned le = lanemask_lt(lane) | (1u << lane);
-			const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
-			const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > c.max_skip);
-			if (over) broke = true, brk = lowest_lane(over), take = recmask & bits_below(brk);
-			else n_skip = n_skip + __popc(hitmask) - done - floor_all;
-		}
-		// new running max: the last record before the break (records are strictly increasing; ties went to the nearest j)
-		if (take) {
-			if ((take >> last) & 1u) max_f = top, max_j = jt - last;
-			else {
+			// records are strictly increasing and ties went to the nearest j, so the last one taken is the new running max
+			if (take) {
 				const int l2 = 31 - __clz(take);
 				max_f = __shfl_sync(FULL, sc, l2);
 				max_j = jt - l2;
@@ -280,7 +282,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		}
 		if (COUNT) n_cells += broke ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
 		if (broke) break;                                                         // chain.c:230-231
-	}
+	} while ((jt -= 32) >= st);
 }
 
 // The sequential step for one block of 32 anchors: the anchors flagged in `todo` (non-empty window), in index order.
