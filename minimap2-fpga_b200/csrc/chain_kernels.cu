@@ -98,9 +98,11 @@ struct DpConst {
 // The order-dependent parts of the reference loop are recovered exactly from warp votes:
 //  * records (chain.c:226, strict '>' running max): the first lane above max_f, then the first later lane above that, ...
 //    — chunks hold 0-2 records in practice, so a warp-uniform loop beats a 5-step shuffle prefix-max;
-//  * stamps (chain.c:233): every visited cell writes t[p[j]] = i, then all lanes read t[j] back.  A stamp only lands on an
-//    index smaller than its writer's, so "all write, then all read" is order-safe; stamps from lanes past the break carry
-//    a value (i) that is never compared again; stamps below st are never read;
+//  * stamps (chain.c:233): every visited cell stamps t[p[j]] = i and a later cell is a "hit" if it finds its own t[j] == i.
+//    A stamp only lands on an index smaller than its writer's, so within a chunk the stamps are a one-hot OR over the lanes
+//    (REDUX.OR, no memory); stamps for cells of later chunks go to the ring (or to t[] in HBM below the ring) only when the
+//    scan does move on, and are read back there.  Stamps from lanes past the break carry a value (i) that is never compared
+//    again; stamps below st are never read;
 //  * n_skip (chain.c:228-231) is a Lindley recursion x_t = max(x_{t-1} + d_t, 0), d = +1 (hit), -1 (record), 0 (other),
 //    with closed form x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum d.  S only drops at records, so the running
 //    minimum is a minimum over the record lanes: scalar work on the two vote masks, no shuffles;
@@ -112,6 +114,19 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 {
 	int n_skip = 0;
 	int jt = i - 1;
+	// end of a chunk, spelled out at the end of each path so that `broke` is a branch and never a register:
+	// the cell tally (iterations of chain.c:197 the reference executes here), then the break of chain.c:230-231
+#define MM2B_CHUNK_END(broke_, brk_) { \
+		if (COUNT) n_cells += (broke_) ? (brk_) + 1 : n_act; \
+		if (broke_) break; \
+		if (valid && pj >= st && pj < jt - 31) {          /* the scan goes on: stamps for the cells of later chunks */ \
+			MM2B_CHK(pj < j && pj > i - RING - 32 - 5000000, 0x2); \
+			MM2B_CHK(DEEP || pj >= ring_lo, 0x4); \
+			if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i; \
+			else rc.T[pj] = i; \
+		} \
+		__syncwarp(); \
+		continue; }
 	do {                                                         // the caller only comes here with a non-empty window (st < i)
 		if (COUNT) ++n_chunks;
 		const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
@@ -219,21 +234,24 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 				}
 			}
 		}
-		// stamps, then hits
-		if (valid && pj >= st) {
-			MM2B_CHK(pj < j && pj > i - RING - 32 - 5000000, 0x2);
-			MM2B_CHK(DEEP || pj >= ring_lo, 0x4);
-			if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i;
-			else rc.T[pj] = i;
-		}
-		__syncwarp();
-		int32_t tj;
-		if (in_ring) tj = ring.b[s].y;
+		// hits (chain.c:229,233): cell j was stamped by an earlier-visited valid cell whose predecessor it is.  A stamp from
+		// inside this chunk is a bit in a one-hot OR over the lanes (lane of the target = jt - p[j]); memory stamps are only
+		// written when the scan moves on to another chunk (end of the loop body), so the usual single-chunk scan has no
+		// store -> load round trip at all.
+		unsigned hot;
+		asm("shl.b32 %0, 1, %1;" : "=r"(hot) : "r"(jt - pj));       // PTX shl clamps: 0 for targets beyond this chunk (distance >= 32)
+		hot = __reduce_or_sync(FULL, valid ? hot : 0u);
+		unsigned hitmask;
+		if (jt == i - 1) hitmask = __ballot_sync(FULL, valid) & hot & ~recmask;
 		else {
-			tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
-			__syncwarp();
+			int32_t tj;
+			if (in_ring) tj = ring.b[s].y;
+			else {
+				tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
+				__syncwarp();
+			}
+			hitmask = __ballot_sync(FULL, valid && (tj == i || (hot >> lane & 1u))) & ~recmask;
 		}
-		const unsigned hitmask = __ballot_sync(FULL, valid && tj == i) & ~recmask;   // chain.c:229
 		// n_skip, whether the loop breaks in this chunk, and the last record before the break = the new running max
 		bool broke = false;
 		int brk = 32;                                         // break lane; only tracked exactly when it is needed
@@ -254,6 +272,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 				brk = lowest_lane(__ballot_sync(FULL, ((run >> lane) & 1u) && __popc(run & le) == k));
 			}
 			n_skip = x3;
+			MM2B_CHUNK_END(broke, brk);
 		} else {
 			unsigned take = recmask;                          // records visited before the break
 			if (hitmask == 0) {                               // only decrements: saturating subtraction
@@ -279,10 +298,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 				max_f = __shfl_sync(FULL, sc, l2);
 				max_j = jt - l2;
 			}
+			MM2B_CHUNK_END(broke, brk);
 		}
-		if (COUNT) n_cells += broke ? brk + 1 : n_act;   // iterations of chain.c:197 the reference executes here
-		if (broke) break;                                                         // chain.c:230-231
 	} while ((jt -= 32) >= st);
+#undef MM2B_CHUNK_END
 }
 
 // The sequential step for one block of 32 anchors: the anchors flagged in `todo` (non-empty window), in index order.
