@@ -309,12 +309,14 @@ template <bool GENERAL, bool DEEP, bool COUNT>
 __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int base, int ring_lo,
                                             unsigned todo, int32_t seg, int st_k, unsigned &n_chunks, unsigned &n_cells)
 {
-	while (todo) {
+	if (todo == 0) return;
+	const int4 *slot0 = ring.a + (base & (RING - 1));      // a block is 32-aligned, so its slots do not wrap inside the ring
+	do {
 		const int ii = lowest_lane(todo);
 		todo &= todo - 1;
 		const int i = base + ii;
-		const int si = i & (RING - 1);
-		const int4 me = ring.a[si];                    // broadcast read: this anchor's own slot still holds its defaults
+		const int4 *slot = slot0 + ii;
+		const int4 me = *slot;                    // broadcast read: this anchor's own slot still holds its defaults
 		// The window start must come through a shuffle, not through shared memory: it bounds the chunk loop, and ptxas only
 		// treats the loop as warp-uniform (no BRA.DIV guards on the collectives inside) when the bound is a shuffle/vote result.
 		const int st = __shfl_sync(FULL, st_k, ii);
@@ -325,9 +327,9 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 		// f[i], p[i] (chain.c:236): one lane publishes them to the anchor's slot; untouched if no predecessor won.
 		// v[i] is not needed by the scan at all; it is filled in per block afterwards (dp_fill).
 		MM2B_CHK(max_j < i && max_j >= -1 && (max_j < 0 || max_j >= st) && (DEEP || max_j < 0 || max_j >= ring_lo), 0x8);
-		if (lane == 0 && max_j >= 0) *(int2*)&ring.a[si].z = make_int2(max_f, max_j);
+		if (lane == 0 && max_j >= 0) *(int2*)&slot->z = make_int2(max_f, max_j);
 		__syncwarp();
-	}
+	} while (todo);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
