@@ -343,7 +343,7 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool GENERAL, bool COUNT>
-__device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, int32_t *smem, int lane,
+__device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, bool lo_safe, int32_t *smem, int lane,
                         unsigned long long &n_chunks64, unsigned long long &n_cells64, unsigned long long &n_window64)
 {
 	Ring ring;
@@ -358,6 +358,8 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 	const uint64_t win = (uint64_t)(int64_t)par.max_dist_x;
 	unsigned n_chunks = 0, n_cells = 0;
 	int st_carry = 0;           // window start of the previous block's last anchor (window starts never move backwards)
+	int run_carry = 0;          // first anchor of the run of equal high words (strand, rid) the previous block ended in
+	uint32_t hi_carry = 0;      // ... and that high word
 
 	for (int base = 0; base < n; base += 32) {
 		const int k = base + lane;
@@ -368,31 +370,76 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 			x = t.x, y = t.y;
 		}
 		__syncwarp();
-		// chain.c:192: first s in [st_carry, k] with !(x > a[s].x + max_dist_x); full 64-bit compare (strand/rid are in the high word)
-		int lo = st_carry, hi = in ? k : st_carry;
-		while (__any_sync(FULL, lo < hi)) {
-			const int mid = (lo + hi) >> 1;
-			if (lo < hi) {
-				if (x > __ldg(&A[mid].x) + win) lo = mid + 1;
-				else hi = mid;
-			}
-			__syncwarp();
-		}
-		int st_k = lo;
-		if (k - st_k > c.max_iter) st_k = k - c.max_iter;                                // chain.c:193
 		const int32_t seg = (int32_t)(y >> SEG_SHIFT & 0xff);
-		if (in) {
+		if (in) {                                          // publish first: the window search below probes the ring
 			const int s = k & (RING - 1);
 			const int32_t q_span = (int32_t)(y >> 32 & 0xff);
 			ring.a[s] = make_int4((int32_t)x, (int32_t)y, q_span, -1);
 			ring.b[s] = make_int2(q_span, -1);
 		}
 		__syncwarp();
+		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
+		// chain.c:192: first s in [st_carry, k] with !(x > a[s].x + max_dist_x) — a 64-bit compare, strand/rid are in the high word.
+		// Anchors are sorted, so the anchors sharing k's high word are a run [run_k, k]; when low word + max_dist_x cannot carry
+		// (`lo_safe`, checked over the whole read) every anchor before the run is out of reach and inside the run the compare is
+		// on the low words, which the ring holds for the most recent RING anchors: the search then runs on shared memory
+		// (probes below the ring read the low word from L1/L2).  Without `lo_safe` it is the plain 64-bit search over L1/L2.
+		const uint32_t xh = (uint32_t)(x >> 32);
+		uint32_t xh_prev = __shfl_up_sync(FULL, xh, 1);
+		if (lane == 0) xh_prev = hi_carry;
+		const unsigned chg = __ballot_sync(FULL, in && (k == 0 || xh != xh_prev)) & (lanemask_lt(lane) | (1u << lane));
+		const int run_k = chg ? base + (31 - __clz(chg)) : run_carry;
+		// Lower bound by halving steps (no data-dependent branch, the same trip count for all lanes): pos = last index known to
+		// be out of reach, starting just before the range.
+		const int lo = lo_safe && run_k > st_carry ? run_k : st_carry, hi = in ? k : lo;
+		int pos = lo - 1;
+		const int span = __reduce_max_sync(FULL, hi - lo);
+		if (lo_safe && __all_sync(FULL, lo >= ring_lo)) {
+			const uint32_t xl = (uint32_t)x - (uint32_t)win;              // x_s + win < x_k on the low words; cannot wrap when it matters:
+			const bool any_far = (uint32_t)x >= (uint32_t)win;           // x_k < win means every anchor of the run is within reach
+			for (int step = 1 << (31 - __clz(span | 1)); step; step >>= 1) {
+				const int q = pos + step;
+				if (q < hi && any_far && (uint32_t)ring.a[q & (RING - 1)].x < xl) pos = q;
+			}
+		} else {
+			// The range reaches below the ring (long windows: CCS reads, repeats) or the low words are not enough.  Window starts
+			// move forward by about one block per block, so instead of ~10 dependent probes into L2 the warp merges: it loads
+			// the next 32 candidate starts with one coalesced read and every lane counts, by a binary search over the lanes'
+			// registers, how many of them are out of its reach; lanes that exhaust the batch go on to the next one.
+			int s0 = __reduce_min_sync(FULL, in ? lo : INT_MAX);
+			bool more = in && lo < k;
+			while (__any_sync(FULL, more)) {
+				const int sidx = s0 + lane;
+				uint64_t v = 0;
+				if (sidx < n) v = __ldg(&A[sidx].x) + win;
+				__syncwarp();
+				int c = -1;                                   // last out-of-reach entry of the batch
+#pragma unroll
+				for (int r = 0; r < 6; ++r) {                 // steps 16, 8, 4, 2, 1 and once more 1: c can reach 31
+					const int q = c + (r < 5 ? 16 >> r : 1);
+					const uint64_t vq = __shfl_sync(FULL, v, q);
+					if (s0 + q < k && x > vq) c = q;
+				}
+				if (more) {
+					pos = s0 + c;
+					more = c == 31 && s0 + 32 < k;
+				}
+				__syncwarp();
+				s0 += 32;
+			}
+		}
+		__syncwarp();
+		int st_k = pos + 1;
+		if (k - st_k > c.max_iter) st_k = k - c.max_iter;                                // chain.c:193
 		if (COUNT && in) n_window64 += (unsigned)(k - st_k);             // per-lane partial sums of the window sizes (chain.c:192-193)
 		unsigned todo = __ballot_sync(FULL, in && st_k < k);
-		const int ring_lo = base + 32 - RING;      // anchors with index >= ring_lo are resident in the ring
 		const bool deep_block = __any_sync(FULL, in && st_k < ring_lo);    // some window in this block reaches below the ring
-		st_carry = __shfl_sync(FULL, st_k, (n - base < 32 ? n - base : 32) - 1);
+		{
+			const int last_lane = (n - base < 32 ? n - base : 32) - 1;
+			st_carry = __shfl_sync(FULL, st_k, last_lane);
+			run_carry = __shfl_sync(FULL, run_k, last_lane);
+			hi_carry = __shfl_sync(FULL, xh, last_lane);
+		}
 		__syncwarp();
 
 		if (!deep_block) chain_block<GENERAL, false, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
@@ -421,6 +468,9 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 				}
 				ring.b[s].x = v;
 				rc.F[k] = fp.x, rc.P[k] = fp.y, rc.V[k] = v;
+				// chain.c:349-351, folded in: t[] was zeroed before the fill and every later writer of t[p] — this mark or a
+				// deep-look-back stamp (an anchor index >= 1) — means "p has a successor", so chain ends are the anchors with t == 0
+				if (fp.y >= 0) rc.T[fp.y] = MARK_SUCC;
 			}
 		}
 		__syncwarp();            // (see the note on convergence at the top of the kernel)
@@ -558,19 +608,13 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 	int32_t *P = rc.P, *V = rc.V, *T = rc.T;
 	uint64_t *U = rc.U;
 
-	// chain.c:349-351: mark anchors that have a successor
-	for (int k = lane; k < n; k += 32) {
-		const int32_t p = P[k];
-		if (p >= 0) T[p] = MARK_SUCC;
-	}
-	__syncwarp();
 	// chain.c:352-367: chain ends whose path peak reaches min_sc, each walked back to that peak
 	int n_u = 0;
 	for (int base = 0; base < n; base += 32) {
 		const int k = base + lane;
 		bool is_end = false;
 		uint64_t key = 0;
-		if (k < n && T[k] != MARK_SUCC && V[k] >= par.min_sc) {
+		if (k < n && T[k] == 0 && V[k] >= par.min_sc) {          // no successor (marks: dp_fill's block epilogue)
 			is_end = true;
 			int j = k;
 			while (j >= 0 && F[j] < V[j]) j = P[j];
@@ -779,13 +823,16 @@ chain_reads_kernel(const BatchArgs args)
 		uint64_t sum = 0;
 		uint32_t seg_diff = 0;
 		const uint32_t seg0 = (uint32_t)(__ldg(&rc.A[0].y) >> SEG_SHIFT & 0xff);
+		uint32_t max_xl = 0;                     // largest low word of x (reference position): see the window search in dp_fill
 		for (int k = lane; k < rc.n; k += 32) {
-			const uint64_t y = __ldg(&rc.A[k].y);
-			sum += y >> 32 & 0xff;
-			seg_diff |= (uint32_t)(y >> SEG_SHIFT & 0xff) ^ seg0;
+			const ulonglong2 t = __ldg(rc.A + k);
+			sum += t.y >> 32 & 0xff;
+			seg_diff |= (uint32_t)(t.y >> SEG_SHIFT & 0xff) ^ seg0;
+			max_xl = max_xl > (uint32_t)t.x ? max_xl : (uint32_t)t.x;
 			rc.T[k] = 0;
 		}
 		__syncwarp();
+		const bool lo_safe = args.par.max_dist_x >= 0 && (uint64_t)__reduce_max_sync(FULL, max_xl) + (uint64_t)args.par.max_dist_x < (1ull << 32);
 #pragma unroll
 		for (int d = 16; d; d >>= 1) {
 			sum += __shfl_xor_sync(FULL, sum, d);
@@ -799,9 +846,9 @@ chain_reads_kernel(const BatchArgs args)
 		__syncwarp();
 		if (general) {
 			++n_general;
-			dp_fill<true, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells, n_window);
+			dp_fill<true, COUNT>(args.par, rc, avg, lo_safe, ring, lane, n_chunks, n_cells, n_window);
 		} else {
-			dp_fill<false, COUNT>(args.par, rc, avg, ring, lane, n_chunks, n_cells, n_window);
+			dp_fill<false, COUNT>(args.par, rc, avg, lo_safe, ring, lane, n_chunks, n_cells, n_window);
 		}
 		if (args.dbg_fpv) {      // test hook (MM2B_KEEP_FPV=1): keep f/p/v as they are at chain.c:238, before the extraction reuses v
 			int32_t *d = args.dbg_fpv + o;
