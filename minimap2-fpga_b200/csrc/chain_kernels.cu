@@ -3,16 +3,20 @@
 // Design (B200-first, not a translation of the FPGA shift-register kernel or of the CPU loop):
 //   * one WARP per read, persistent CTAs (2 warps, 16 CTAs/SM = 32 warps/SM) pulling reads longest-first from a
 //     global work counter, so 148 SMs x 32 warps chain 4736 reads concurrently;
-//   * anchors stream in 32 at a time with one coalesced 16-byte load per lane; each lane binary-searches its own
-//     anchor's window start, anchors with an empty window are finished in parallel, and the most recent 256 anchors'
-//     {x_lo, y_lo, f, p | v, t} live in a per-warp shared-memory ring (6 KB); deeper look-back (rare) reads L2;
+//   * anchors stream in 32 at a time with one coalesced 16-byte load per lane; each lane finds its own anchor's window
+//     start (halving-step lower bound over the shared-memory ring, or a register merge against coalesced batches of
+//     candidate starts when the window reaches below the ring), anchors with an empty window are finished in parallel,
+//     and the most recent 256 anchors' {x_lo, y_lo, f, p | v, t} live in a per-warp shared-memory ring (6 KB); deeper
+//     look-back (rare) reads L2;
 //   * the inner loop over predecessors j = i-1 .. st is evaluated 32 lanes at a time; the order-dependent parts of
 //     the reference loop (strict '>' running max, t[] stamps, the n_skip counter and its break, chain.c:226-233)
-//     are recovered exactly from warp votes: REDUX.MAX + ballots for the records, stamp-then-read for t[], and a
-//     closed-form (Lindley) evaluation of the n_skip counter on the two vote masks;
-//   * chain ends / peaks, the descending sort, the priority backtrack and the final order by reference position
-//     (including the reference's unstable radix-sort tie order) run in the same warp right after the fill while
-//     f/p/v are still in L1/L2; a scan + gather kernel pair then packs u[]/b[] in read order.
+//     are recovered exactly from warp votes: REDUX.MAX + ballots for the records, a one-hot REDUX.OR for the stamps
+//     that land inside the chunk (memory stamps only when the scan moves to another chunk), and a closed-form
+//     (Lindley) evaluation of the n_skip counter on the two vote masks;
+//   * chain ends / peaks, the descending sort, the priority backtrack (32 anchors per step by pointer jumping inside
+//     aligned blocks of p[]) and the final order by reference position (including the reference's unstable radix-sort
+//     tie order) run in the same warp right after the fill while f/p/v are still in L1/L2; a scan + gather kernel
+//     pair then packs u[]/b[] in read order.
 // No tensor cores (nothing here is a contraction) and no collective (reads are independent).
 #include "chain_kernels.cuh"
 #include <limits.h>

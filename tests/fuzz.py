@@ -103,3 +103,44 @@ def mixed_batch(seed, n_reads=40, seg_ids=1, scale=1.0):
         else:
             reads.append(collinear(rng, int(rng.integers(30, 1500 * scale + 31)), 0, indel=0.3, step=(1, 200)))
     return batch(reads)
+
+def high_positions(rng, n, n_rid=3, span=15, spread=30_000):
+    """Reference positions just below 2^32, plus small positions on the next rid: `x + max_dist_x` carries into the
+    rid/strand word (chain.c:192 does the addition on the whole 64-bit x), so the window search cannot work on low words."""
+    top = (1 << 32) - 1
+    rid = rng.integers(0, n_rid, n)
+    hi = rng.random(n) < 0.6
+    rpos = np.where(hi, top - rng.integers(0, spread, n), rng.integers(0, spread, n))
+    qpos = span + rng.integers(0, spread, n)
+    return _pack(rng.integers(0, 2, n), rid, rpos, qpos, np.full(n, span))
+
+
+def many_runs(rng, n, n_rid=60, span=15):
+    """Short runs of equal (strand, rid): several run boundaries inside every block of 32 anchors, each run a small cluster."""
+    rid = rng.integers(0, n_rid, n)
+    rev = rng.integers(0, 2, n)
+    r0 = 200_000 + (rid * 7919 + rev * 104729) % 50_000
+    k = rng.integers(0, 12, n)
+    return _pack(rev, rid, r0 + k * 21 + rng.integers(0, 3, n), span + k * 21 + rng.integers(0, 3, n), np.full(n, span))
+
+
+def interleaved(rng, n_diag, per, span=15):
+    """n_diag chains on diagonals far apart in the query but interleaved on the reference: every chain link skips
+    n_diag - 1 anchors (links longer than a 32-anchor block when n_diag > 32), and the chains tie in score."""
+    k = np.repeat(np.arange(per), n_diag)
+    d = np.tile(np.arange(n_diag), per)
+    rpos = 300_000 + k * (n_diag + 5) + d
+    qpos = span + d * 6000 + k * (n_diag + 5)
+    return _pack(np.zeros(len(k), np.int64), np.zeros(len(k), np.int64), rpos, qpos, np.full(len(k), span))
+
+
+def edge_batch(seed, scale=1.0):
+    """The shapes the window search and the block-wise backtrack have to get right; see tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(seed)
+    s = lambda v: max(2, int(v * scale))
+    reads = [high_positions(rng, s(900)), high_positions(rng, s(300), n_rid=1, spread=6000), many_runs(rng, s(1500)),
+             many_runs(rng, s(200), n_rid=5), interleaved(rng, 40, s(30)), interleaved(rng, 3, s(200)), interleaved(rng, 70, s(12)),
+             np.concatenate([dense_repeat(rng, s(700), width=4500, qwidth=4000), high_positions(rng, s(200))]),
+             collinear(rng, s(2500), s(400), n_rid=40), collinear(rng, s(800), s(800), n_rid=200, genome=400_000)]
+    reads[7] = reads[7][np.argsort(reads[7]["x"], kind="stable")]
+    return batch(reads)

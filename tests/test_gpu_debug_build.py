@@ -45,6 +45,9 @@ off, a = fuzz.batch([fuzz.dense_repeat(rng, 6000, width=4500, qwidth=4000), fuzz
                      fuzz.lattice(rng, 3000)] + [fuzz.dense_repeat(rng, n, width=max(4, n // 2), qwidth=max(4, n // 2)) for n in (1, 31, 32, 33, 255, 256, 257, 289)])
 for kw in ({}, dict(min_cnt=1, min_sc=1), dict(max_iter=300, max_skip=2)):
     check(kw, off, a)
+off, a = fuzz.edge_batch(11)
+for kw in ({}, dict(max_dist_x=60000, max_dist_y=60000, bw=40000, max_skip=5), dict(max_skip=200)):
+    check(kw, off, a)
 for name in ("tandem_iter64", "syn_ccs", "sr_paired"):
     recs = dumpio.read_dump(%(root)r + "/tests/golden/" + name + ".dump.gz")
     groups = {}

@@ -103,6 +103,18 @@ def test_deep_lookback_and_long_reads(binding, oracle):
         _compare_batch(res, ref, off, kw)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(max_dist_x=60000, max_dist_y=60000, bw=40000, max_skip=5), dict(min_cnt=1, min_sc=1, max_iter=40),
+                                dict(max_skip=200), dict(n_segs=2, max_dist_x=800, max_dist_y=600, bw=100, min_cnt=2, min_sc=25)])
+def test_window_search_and_backtrack_edge_shapes(binding, oracle, kw):
+    """x + max_dist_x carrying into the rid word (64-bit merge search), run boundaries inside blocks (low-word search),
+    chain links longer than a 32-anchor block and interleaved tying chains (block-wise backtrack), quiet tails (max_skip=200)."""
+    for seed in (11, 12):
+        off, a = fuzz.edge_batch(seed)
+        ref = oracle.replay(oracle.Params(**kw), off, a, n_threads=8)
+        res = binding.chain_batch(binding.Params(**kw), off, a)
+        _compare_batch(res, ref, off, kw)
+
+
 def test_subbatching_and_order_independence(binding, oracle, monkeypatch):
     """Results must not depend on how the batch is cut into sub-batches or on read order."""
     off, a = fuzz.mixed_batch(77, n_reads=120, scale=0.5)

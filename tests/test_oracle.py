@@ -66,6 +66,21 @@ def test_oracle_matches_compiled_reference_fuzz(oracle, pi):
         assert (o["status"] != 2) == ref["u_null"], (kw, r)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(max_dist_x=60000, max_dist_y=60000, bw=40000, max_skip=5), dict(min_cnt=1, min_sc=1, max_iter=40)])
+def test_oracle_matches_compiled_reference_edge_shapes(oracle, kw):
+    """x + max_dist_x carrying into the rid word, run boundaries inside blocks, chain links longer than 32 anchors."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libmm2ref.so not built (needs /root/reference)")
+    par = oracle.Params(**kw)
+    off, a = fuzz.edge_batch(11, scale=0.5)
+    for r in range(len(off) - 1):
+        ar = a[off[r]:off[r + 1]]
+        o = oracle.chain(par, ar)
+        ref = oracle.ref_chain(par, ar)
+        assert np.array_equal(o["u"], ref["u"]), (kw, r, "u")
+        assert np.array_equal(o["b"], ref["b"]), (kw, r, "b")
+
+
 def test_replay_threads_and_reference_agree(oracle):
     par = oracle.Params()
     off, a = fuzz.mixed_batch(7, n_reads=48)
