@@ -212,41 +212,15 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			continue;
 		}
 
-		// records: the largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane
-		// above max_f, i.e. the only one.  Otherwise (`multi`) walk from the first candidate up to it.
-		unsigned recmask = 0;
-		const unsigned cand = __ballot_sync(FULL, sc > max_f);
-		int32_t top = max_f, top_j = -1;
-		bool multi = false;
-		if (cand == 0) {
-			if (__ballot_sync(FULL, valid) == 0) {       // every cell `continue`d: no stamps, no n_skip change
-				if (COUNT) n_cells += n_act;
-				continue;
-			}
-		} else {
-			top = __reduce_max_sync(FULL, sc);
-			// the nearest lane holding the maximum = the lane with the largest j among them: a second REDUX instead of vote + bit scan
-			top_j = __reduce_max_sync(FULL, sc == top ? j : INT_MIN);
-			const int last = jt - top_j;
-			recmask = 1u << last;
-			multi = (cand & (recmask - 1u)) != 0;          // candidates before it: more than one record (rare)
-			if (multi) {
-				for (int r = lowest_lane(cand); r != last;) {
-					recmask |= 1u << r;
-					const int32_t t = __shfl_sync(FULL, sc, r);
-					r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
-				}
-			}
-		}
 		// hits (chain.c:229,233): cell j was stamped by an earlier-visited valid cell whose predecessor it is.  A stamp from
 		// inside this chunk is a bit in a one-hot OR over the lanes (lane of the target = jt - p[j]); memory stamps are only
 		// written when the scan moves on to another chunk (end of the loop body), so the usual single-chunk scan has no
-		// store -> load round trip at all.
+		// store -> load round trip at all.  `hitv` still includes the record lanes; they are masked out below.
 		unsigned hot;
 		asm("shl.b32 %0, 1, %1;" : "=r"(hot) : "r"(jt - pj));       // PTX shl clamps: 0 for targets beyond this chunk (distance >= 32)
 		hot = __reduce_or_sync(FULL, valid ? hot : 0u);
-		unsigned hitmask;
-		if (jt == i - 1) hitmask = __ballot_sync(FULL, valid) & hot & ~recmask;
+		unsigned hitv;
+		if (jt == i - 1) hitv = __ballot_sync(FULL, valid) & hot;
 		else {
 			int32_t tj;
 			if (in_ring) tj = ring.b[s].y;
@@ -254,20 +228,38 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 				tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
 				__syncwarp();
 			}
-			hitmask = __ballot_sync(FULL, valid && (tj == i || (hot >> lane & 1u))) & ~recmask;
+			hitv = __ballot_sync(FULL, valid && (tj == i || (hot >> lane & 1u)));
 		}
-		// n_skip, whether the loop breaks in this chunk, and the last record before the break = the new running max
-		bool broke = false;
-		int brk = 32;                                         // break lane; only tracked exactly when it is needed
-		if (!multi) {                                         // at most one record (the usual case): two runs of hits, branch-free
-			const unsigned before = recmask ? (recmask - 1u) : FULL;           // lanes visited before the record
-			const unsigned h1 = hitmask & before, h2 = hitmask & ~before;
+		// records (chain.c:226, strict '>'), n_skip, whether the loop breaks in this chunk, and the last record before the
+		// break = the new running max.  Three cases, the first two branch-free:
+		const unsigned cand = __ballot_sync(FULL, sc > max_f);
+		int brk = 32;                                         // break lane; only tracked exactly when it is needed (cell tally)
+		if (cand == 0) {                                      // (i) no record: the counter only goes up
+			const int x0 = n_skip;
+			n_skip += __popc(hitv);
+			const bool broke = n_skip > c.max_skip;
+			if (COUNT && broke) {
+				const unsigned le = lanemask_lt(lane) | (1u << lane);
+				brk = lowest_lane(__ballot_sync(FULL, ((hitv >> lane) & 1u) && x0 + __popc(hitv & le) == c.max_skip + 1));
+			}
+			MM2B_CHUNK_END(broke, brk);
+		}
+		// The largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane above
+		// max_f, i.e. the only one.  Otherwise (`multi`) walk from the first candidate up to it.
+		const int32_t top = __reduce_max_sync(FULL, sc);
+		// the nearest lane holding the maximum = the lane with the largest j among them: a second REDUX instead of vote + bit scan
+		const int32_t top_j = __reduce_max_sync(FULL, sc == top ? j : INT_MIN);
+		const int last = jt - top_j;
+		unsigned recmask = 1u << last;
+		const unsigned hitmask = hitv & ~recmask;
+		if ((cand & (recmask - 1u)) == 0) {                   // (ii) one record: a run of hits before it and one after it
+			const unsigned h1 = hitmask & (recmask - 1u), h2 = hitmask & ~(recmask - 1u);
 			const int x1 = n_skip + __popc(h1);                                // counter when the record is reached
-			const int x2 = x1 - (recmask != 0 && x1 > 0);                      // ... after it
+			const int x2 = x1 > 0 ? x1 - 1 : 0;                                // ... after it
 			const int x3 = x2 + __popc(h2);                                    // ... at the end of the chunk
 			const bool early = x1 > c.max_skip;                                // the loop ends before it reaches the record
-			broke = early || x3 > c.max_skip;
-			if (recmask != 0 && !early) max_f = top, max_j = top_j;
+			const bool broke = early || x3 > c.max_skip;
+			if (!early) max_f = top, max_j = top_j;
 			if (COUNT && broke) {                             // the exact lane only matters for the cell tally
 				const unsigned run = early ? h1 : h2;         // the run of hits in which the counter first exceeds max_skip ...
 				int k = c.max_skip + 1 - (early ? n_skip : x2);                // ... at its k-th hit
@@ -277,24 +269,31 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 			}
 			n_skip = x3;
 			MM2B_CHUNK_END(broke, brk);
-		} else {
+		} else {                                              // (iii) several records (rare)
+			for (int r = lowest_lane(cand); r != last;) {
+				recmask |= 1u << r;
+				const int32_t t = __shfl_sync(FULL, sc, r);
+				r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
+			}
+			const unsigned hm = hitv & ~recmask;
+			bool broke = false;
 			unsigned take = recmask;                          // records visited before the break
-			if (hitmask == 0) {                               // only decrements: saturating subtraction
+			if (hm == 0) {                               // only decrements: saturating subtraction
 				n_skip -= __popc(recmask);
 				n_skip = n_skip > 0 ? n_skip : 0;
 			} else {
 				int corr = 0, floor_all = 0, done = 0;        // corr: min(0, min S over the records at or before this lane)
 				for (unsigned rm = recmask; rm; rm &= rm - 1) {
 					const unsigned below = (rm - 1u) & ~rm;   // lanes before this record
-					const int S_r = n_skip + __popc(hitmask & below) - (++done);
+					const int S_r = n_skip + __popc(hm & below) - (++done);
 					floor_all = S_r < floor_all ? S_r : floor_all;
 					if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
 				}
 				const unsigned le = lanemask_lt(lane) | (1u << lane);
-				const int x = n_skip + __popc(hitmask & le) - __popc(recmask & le) - corr;
-				const unsigned over = __ballot_sync(FULL, ((hitmask >> lane) & 1u) && x > c.max_skip);
+				const int x = n_skip + __popc(hm & le) - __popc(recmask & le) - corr;
+				const unsigned over = __ballot_sync(FULL, ((hm >> lane) & 1u) && x > c.max_skip);
 				if (over) broke = true, brk = lowest_lane(over), take = recmask & bits_below(brk);
-				else n_skip = n_skip + __popc(hitmask) - done - floor_all;
+				else n_skip = n_skip + __popc(hm) - done - floor_all;
 			}
 			// records are strictly increasing and ties went to the nearest j, so the last one taken is the new running max
 			if (take) {
