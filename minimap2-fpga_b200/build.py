@@ -1,6 +1,7 @@
 """In-tree build of the native library (explicit nvcc / g++ commands, no JIT cache).
 
   libmm2chain_b200.so = csrc/chain_kernels.cu + csrc/chain_api.cu (nvcc, sm_100a) + host/chain_backend.cpp (g++)
+  mm2b-replay         = host/replay_main.cpp (g++) linked against the library: the batched caller for anchor dumps
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
@@ -14,6 +15,7 @@ ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libmm2chain_b200.so")
 LIB_DBG = os.path.join(HERE, "libmm2chain_b200_dbg.so")
+REPLAY = os.path.join(HERE, "mm2b-replay")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -62,6 +64,10 @@ def build_all(verbose=False, force=False):
         _run([NVCC] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-DMM2B_DEBUG_CHECKS"] + INC + ["-c", ksrc, "-o", dbg_obj], verbose)
     if force or _newer(LIB_DBG, [dbg_obj] + objs[1:]):
         _run([NVCC] + ARCH + ["-shared", "-o", LIB_DBG, dbg_obj] + objs[1:] + ["-cudart", "static", "-lpthread"], verbose)
+    # the batched caller for anchor dumps (include/mm2chain_dump.h); finds the library next to itself
+    rsrc = os.path.join(HERE, "host/replay_main.cpp")
+    if force or _newer(REPLAY, [rsrc, LIB, os.path.join(ROOT, "include/mm2chain_dump.h")] + hdrs):
+        _run(["g++", "-O2", "-std=c++17", "-Wall"] + INC + [rsrc, "-o", REPLAY, "-L" + HERE, "-lmm2chain_b200", "-Wl,-rpath,$ORIGIN", "-lz"], verbose)
     return LIB
 
 
