@@ -137,7 +137,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		const bool act = lane < n_act;
 		const int j = jt - lane;
 		const int s = j & (RING - 1);
-		int32_t xj, yj, fj, pj, sidj = sidi;
+		int32_t xj, yj, fj, pj, sidj = sidi, tj_deep = -1;
 		const bool in_ring = !DEEP || jt - n_act + 1 >= ring_lo;   // warp-uniform: the whole chunk is resident in the ring
 		if (in_ring) {
 			const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
@@ -147,16 +147,21 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 				__syncwarp();
 			}
 		} else {
+			// (never the first chunk of a scan: that one is always resident.)  The cell's memory stamp is fetched together with
+			// the cell: the stamps of earlier chunks are in place by now (end of their loop body) and the ones from inside this
+			// chunk come through the one-hot OR, so a deep chunk costs one round trip to L2, not two.
 			xj = 0, yj = 0, fj = 0, pj = -1;
 			if (act) {
 				if (j >= ring_lo) {
 					const int4 q = ring.a[s];
 					xj = q.x, yj = q.y, fj = q.z, pj = q.w;
+					tj_deep = ring.b[s].y;
 					if (GENERAL) sidj = (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff);
 				} else {                                           // deep look-back: L1/L2
 					MM2B_CHK(j >= 0 && j < i, 0x1);
 					const ulonglong2 t = __ldg(rc.A + j);
 					xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j];
+					tj_deep = rc.T[j];
 					sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
 				}
 			}
@@ -222,12 +227,7 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 		unsigned hitv;
 		if (jt == i - 1) hitv = __ballot_sync(FULL, valid) & hot;
 		else {
-			int32_t tj;
-			if (in_ring) tj = ring.b[s].y;
-			else {
-				tj = !act ? -1 : j >= ring_lo ? ring.b[s].y : rc.T[j];
-				__syncwarp();
-			}
+			const int32_t tj = in_ring ? ring.b[s].y : tj_deep;
 			hitv = __ballot_sync(FULL, valid && (tj == i || (hot >> lane & 1u)));
 		}
 		// records (chain.c:226, strict '>'), n_skip, whether the loop breaks in this chunk, and the last record before the
