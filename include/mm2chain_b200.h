@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MM2B_ABI_VERSION 1
+#define MM2B_ABI_VERSION 2
 
 /* == mm128_t (minimap.h:53).  x = rev<<63 | rid<<32 | ref_pos;  y = seg_id<<48 | flags(40..43) | q_span<<32 | q_pos */
 typedef struct { uint64_t x, y; } mm2b_anchor_t;
@@ -61,6 +61,7 @@ typedef struct {
 	int64_t window_cells;            /* sum over anchors of the window size i - st after the max_iter clamp (chain.c:192-193); 0 unless counting is on */
 	int64_t n_general_reads;         /* reads that took the general (multi-segment / cDNA / gap_scale != 1) scoring path */
 	double  h2d_ms, kernel_ms, d2h_ms; /* device-side timings of the last host-buffer call (CUDA events), 0 for device calls */
+	int64_t n_heavy_reads;           /* reads chained by the heavy-read kernel (one CTA per read: long windows, e.g. tandem repeats) */
 } mm2b_stats_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */

@@ -40,7 +40,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "cells_ref", "window_cells", "n_general_reads")] + \
-               [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")]
+               [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")] + [("n_heavy_reads", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -33,8 +33,12 @@ struct mm2b_workspace {
 	int64_t max_anchors, max_reads;
 	uint8_t *scratch;           // SCRATCH_BYTES_PER_ANCHOR * max_anchors
 	int32_t *order;             // max_reads
+	int32_t *heavy_list;        // max_reads: reads routed to the heavy-read kernel
+	uint8_t *heavy_flag;        // max_reads
+	int heavy_on;               // MM2B_HEAVY (default 1)
+	long long heavy_min_cells;  // MM2B_HEAVY_MIN_CELLS: estimated window cells from which a read counts as heavy
 	int64_t *tile;              // 2 * ceil(max_reads / 2048)
-	int *small;                 // [0] work counter, [64..320) length buckets
+	int *small;                 // [0] work counter, [2] heavy-read count, [3] heavy-read cursor, [64..320) length buckets
 	unsigned long long *counters;
 	int32_t *dbg_fpv;           // 3 * max_anchors when MM2B_KEEP_FPV=1
 	size_t bytes;
@@ -74,6 +78,8 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	mm2b_workspace_t *ws = (mm2b_workspace_t*)calloc(1, sizeof(*ws));
 	ws->device = device, ws->max_anchors = max_anchors, ws->max_reads = max_reads;
 	{ const char *e = getenv("MM2B_COUNT_CELLS"); ws->count_cells = e && atoi(e) > 0; }
+	{ const char *e = getenv("MM2B_HEAVY"); ws->heavy_on = e ? atoi(e) != 0 : 1; }
+	{ const char *e = getenv("MM2B_HEAVY_MIN_CELLS"); ws->heavy_min_cells = e ? atoll(e) : 16ll << 20; }
 	cudaDeviceGetAttribute(&ws->n_sms, cudaDevAttrMultiProcessorCount, device);
 	const size_t sz_scratch = (size_t)max_anchors * SCRATCH_BYTES_PER_ANCHOR;
 	const size_t sz_order = (size_t)max_reads * sizeof(int32_t);
@@ -81,15 +87,17 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	const char *keep = getenv("MM2B_KEEP_FPV");
 	bool ok = cuda_ok(cudaMalloc(&ws->scratch, sz_scratch), "cudaMalloc(scratch)")
 	       && cuda_ok(cudaMalloc(&ws->order, sz_order), "cudaMalloc(order)")
+	       && cuda_ok(cudaMalloc(&ws->heavy_list, sz_order), "cudaMalloc(heavy_list)")
+	       && cuda_ok(cudaMalloc(&ws->heavy_flag, (size_t)max_reads), "cudaMalloc(heavy_flag)")
 	       && cuda_ok(cudaMalloc(&ws->tile, sz_tile), "cudaMalloc(tile)")
 	       && cuda_ok(cudaMalloc(&ws->small, 512 * sizeof(int)), "cudaMalloc(small)")
-	       && cuda_ok(cudaMalloc(&ws->counters, 4 * sizeof(unsigned long long)), "cudaMalloc(counters)");
-	ws->bytes = sz_scratch + sz_order + sz_tile + 512 * sizeof(int) + 32;
+	       && cuda_ok(cudaMalloc(&ws->counters, 8 * sizeof(unsigned long long)), "cudaMalloc(counters)");
+	ws->bytes = sz_scratch + 2 * sz_order + (size_t)max_reads + sz_tile + 512 * sizeof(int) + 32;
 	if (ok && keep && atoi(keep) > 0) {
 		ok = cuda_ok(cudaMalloc(&ws->dbg_fpv, (size_t)max_anchors * 12), "cudaMalloc(dbg_fpv)");
 		ws->bytes += (size_t)max_anchors * 12;
 	}
-	if (ok) ok = cuda_ok(cudaMemset(ws->counters, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
+	if (ok) ok = cuda_ok(cudaMemset(ws->counters, 0, 8 * sizeof(unsigned long long)), "cudaMemset");
 	if (ok) ok = cuda_ok(cudaEventCreate(&ws->ev_k1[0]), "cudaEventCreate") && cuda_ok(cudaEventCreate(&ws->ev_k1[1]), "cudaEventCreate");
 	if (!ok) { mm2b_ws_destroy(ws); return 0; }
 	return ws;
@@ -101,7 +109,7 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 	cudaSetDevice(ws->device);
 	if (ws->ev_k1[0]) cudaEventDestroy(ws->ev_k1[0]);
 	if (ws->ev_k1[1]) cudaEventDestroy(ws->ev_k1[1]);
-	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->tile), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
+	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->heavy_list), cudaFree(ws->heavy_flag), cudaFree(ws->tile), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
 	free(ws);
 }
 
@@ -130,6 +138,13 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	ba.par = *par, ba.n_reads = n_reads, ba.off = d_off, ba.a = d_a, ba.scratch = ws->scratch;
 	ba.n_u = d_n_u, ba.n_v = d_n_v, ba.status = d_status, ba.order = ws->order, ba.work_counter = ws->small;
 	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors, ba.count_cells = ws->count_cells;
+	// Reads with long windows (tandem repeats) go to the heavy-read kernel when the batch's arguments allow its scoring path
+	// (same-segment genomic cost) and its ring holds a whole window; the cell tally is a warp-per-read feature.
+	if (ws->heavy_on && !ws->count_cells && !par->is_cdna && par->gap_scale == 1.0f && par->n_segs <= 1 && par->bw >= 0 && par->bw < (1 << 24)
+	    && par->max_dist_x > 0 && par->max_dist_y > 0 && par->max_iter > heavy_min_window() && (int64_t)par->max_iter + 64 <= heavy_ring_slots()) {
+		ba.heavy_flag = ws->heavy_flag, ba.heavy_list = ws->heavy_list, ba.heavy_count = ws->small + 2, ba.heavy_counter = ws->small + 3;
+		ba.heavy_min_cells = ws->heavy_min_cells;
+	}
 	cudaEventRecord(ws->ev_k1[0], stream);
 	launches += launch_chain(ba, ws->n_sms, stream);
 	cudaEventRecord(ws->ev_k1[1], stream);
@@ -153,7 +168,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	int prev = -1;
 	cudaGetDevice(&prev);
 	if (prev != ws->device) cudaSetDevice(ws->device);
-	unsigned long long c[4] = {0, 0, 0, 0};
+	unsigned long long c[5] = {0, 0, 0, 0, 0};
 	int64_t tot[2] = {0, 0};
 	bool ok = cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize")
 	       && cuda_ok(cudaMemcpy(c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
@@ -165,6 +180,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	st->n_reads = ws->last_reads, st->n_anchors = ws->last_anchors;
 	st->n_chains = tot[0], st->n_chained = tot[1];
 	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1], st->cells_ref = (int64_t)c[2], st->window_cells = (int64_t)c[3];
+	st->n_heavy_reads = (int64_t)c[4];
 	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
 	return ok ? MM2B_OK : MM2B_ERR_CUDA;
 }

@@ -29,7 +29,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef MM2B_RING
 #define MM2B_RING 256
 #endif
-constexpr int RING = MM2B_RING;          // ring slots per warp (power of two)
+constexpr int LIGHT_RING = MM2B_RING;    // ring slots per warp in the warp-per-read kernel (power of two)
 constexpr int RING_ARRAYS = 6;          // x_lo, y_lo, f, p, v, t
 // 2 warps per CTA, 16 CTAs per SM (32 warps/SM, 64 registers): small CTAs retire as soon as their reads are done, so when
 // several sub-batch kernels share the GPU (the host-buffer pipeline) SM slots are handed on at 2-read granularity.
@@ -85,6 +85,7 @@ __device__ __forceinline__ int lowest_lane(unsigned m) { return __popc((m - 1u) 
 struct Ring {
 	int4 *a;
 	int2 *b;
+	int32_t *coop;          // mailbox of the heavy-read kernel (CTA-cooperative scans); unused by the warp-per-read kernel
 };
 
 struct DpConst {
@@ -111,7 +112,7 @@ struct DpConst {
 //    with closed form x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum d.  S only drops at records, so the running
 //    minimum is a minimum over the record lanes: scalar work on the two vote masks, no shuffles;
 //  * the loop breaks at the first hit lane with x > max_skip; the new (max_f, max_j) is the last record before it.
-template <bool GENERAL, bool DEEP, bool COUNT>
+template <int RING, bool GENERAL, bool DEEP, bool COUNT>
 __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo,
                                                   int32_t xi, int32_t qi, int32_t q_span, int32_t sidi,
                                                   int32_t &max_f, int32_t &max_j, unsigned &n_chunks, unsigned &n_cells)
@@ -307,8 +308,160 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 #undef MM2B_CHUNK_END
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Heavy reads: scans shared by the warps of a CTA
+// ---------------------------------------------------------------------------------------------------------------
+// A read in tandem repeats has windows at the max_iter clamp (thousands of anchors) and scans dozens of chunks per anchor; on
+// one warp that is a serial chain of ~100 instructions per chunk.  The heavy-read kernel gives such a read a CTA of HEAVY_WARPS
+// warps and a ring that holds the whole window.  Warp 0 runs the read exactly like the warp-per-read kernel; for a long scan
+// it posts the anchor in a mailbox and all warps take the window's chunks round-robin, HEAVY_WARPS chunks per round:
+//   A  every warp scores its chunk and writes ALL its stamps (chain.c:233) to the ring                           -> barrier
+//   B  every warp reads its cells' stamps and reduces the chunk to a summary that does not depend on the scan's state:
+//      the chunk's maximum score and its number of stamped valid cells (a stamp only comes from a nearer cell, and the
+//      nearer chunks stamped in A of this round or earlier)                                                        -> barrier
+//   C  every warp folds the round's summaries in chunk order with the same replicated state (max_f, max_j, n_skip): a chunk
+//      whose maximum does not beat max_f has no record, so it is n_skip += hits and one compare (chain.c:229-231); a chunk
+//      with a record is resolved in detail by its owner (which still holds the lanes' scores) and published       -> barrier
+// Stamps and summaries of chunks past the break are computed in vain and never looked at, like the lanes past the break
+// inside a chunk.
+constexpr int HEAVY_RING = 8192;           // covers max_iter = 5000 entirely: no look-back below the ring in this kernel
+constexpr int HEAVY_WARPS = 8;
+constexpr int COOP_MIN_CELLS = 128;        // windows longer than this are scanned cooperatively
+constexpr int COOP_WORDS = 64;             // mailbox: [0,8) job, [16,32) chunk summaries, [32,64) detailed results
+enum { JOB_SCAN = 1, JOB_EXIT = 2 };
+enum { BAR_JOB = 1, BAR_STAMPS = 2, BAR_SUMM = 3, BAR_DETAIL = 4 };
+
+__device__ __forceinline__ void cta_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(HEAVY_WARPS * 32) : "memory"); }
+
+// One chunk whose maximum beats the running max, i.e. with at least one record: cases (ii) and (iii) of scan_predecessors
+// (kept as a separate copy so that the warp-per-read kernel's hot loop stays exactly as tuned).  Returns whether the loop breaks.
+__device__ __forceinline__ bool resolve_records(int32_t sc, unsigned hitv, int lane, int jt, int max_skip, int32_t &max_f, int32_t &max_j, int &n_skip)
+{
+	const unsigned cand = __ballot_sync(FULL, sc > max_f);
+	const int32_t top = __reduce_max_sync(FULL, sc);
+	const int32_t top_j = __reduce_max_sync(FULL, sc == top ? jt - lane : INT_MIN);
+	const int last = jt - top_j;
+	unsigned recmask = 1u << last;
+	if ((cand & (recmask - 1u)) == 0) {                       // one record
+		const unsigned hitmask = hitv & ~recmask;
+		const unsigned h1 = hitmask & (recmask - 1u), h2 = hitmask & ~(recmask - 1u);
+		const int x1 = n_skip + __popc(h1);
+		const int x2 = x1 > 0 ? x1 - 1 : 0;
+		const int x3 = x2 + __popc(h2);
+		const bool early = x1 > max_skip;
+		if (!early) max_f = top, max_j = top_j;
+		n_skip = x3;
+		return early || x3 > max_skip;
+	}
+	for (int r = lowest_lane(cand); r != last;) {             // several records
+		recmask |= 1u << r;
+		const int32_t t = __shfl_sync(FULL, sc, r);
+		r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
+	}
+	const unsigned hm = hitv & ~recmask;
+	bool broke = false;
+	unsigned take = recmask;
+	if (hm == 0) {
+		n_skip -= __popc(recmask);
+		n_skip = n_skip > 0 ? n_skip : 0;
+	} else {
+		int corr = 0, floor_all = 0, done = 0;
+		for (unsigned rm = recmask; rm; rm &= rm - 1) {
+			const unsigned below = (rm - 1u) & ~rm;
+			const int S_r = n_skip + __popc(hm & below) - (++done);
+			floor_all = S_r < floor_all ? S_r : floor_all;
+			if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
+		}
+		const unsigned le = lanemask_lt(lane) | (1u << lane);
+		const int x = n_skip + __popc(hm & le) - __popc(recmask & le) - corr;
+		const unsigned over = __ballot_sync(FULL, ((hm >> lane) & 1u) && x > max_skip);
+		if (over) broke = true, take = recmask & bits_below(lowest_lane(over));
+		else n_skip = n_skip + __popc(hm) - done - floor_all;
+	}
+	if (take) {
+		const int l2 = 31 - __clz(take);
+		max_f = __shfl_sync(FULL, sc, l2);
+		max_j = jt - l2;
+	}
+	return broke;
+}
+
+// The scan of anchor i over [st, i) by all warps of the CTA (same-segment, non-cDNA cost only); w = this warp's index.
+template <int RING>
+__device__ void coop_scan(const DpConst &c, const Ring &ring, int lane, int w, int i, int st, int32_t xi, int32_t qi, int32_t q_span,
+                          int32_t &max_f_out, int32_t &max_j_out)
+{
+	int32_t *summ = ring.coop + 16, *detail = ring.coop + 32;
+	int32_t max_f = q_span, max_j = -1;
+	int n_skip = 0;
+	const int n_chunks = (i - st + 31) >> 5;
+	bool broke = false;
+	for (int g0 = 0; g0 < n_chunks && !broke; g0 += HEAVY_WARPS) {
+		// A: this warp's chunk of the round
+		const int jt = i - 1 - 32 * (g0 + w);
+		const int left = jt - st + 1;                             // <= 0 for a warp without a chunk in the last round
+		const bool act = lane < left;
+		const int j = jt - lane;
+		const int s = j & (RING - 1);
+		const int4 q = ring.a[s];
+		const int32_t pj = q.w;
+		const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)q.x);
+		const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)q.y);
+		const int32_t diff = dr - dq;
+		const int32_t dd = diff < 0 ? -diff : diff;
+		const bool valid = act && dr != 0 && (uint32_t)(dq - 1) < (uint32_t)c.max_dq_same && dd <= c.bw;    // chain.c:202-205
+		const int32_t md = dq < dr ? dq : dr;
+		int32_t sc = md < q_span ? md : q_span;
+		const float fdd = __int2float_rn(dd);
+		const int c_lin = __float2int_rz(__fmul_rn(fdd, c.avg));
+		int lg = (__float_as_int(fdd) >> 23) - 127;
+		lg = lg < 0 ? 0 : lg;
+		sc = valid ? sc - (c_lin + (lg >> 1)) + q.z : INT_MIN;
+		MM2B_CHK(!valid || (j >= st && j < i && pj < j), 0x100);
+		if (valid && pj >= st) ring.b[pj & (RING - 1)].y = i;
+		__syncwarp();
+		cta_bar(BAR_STAMPS);
+		// B: state-independent summary
+		const int32_t tj = ring.b[s].y;
+		const unsigned hitv = __ballot_sync(FULL, valid && tj == i);
+		const int32_t best = __reduce_max_sync(FULL, sc);
+		if (lane == 0) summ[2 * w] = best, summ[2 * w + 1] = __popc(hitv);
+		__syncwarp();
+		cta_bar(BAR_SUMM);
+		// C: fold in chunk order (every warp, same values)
+		int2 mine = make_int2(INT_MIN, 0);
+		if (lane < HEAVY_WARPS) mine = *(const int2*)&summ[2 * lane];
+		__syncwarp();
+		const int in_round = n_chunks - g0 < HEAVY_WARPS ? n_chunks - g0 : HEAVY_WARPS;
+		for (int k = 0; k < in_round; ++k) {
+			const int32_t mk = __shfl_sync(FULL, mine.x, k);
+			const int hk = __shfl_sync(FULL, mine.y, k);
+			if (mk > max_f) {                                     // chunk k holds a record: its owner resolves it with the state so far
+				if (w == k) {
+					int32_t f2 = max_f, j2 = max_j;
+					int s2 = n_skip;
+					const bool b2 = resolve_records(sc, hitv, lane, jt, c.max_skip, f2, j2, s2);
+					if (lane == 0) *(int4*)&detail[4 * k] = make_int4(f2, j2, s2, b2 ? 1 : 0);
+					__syncwarp();
+				}
+				cta_bar(BAR_DETAIL);
+				int4 d = make_int4(0, 0, 0, 0);
+				if (lane == 0) d = *(const int4*)&detail[4 * k];
+				__syncwarp();
+				max_f = __shfl_sync(FULL, d.x, 0), max_j = __shfl_sync(FULL, d.y, 0), n_skip = __shfl_sync(FULL, d.z, 0);
+				broke = __shfl_sync(FULL, d.w, 0) != 0;
+			} else {                                              // no record: the counter only goes up (chain.c:229-231)
+				n_skip += hk;
+				broke = n_skip > c.max_skip;
+			}
+			if (broke) break;
+		}
+	}
+	max_f_out = max_f, max_j_out = max_j;
+}
+
 // The sequential step for one block of 32 anchors: the anchors flagged in `todo` (non-empty window), in index order.
-template <bool GENERAL, bool DEEP, bool COUNT>
+template <int RING, bool GENERAL, bool DEEP, bool COUNT, bool COOP>
 __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int base, int ring_lo,
                                             unsigned todo, int32_t seg, int st_k, unsigned &n_chunks, unsigned &n_cells)
 {
@@ -326,7 +479,16 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 		const int32_t q_span = me.z;
 		const int32_t sidi = GENERAL ? __shfl_sync(FULL, seg, ii) : 0;
 		int32_t max_f = q_span, max_j = -1;
-		scan_predecessors<GENERAL, DEEP, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
+		if (COOP && !GENERAL && i - st > COOP_MIN_CELLS) {     // a long scan in the heavy-read kernel: all warps of the CTA share it
+			if (lane == 0) {
+				ring.coop[0] = JOB_SCAN, ring.coop[1] = i, ring.coop[2] = st, ring.coop[3] = me.x, ring.coop[4] = me.y, ring.coop[5] = q_span;
+				ring.coop[6] = __float_as_int(c.avg);
+			}
+			__syncwarp();
+			cta_bar(BAR_JOB);
+			coop_scan<RING>(c, ring, lane, 0, i, st, me.x, me.y, q_span, max_f, max_j);
+		} else
+		scan_predecessors<RING, GENERAL, DEEP, COUNT>(c, rc, ring, lane, i, st, ring_lo, me.x, me.y, q_span, sidi, max_f, max_j, n_chunks, n_cells);
 		// f[i], p[i] (chain.c:236): one lane publishes them to the anchor's slot; untouched if no predecessor won.
 		// v[i] is not needed by the scan at all; it is filled in per block afterwards (dp_fill).
 		MM2B_CHK(max_j < i && max_j >= -1 && (max_j < 0 || max_j >= st) && (DEEP || max_j < 0 || max_j >= ring_lo), 0x8);
@@ -345,12 +507,12 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 // and publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = -1} to the ring.  Anchors whose window is empty
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool GENERAL, bool COUNT>
-__device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, bool lo_safe, int32_t *smem, int lane,
+template <int RING, bool GENERAL, bool COUNT, bool COOP>
+__device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, bool lo_safe, int32_t *smem, int32_t *coop, int lane,
                         unsigned long long &n_chunks64, unsigned long long &n_cells64, unsigned long long &n_window64)
 {
 	Ring ring;
-	ring.a = (int4*)smem, ring.b = (int2*)(smem + 4 * RING);
+	ring.a = (int4*)smem, ring.b = (int2*)(smem + 4 * RING), ring.coop = coop;
 	const ulonglong2 *A = rc.A;
 	const int n = rc.n;
 	DpConst c;
@@ -445,8 +607,8 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 		}
 		__syncwarp();
 
-		if (!deep_block) chain_block<GENERAL, false, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
-		else chain_block<GENERAL, true, COUNT>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
+		if (!deep_block) chain_block<RING, GENERAL, false, COUNT, COOP>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
+		else chain_block<RING, GENERAL, true, COUNT, false>(c, rc, ring, lane, base, ring_lo, todo, seg, st_k, n_chunks, n_cells);
 		// Block epilogue.  v[i] = max(f[i], v[p[i]]) (chain.c:237) is the maximum of f along the chain behind i.  Inside the block
 		// it is resolved by pointer jumping over the lanes (5 rounds cover 32 anchors); a chain that leaves the block picks up the
 		// finished v of an earlier block from the ring (or from HBM when it reaches below the ring).  Then one coalesced write
@@ -791,11 +953,74 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 // the persistent loop and guards EVERY shuffle/vote/redux with a `BRA.DIV` + `WARPSYNC.COLLECTIVE` slow path (2 extra
 // instructions per collective: ~16 of the ~150 per anchor).  Found by bisecting SASS; one missing __syncwarp() after the
 // `if (lane == 0) ...` at the end of a read was enough to poison the whole kernel.
+// mm_chain_dp for read r by one warp: prologue (chain.c:46-49), fill, extraction.  RING_N / COOP select the kernel flavour.
+template <int RING_N, bool COUNT, bool COOP>
+__device__ __forceinline__ void chain_one_read(const BatchArgs &args, int64_t r, int32_t *ring, int32_t *coop, int lane,
+                                               unsigned long long &n_chunks, unsigned long long &n_general, unsigned long long &n_cells,
+                                               unsigned long long &n_window)
+{
+	const int64_t o = args.off[r];
+	const int64_t n64 = args.off[r + 1] - o;
+	if (n64 <= 0) {                                                               // chain.c:38-41
+		if (lane == 0) args.n_u[r] = 0, args.n_v[r] = 0, args.status[r] = MM2B_READ_EMPTY;
+		__syncwarp();
+		return;
+	}
+	ReadCtx rc;
+	rc.n = (int)n64;
+	rc.A = (const ulonglong2*)(args.a + o);
+	uint8_t *s = args.scratch + (size_t)o * SCRATCH_BYTES_PER_ANCHOR;
+	const size_t n = (size_t)n64;
+	rc.F = (int32_t*)s, rc.P = (int32_t*)(s + 4 * n), rc.X = (uint64_t*)(s + 8 * n);
+	rc.V = (int32_t*)(s + 16 * n), rc.T = (int32_t*)(s + 20 * n), rc.U = (uint64_t*)(s + 24 * n), rc.UF = (uint64_t*)(s + 32 * n);
+
+	// chain.c:46-49: zero t[], sum the 8-bit q_span fields; also find out whether every anchor carries the same segment id
+	uint64_t sum = 0;
+	uint32_t seg_diff = 0;
+	const uint32_t seg0 = (uint32_t)(__ldg(&rc.A[0].y) >> SEG_SHIFT & 0xff);
+	uint32_t max_xl = 0;                     // largest low word of x (reference position): see the window search in dp_fill
+	for (int k = lane; k < rc.n; k += 32) {
+		const ulonglong2 t = __ldg(rc.A + k);
+		sum += t.y >> 32 & 0xff;
+		seg_diff |= (uint32_t)(t.y >> SEG_SHIFT & 0xff) ^ seg0;
+		max_xl = max_xl > (uint32_t)t.x ? max_xl : (uint32_t)t.x;
+		rc.T[k] = 0;
+	}
+	__syncwarp();
+	const bool lo_safe = args.par.max_dist_x >= 0 && (uint64_t)__reduce_max_sync(FULL, max_xl) + (uint64_t)args.par.max_dist_x < (1ull << 32);
+#pragma unroll
+	for (int d = 16; d; d >>= 1) {
+		sum += __shfl_xor_sync(FULL, sum, d);
+		seg_diff |= __shfl_xor_sync(FULL, seg_diff, d);
+	}
+	// `.01 * (float)sum_qspan / n` — double arithmetic on a float-rounded sum, rounded once more to float
+	const float avg = __double2float_rn(__ddiv_rn(__dmul_rn(.01, (double)__ull2float_rn(sum)), (double)n64));
+	// (through a vote so that ptxas sees a warp-uniform branch: see the convergence note above)
+	const bool general = __any_sync(FULL, seg_diff != 0) || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24) || args.par.bw < 0
+	                  || args.par.n_segs > 1 || args.par.max_dist_x <= 0 || args.par.max_dist_y <= 0;
+	__syncwarp();
+	if (general) {
+		++n_general;
+		dp_fill<RING_N, true, COUNT, false>(args.par, rc, avg, lo_safe, ring, coop, lane, n_chunks, n_cells, n_window);
+	} else {
+		dp_fill<RING_N, false, COUNT, COOP>(args.par, rc, avg, lo_safe, ring, coop, lane, n_chunks, n_cells, n_window);
+	}
+	if (args.dbg_fpv) {      // test hook (MM2B_KEEP_FPV=1): keep f/p/v as they are at chain.c:238, before the extraction reuses v
+		int32_t *d = args.dbg_fpv + o;
+		for (int k = lane; k < rc.n; k += 32) d[k] = rc.F[k], d[args.n_anchors + k] = rc.P[k], d[2 * args.n_anchors + k] = rc.V[k];
+		__syncwarp();
+	}
+	int n_u = 0, n_v = 0, status = MM2B_READ_OK;
+	extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
+	if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status;
+	__syncwarp();
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 chain_reads_kernel(const BatchArgs args)
 {
-	__shared__ __align__(16) int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * RING];
+	__shared__ __align__(16) int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * LIGHT_RING];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int32_t *ring = smem_ring[warp];
 	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0, n_window = 0;
@@ -807,61 +1032,13 @@ chain_reads_kernel(const BatchArgs args)
 		slot = __shfl_sync(FULL, slot, 0);
 		if (slot >= args.n_reads) break;
 		const int64_t r = args.order ? args.order[slot] : slot;
-		const int64_t o = args.off[r];
-		const int64_t n64 = args.off[r + 1] - o;
-		if (n64 <= 0) {                                                               // chain.c:38-41
-			if (lane == 0) args.n_u[r] = 0, args.n_v[r] = 0, args.status[r] = MM2B_READ_EMPTY;
+		if (args.heavy_flag) {                                                        // reads taken by the heavy-read kernel
+			int hv = 0;
+			if (lane == 0) hv = args.heavy_flag[r];
 			__syncwarp();
-			continue;
+			if (__shfl_sync(FULL, hv, 0)) continue;
 		}
-		ReadCtx rc;
-		rc.n = (int)n64;
-		rc.A = (const ulonglong2*)(args.a + o);
-		uint8_t *s = args.scratch + (size_t)o * SCRATCH_BYTES_PER_ANCHOR;
-		const size_t n = (size_t)n64;
-		rc.F = (int32_t*)s, rc.P = (int32_t*)(s + 4 * n), rc.X = (uint64_t*)(s + 8 * n);
-		rc.V = (int32_t*)(s + 16 * n), rc.T = (int32_t*)(s + 20 * n), rc.U = (uint64_t*)(s + 24 * n), rc.UF = (uint64_t*)(s + 32 * n);
-
-		// chain.c:46-49: zero t[], sum the 8-bit q_span fields; also find out whether every anchor carries the same segment id
-		uint64_t sum = 0;
-		uint32_t seg_diff = 0;
-		const uint32_t seg0 = (uint32_t)(__ldg(&rc.A[0].y) >> SEG_SHIFT & 0xff);
-		uint32_t max_xl = 0;                     // largest low word of x (reference position): see the window search in dp_fill
-		for (int k = lane; k < rc.n; k += 32) {
-			const ulonglong2 t = __ldg(rc.A + k);
-			sum += t.y >> 32 & 0xff;
-			seg_diff |= (uint32_t)(t.y >> SEG_SHIFT & 0xff) ^ seg0;
-			max_xl = max_xl > (uint32_t)t.x ? max_xl : (uint32_t)t.x;
-			rc.T[k] = 0;
-		}
-		__syncwarp();
-		const bool lo_safe = args.par.max_dist_x >= 0 && (uint64_t)__reduce_max_sync(FULL, max_xl) + (uint64_t)args.par.max_dist_x < (1ull << 32);
-#pragma unroll
-		for (int d = 16; d; d >>= 1) {
-			sum += __shfl_xor_sync(FULL, sum, d);
-			seg_diff |= __shfl_xor_sync(FULL, seg_diff, d);
-		}
-		// `.01 * (float)sum_qspan / n` — double arithmetic on a float-rounded sum, rounded once more to float
-		const float avg = __double2float_rn(__ddiv_rn(__dmul_rn(.01, (double)__ull2float_rn(sum)), (double)n64));
-		// (through a vote so that ptxas sees a warp-uniform branch: see the convergence note above)
-		const bool general = __any_sync(FULL, seg_diff != 0) || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24) || args.par.bw < 0
-		                  || args.par.n_segs > 1 || args.par.max_dist_x <= 0 || args.par.max_dist_y <= 0;
-		__syncwarp();
-		if (general) {
-			++n_general;
-			dp_fill<true, COUNT>(args.par, rc, avg, lo_safe, ring, lane, n_chunks, n_cells, n_window);
-		} else {
-			dp_fill<false, COUNT>(args.par, rc, avg, lo_safe, ring, lane, n_chunks, n_cells, n_window);
-		}
-		if (args.dbg_fpv) {      // test hook (MM2B_KEEP_FPV=1): keep f/p/v as they are at chain.c:238, before the extraction reuses v
-			int32_t *d = args.dbg_fpv + o;
-			for (int k = lane; k < rc.n; k += 32) d[k] = rc.F[k], d[args.n_anchors + k] = rc.P[k], d[2 * args.n_anchors + k] = rc.V[k];
-			__syncwarp();
-		}
-		int n_u = 0, n_v = 0, status = MM2B_READ_OK;
-		extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
-		if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status;
-		__syncwarp();
+		chain_one_read<LIGHT_RING, COUNT, false>(args, r, ring, nullptr, lane, n_chunks, n_general, n_cells, n_window);
 	}
 	if (COUNT) {
 #pragma unroll
@@ -872,6 +1049,99 @@ chain_reads_kernel(const BatchArgs args)
 		if (n_chunks) atomicAdd(&args.counters[0], n_chunks);
 		if (n_general) atomicAdd(&args.counters[1], n_general);
 		if (n_cells) atomicAdd(&args.counters[2], n_cells);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1h: heavy reads, one CTA per read (see "Heavy reads" above).  Warp 0 is the read's warp; the others serve its long scans.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HEAVY_SMEM_BYTES = (RING_ARRAYS * HEAVY_RING + COOP_WORDS) * 4;
+
+__global__ void __launch_bounds__(HEAVY_WARPS * 32, 1)
+chain_heavy_kernel(const BatchArgs args)
+{
+	extern __shared__ __align__(16) int32_t heavy_smem[];
+	int32_t *ring = heavy_smem, *coop = heavy_smem + RING_ARRAYS * HEAVY_RING;
+	const int lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);      // through a shuffle: warp-uniform by construction (convergence note)
+	if (warp != 0) {
+		DpConst c;
+		c.max_dist_x = args.par.max_dist_x, c.max_dist_y = args.par.max_dist_y, c.bw = args.par.bw, c.max_skip = args.par.max_skip, c.max_iter = args.par.max_iter;
+		c.max_dq_same = args.par.max_dist_x < args.par.max_dist_y ? args.par.max_dist_x : args.par.max_dist_y;
+		c.cap_dr = false, c.is_cdna = false, c.avg = 0.f, c.gap_scale = 1.0;
+		Ring rg;
+		rg.a = (int4*)ring, rg.b = (int2*)(ring + 4 * HEAVY_RING), rg.coop = coop;
+		for (;;) {
+			cta_bar(BAR_JOB);
+			int v = 0;
+			if (lane < 8) v = coop[lane];
+			__syncwarp();
+			if (__shfl_sync(FULL, v, 0) == JOB_EXIT) break;
+			c.avg = __int_as_float(__shfl_sync(FULL, v, 6));
+			int32_t f, jj;
+			coop_scan<HEAVY_RING>(c, rg, lane, warp, __shfl_sync(FULL, v, 1), __shfl_sync(FULL, v, 2), __shfl_sync(FULL, v, 3), __shfl_sync(FULL, v, 4),
+			                      __shfl_sync(FULL, v, 5), f, jj);
+		}
+		return;
+	}
+	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0, n_window = 0;
+	int n_heavy = 0;
+	if (lane == 0) n_heavy = *args.heavy_count;
+	__syncwarp();
+	n_heavy = __shfl_sync(FULL, n_heavy, 0);
+	for (;;) {
+		int slot = 0;
+		if (lane == 0) slot = atomicAdd(args.heavy_counter, 1);
+		__syncwarp();
+		slot = __shfl_sync(FULL, slot, 0);
+		if (slot >= n_heavy) break;
+		chain_one_read<HEAVY_RING, false, true>(args, args.heavy_list[slot], ring, coop, lane, n_chunks, n_general, n_cells, n_window);
+	}
+	if (lane == 0) {
+		coop[0] = JOB_EXIT;
+		if (n_general) atomicAdd(&args.counters[1], n_general);
+		if (blockIdx.x == 0) args.counters[4] = (unsigned long long)n_heavy;
+	}
+	__syncwarp();
+	cta_bar(BAR_JOB);
+}
+
+// Which reads go to the heavy-read kernel: an estimate of the read's window cells (sum over anchors of min(i - st, max_iter),
+// chain.c:192-193) from 32 sampled anchors.  One warp per read.
+constexpr int HEAVY_MIN_ANCHORS = 64;
+
+__global__ void __launch_bounds__(256) classify_heavy_kernel(const BatchArgs args)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < args.n_reads; r += n_warps) {
+		const int64_t o = args.off[r], n = args.off[r + 1] - o;
+		bool heavy = false;
+		// (a window has at most max_iter cells, so a read with fewer than heavy_min_cells / max_iter anchors cannot qualify: no sampling)
+		if (n >= HEAVY_MIN_ANCHORS && n * (int64_t)args.par.max_iter >= args.heavy_min_cells) {
+			const ulonglong2 *A = (const ulonglong2*)(args.a + o);
+			const uint64_t win = (uint64_t)(int64_t)args.par.max_dist_x;
+			const int64_t k = (int64_t)(lane + 1) * n / 33;
+			const uint64_t x = __ldg(&A[k].x);
+			int64_t lo = 0, hi = k;
+			while (lo < hi) {
+				const int64_t mid = (lo + hi) >> 1;
+				if (x > __ldg(&A[mid].x) + win) lo = mid + 1;
+				else hi = mid;
+			}
+			__syncwarp();
+			long long w = k - lo;
+			w = w > args.par.max_iter ? args.par.max_iter : w;
+#pragma unroll
+			for (int d = 16; d; d >>= 1) w += __shfl_xor_sync(FULL, w, d);
+			const long long mean_window = w / 32;
+			heavy = mean_window > COOP_MIN_CELLS && mean_window * n >= args.heavy_min_cells;
+		}
+		if (lane == 0) {
+			args.heavy_flag[r] = heavy ? 1 : 0;
+			if (heavy) args.heavy_list[atomicAdd(args.heavy_count, 1)] = (int32_t)r;
+		}
+		__syncwarp();
 	}
 }
 
@@ -1040,14 +1310,32 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 {
 	if (args.n_reads <= 0) return 0;
 	cudaMemsetAsync(args.work_counter, 0, sizeof(int), stream);
-	cudaMemsetAsync(args.counters, 0, 4 * sizeof(unsigned long long), stream);
+	cudaMemsetAsync(args.counters, 0, 5 * sizeof(unsigned long long), stream);
 	int64_t ctas = (args.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const int64_t resident = (int64_t)n_sms * CTAS_PER_SM;
 	if (ctas > resident) ctas = resident;
+	int launches = 1;
+	if (args.heavy_flag) {          // classify, then the heavy reads on CTAs of their own (same stream: a heavy read outlasts everything else anyway)
+		static bool attr_set[64];
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev < 64 && !attr_set[dev]) {
+			cudaFuncSetAttribute(chain_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAVY_SMEM_BYTES);
+			attr_set[dev] = true;
+		}
+		cudaMemsetAsync(args.heavy_count, 0, 2 * sizeof(int), stream);          // heavy_count and heavy_counter are adjacent
+		const int64_t warps_needed = args.n_reads, blocks = (warps_needed + 7) / 8;
+		classify_heavy_kernel<<<(int)(blocks > 4 * n_sms ? 4 * n_sms : blocks), 256, 0, stream>>>(args);
+		chain_heavy_kernel<<<n_sms, HEAVY_WARPS * 32, HEAVY_SMEM_BYTES, stream>>>(args);
+		launches += 2;
+	}
 	if (args.count_cells) chain_reads_kernel<true><<<(int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args);
 	else chain_reads_kernel<false><<<(int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args);
-	return 1;
+	return launches;
 }
+
+int heavy_ring_slots() { return HEAVY_RING; }
+int heavy_min_window() { return COOP_MIN_CELLS; }
 
 int launch_offsets(int64_t n_reads, const int32_t *n_u, const int32_t *n_v, int64_t *u_off, int64_t *b_off,
                    int64_t *tile_scratch, cudaStream_t stream)

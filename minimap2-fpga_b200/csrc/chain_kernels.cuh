@@ -23,10 +23,15 @@ struct BatchArgs {
 	int32_t *n_u, *n_v, *status;
 	const int32_t *order;           // processing order (longest reads first) or nullptr
 	int *work_counter;              // persistent-warp work queue
-	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells, [3] window cells
+	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells, [3] window cells, [4] reads taken by the heavy-read kernel
 	int32_t *dbg_fpv;               // optional 3 x n_anchors int32 (f, p, v) copy for tests, or nullptr
 	int64_t n_anchors;
 	int count_cells;                // tally reference-semantics cells / issued chunks (statistics only; costs kernel time)
+	// heavy-read kernel (one CTA per read with long windows); all null / 0 when it is not used for this batch
+	uint8_t *heavy_flag;            // per read: taken by the heavy-read kernel
+	int32_t *heavy_list;            // the reads it takes
+	int *heavy_count, *heavy_counter;   // adjacent ints: length of heavy_list, its work-queue cursor
+	long long heavy_min_cells;      // a read is heavy when its estimated window cells reach this (and its mean window is long)
 };
 
 struct EmitArgs {
@@ -47,6 +52,8 @@ int launch_offsets(int64_t n_reads, const int32_t *n_u, const int32_t *n_v, int6
                    int64_t *tile_scratch, cudaStream_t stream);
 int launch_emit(const EmitArgs &args, int n_sms, cudaStream_t stream);
 double measure_int32_peak(int device);
+int heavy_ring_slots();          // ring capacity of the heavy-read kernel: it needs max_iter + 64 <= this
+int heavy_min_window();          // ... and only pays off for windows longer than this
 unsigned debug_flags();          // range-check violations seen so far (0x80000000 | codes) in the -DMM2B_DEBUG_CHECKS build, else 0
 
 }  // namespace mm2b

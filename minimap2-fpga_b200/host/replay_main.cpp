@@ -96,7 +96,7 @@ template <class T> struct Pinned {    // mm2b_host_alloc'ed array (pinned: the c
 	~Pinned() { mm2b_host_free(p); }
 };
 
-struct Totals { long long reads = 0, anchors = 0, chains = 0, chained = 0, calls = 0, bad_reads = 0; double seconds = 0; };
+struct Totals { long long reads = 0, anchors = 0, chains = 0, chained = 0, calls = 0, bad_reads = 0, heavy = 0; double seconds = 0; };
 
 int usage()
 {
@@ -181,7 +181,7 @@ int main(int argc, char **argv)
 				if (repeats == 1 || rep > 0) best = std::min(best, dt);
 			}
 			if (rc) break;
-			gt.reads += (long long)nr, gt.anchors += (long long)na, gt.chains += st.n_chains, gt.chained += st.n_chained, gt.seconds += best, ++gt.calls;
+			gt.reads += (long long)nr, gt.anchors += (long long)na, gt.chains += st.n_chains, gt.chained += st.n_chained, gt.heavy += st.n_heavy_reads, gt.seconds += best, ++gt.calls;
 			if (check) {
 				for (size_t r = 0; r < nr; ++r) {
 					const Record &rec = *g.reads[first + r];
@@ -203,12 +203,12 @@ int main(int argc, char **argv)
 			       g.par.min_cnt, g.par.min_sc, g.par.is_cdna, g.par.n_segs, (double)g.par.gap_scale, gt.reads, gt.anchors, gt.chains, gt.chained, gt.calls,
 			       gt.seconds * 1e3, gt.reads / std::max(gt.seconds, 1e-12), gt.anchors / std::max(gt.seconds, 1e-12),
 			       check ? (gt.bad_reads ? "  MISMATCH" : "  identical to the recorded results") : "");
-		tot.reads += gt.reads, tot.anchors += gt.anchors, tot.chains += gt.chains, tot.chained += gt.chained, tot.calls += gt.calls, tot.seconds += gt.seconds, tot.bad_reads += gt.bad_reads;
+		tot.reads += gt.reads, tot.anchors += gt.anchors, tot.chains += gt.chains, tot.chained += gt.chained, tot.calls += gt.calls, tot.seconds += gt.seconds, tot.bad_reads += gt.bad_reads, tot.heavy += gt.heavy;
 	}
 	}
 	if (rc == 0)
-		printf("total  devices %d | reads %lld anchors %lld chains %lld chained %lld | %lld call(s) %.3f ms  %.3g reads/s  %.3g anchors/s | mismatching reads %lld%s\n",
-		       mm2b_num_devices(), tot.reads, tot.anchors, tot.chains, tot.chained, tot.calls, tot.seconds * 1e3, tot.reads / std::max(tot.seconds, 1e-12),
+		printf("total  devices %d | reads %lld (%lld on the heavy-read kernel) anchors %lld chains %lld chained %lld | %lld call(s) %.3f ms  %.3g reads/s  %.3g anchors/s | mismatching reads %lld%s\n",
+		       mm2b_num_devices(), tot.reads, tot.heavy, tot.anchors, tot.chains, tot.chained, tot.calls, tot.seconds * 1e3, tot.reads / std::max(tot.seconds, 1e-12),
 		       tot.anchors / std::max(tot.seconds, 1e-12), tot.bad_reads, check ? "" : " (not checked)");
 	mm2b_shutdown();
 	if (rc == 0 && check && tot.bad_reads) rc = 1;
