@@ -325,9 +325,9 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 // Stamps and summaries of chunks past the break are computed in vain and never looked at, like the lanes past the break
 // inside a chunk.
 constexpr int HEAVY_RING = 8192;           // covers max_iter = 5000 entirely: no look-back below the ring in this kernel
-constexpr int HEAVY_WARPS = 8;
+constexpr int HEAVY_WARPS = 16;
 constexpr int COOP_MIN_CELLS = 128;        // windows longer than this are scanned cooperatively
-constexpr int COOP_WORDS = 64;             // mailbox: [0,8) job, [16,32) chunk summaries, [32,64) detailed results
+constexpr int COOP_WORDS = 128;            // mailbox: [0,8) job, [16,48) chunk summaries, [48,112) detailed results
 enum { JOB_SCAN = 1, JOB_EXIT = 2 };
 enum { BAR_JOB = 1, BAR_STAMPS = 2, BAR_SUMM = 3, BAR_DETAIL = 4 };
 
@@ -391,7 +391,7 @@ template <int RING>
 __device__ void coop_scan(const DpConst &c, const Ring &ring, int lane, int w, int i, int st, int32_t xi, int32_t qi, int32_t q_span,
                           int32_t &max_f_out, int32_t &max_j_out)
 {
-	int32_t *summ = ring.coop + 16, *detail = ring.coop + 32;
+	int32_t *summ = ring.coop + 16, *detail = ring.coop + 16 + 2 * HEAVY_WARPS;
 	int32_t max_f = q_span, max_j = -1;
 	int n_skip = 0;
 	const int n_chunks = (i - st + 31) >> 5;
@@ -428,33 +428,41 @@ __device__ void coop_scan(const DpConst &c, const Ring &ring, int lane, int w, i
 		if (lane == 0) summ[2 * w] = best, summ[2 * w + 1] = __popc(hitv);
 		__syncwarp();
 		cta_bar(BAR_SUMM);
-		// C: fold in chunk order (every warp, same values)
+		// C: fold in chunk order (every warp, same values).  Lane k holds chunk k's summary; votes find the first chunk with a
+		// record and, from a prefix sum of the hit counts, the first chunk in which the counter passes max_skip.
 		int2 mine = make_int2(INT_MIN, 0);
 		if (lane < HEAVY_WARPS) mine = *(const int2*)&summ[2 * lane];
 		__syncwarp();
 		const int in_round = n_chunks - g0 < HEAVY_WARPS ? n_chunks - g0 : HEAVY_WARPS;
-		for (int k = 0; k < in_round; ++k) {
-			const int32_t mk = __shfl_sync(FULL, mine.x, k);
-			const int hk = __shfl_sync(FULL, mine.y, k);
-			if (mk > max_f) {                                     // chunk k holds a record: its owner resolves it with the state so far
-				if (w == k) {
-					int32_t f2 = max_f, j2 = max_j;
-					int s2 = n_skip;
-					const bool b2 = resolve_records(sc, hitv, lane, jt, c.max_skip, f2, j2, s2);
-					if (lane == 0) *(int4*)&detail[4 * k] = make_int4(f2, j2, s2, b2 ? 1 : 0);
-					__syncwarp();
-				}
-				cta_bar(BAR_DETAIL);
-				int4 d = make_int4(0, 0, 0, 0);
-				if (lane == 0) d = *(const int4*)&detail[4 * k];
-				__syncwarp();
-				max_f = __shfl_sync(FULL, d.x, 0), max_j = __shfl_sync(FULL, d.y, 0), n_skip = __shfl_sync(FULL, d.z, 0);
-				broke = __shfl_sync(FULL, d.w, 0) != 0;
-			} else {                                              // no record: the counter only goes up (chain.c:229-231)
-				n_skip += hk;
-				broke = n_skip > c.max_skip;
+		for (int k0 = 0; k0 < in_round;) {                        // chunks [k0, in_round) are still to be folded
+			const bool todo = lane >= k0 && lane < in_round;
+			const unsigned recs = __ballot_sync(FULL, todo && mine.x > max_f);
+			int h = todo ? mine.y : 0;                            // inclusive prefix sum of the hits over the chunks still to fold
+#pragma unroll
+			for (int d = 1; d < HEAVY_WARPS; d <<= 1) {
+				const int o = __shfl_up_sync(FULL, h, d);
+				if (lane >= d) h += o;
 			}
+			const unsigned over = __ballot_sync(FULL, todo && n_skip + h > c.max_skip);
+			const int kr = recs ? lowest_lane(recs) : 32, kb = over ? lowest_lane(over) : 32;
+			if (kb < kr) { broke = true; break; }                 // the counter passes max_skip before any record (chain.c:229-231)
+			if (kr == 32) { n_skip += __shfl_sync(FULL, h, in_round - 1); break; }
+			if (kr > k0) n_skip += __shfl_sync(FULL, h, kr - 1);  // up to the chunk with a record; its owner resolves that one in detail
+			if (w == kr) {
+				int32_t f2 = max_f, j2 = max_j;
+				int s2 = n_skip;
+				const bool b2 = resolve_records(sc, hitv, lane, jt, c.max_skip, f2, j2, s2);
+				if (lane == 0) *(int4*)&detail[4 * kr] = make_int4(f2, j2, s2, b2 ? 1 : 0);
+				__syncwarp();
+			}
+			cta_bar(BAR_DETAIL);
+			int4 d4 = make_int4(0, 0, 0, 0);
+			if (lane == 0) d4 = *(const int4*)&detail[4 * kr];
+			__syncwarp();
+			max_f = __shfl_sync(FULL, d4.x, 0), max_j = __shfl_sync(FULL, d4.y, 0), n_skip = __shfl_sync(FULL, d4.z, 0);
+			broke = __shfl_sync(FULL, d4.w, 0) != 0;
 			if (broke) break;
+			k0 = kr + 1;
 		}
 	}
 	max_f_out = max_f, max_j_out = max_j;
