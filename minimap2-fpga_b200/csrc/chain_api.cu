@@ -143,7 +143,7 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	if (ws->heavy_on && !ws->count_cells && !par->is_cdna && par->gap_scale == 1.0f && par->n_segs <= 1 && par->bw >= 0 && par->bw < (1 << 24)
 	    && par->max_dist_x > 0 && par->max_dist_y > 0 && par->max_iter > heavy_min_window() && (int64_t)par->max_iter + 64 <= heavy_ring_slots()) {
 		ba.heavy_flag = ws->heavy_flag, ba.heavy_list = ws->heavy_list, ba.heavy_count = ws->small + 2, ba.heavy_counter = ws->small + 3;
-		ba.heavy_min_cells = ws->heavy_min_cells;
+		ba.heavy_min_cells = ws->heavy_min_cells, ba.heavy_cap = ws->n_sms;
 	}
 	cudaEventRecord(ws->ev_k1[0], stream);
 	launches += launch_chain(ba, ws->n_sms, stream);

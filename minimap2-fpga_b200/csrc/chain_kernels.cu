@@ -17,6 +17,8 @@
 //     aligned blocks of p[]) and the final order by reference position (including the reference's unstable radix-sort
 //     tie order) run in the same warp right after the fill while f/p/v are still in L1/L2; a scan + gather kernel
 //     pair then packs u[]/b[] in read order.
+//   * the few reads with very long windows (tandem repeats) get a CTA of 16 warps and a ring that holds a whole window;
+//     their long scans are shared by the warps (chain_heavy_kernel, "Heavy reads" below).
 // No tensor cores (nothing here is a contraction) and no collective (reads are independent).
 #include "chain_kernels.cuh"
 #include <limits.h>
@@ -1097,6 +1099,7 @@ chain_heavy_kernel(const BatchArgs args)
 	if (lane == 0) n_heavy = *args.heavy_count;
 	__syncwarp();
 	n_heavy = __shfl_sync(FULL, n_heavy, 0);
+	n_heavy = n_heavy < args.heavy_cap ? n_heavy : args.heavy_cap;            // (the counter also counted the reads turned away)
 	for (;;) {
 		int slot = 0;
 		if (lane == 0) slot = atomicAdd(args.heavy_counter, 1);
@@ -1146,8 +1149,12 @@ __global__ void __launch_bounds__(256) classify_heavy_kernel(const BatchArgs arg
 			heavy = mean_window > COOP_MIN_CELLS && mean_window * n >= args.heavy_min_cells;
 		}
 		if (lane == 0) {
+			if (heavy) {                                          // beyond one wave of CTAs the warp-per-read kernel has the higher throughput
+				const int idx = atomicAdd(args.heavy_count, 1);
+				if (idx < args.heavy_cap) args.heavy_list[idx] = (int32_t)r;
+				else heavy = false;
+			}
 			args.heavy_flag[r] = heavy ? 1 : 0;
-			if (heavy) args.heavy_list[atomicAdd(args.heavy_count, 1)] = (int32_t)r;
 		}
 		__syncwarp();
 	}

@@ -32,6 +32,7 @@ struct BatchArgs {
 	int32_t *heavy_list;            // the reads it takes
 	int *heavy_count, *heavy_counter;   // adjacent ints: length of heavy_list, its work-queue cursor
 	long long heavy_min_cells;      // a read is heavy when its estimated window cells reach this (and its mean window is long)
+	int heavy_cap;                  // at most this many reads per batch (one wave of CTAs): the kernel buys latency, not throughput
 };
 
 struct EmitArgs {
