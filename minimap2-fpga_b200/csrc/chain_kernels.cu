@@ -512,9 +512,9 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 // (one segment id, !is_cdna, gap_scale == 1) with a pure-integer + one float-multiply cost; GENERAL=true carries
 // the full cost switch of chain.c:211-219 (cross-segment, cDNA, gap_scale in double).
 //
-// Anchors are taken 32 at a time.  For a block, every lane first finds its own anchor's window start st (chain.c:192-193)
-// by binary search — st_i = max(lower_bound{s : x_s + max_dist_x >= x_i}, i - max_iter) since the input is sorted by x —
-// and publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = -1} to the ring.  Anchors whose window is empty
+// Anchors are taken 32 at a time.  For a block, every lane publishes {x_lo, y_lo, f = q_span, p = -1 | v = q_span, t = -1} to
+// the ring and finds its own anchor's window start st (chain.c:192-193) as a lower bound —
+// st_i = max(lower_bound{s : x_s + max_dist_x >= x_i}, i - max_iter) since the input is sorted by x.  Anchors whose window is empty
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
 template <int RING, bool GENERAL, bool COUNT, bool COOP>
