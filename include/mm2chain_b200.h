@@ -107,6 +107,10 @@ size_t mm2b_ws_bytes(const mm2b_workspace_t *ws);
 /* Statistics switch: when on, batches run on this workspace also tally cells_ref / cells_issued (mm2b_stats_t).  Off by default
  * (the tally costs kernel time and is not part of the result); also switched on by the environment variable MM2B_COUNT_CELLS=1. */
 void mm2b_ws_set_counting(mm2b_workspace_t *ws, int on);
+/* Optional hint for the NEXT batch on this workspace: the anchor count of its longest read (the host knows the offsets, the
+ * device call does not).  When no read can be long enough for the heavy-read kernel, that kernel and its classification pass
+ * are not launched at all.  -1 (the default, restored after every batch) = unknown: classify on the device. */
+void mm2b_ws_set_longest_read(mm2b_workspace_t *ws, int64_t n_anchors);
 
 /* All d_* pointers are device memory on the workspace's device; `stream` is a cudaStream_t passed as void* (NULL = default
  * stream).  Asynchronous: work is enqueued on `stream` and the call returns.  `n_anchors` == off[n_reads] (known to the host).

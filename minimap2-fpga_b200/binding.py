@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("MM2B_LIB") or os.path.join(HERE, "libmm2chain_b200.so
 ANCHOR = np.dtype([("x", "<u8"), ("y", "<u8")])
 READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 
-EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version",
+EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version", "mm2b_ws_set_longest_read",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
            "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
@@ -80,6 +80,7 @@ def load():
     L.mm2b_ws_destroy.restype, L.mm2b_ws_destroy.argtypes = None, [vp]
     L.mm2b_ws_bytes.restype, L.mm2b_ws_bytes.argtypes = C.c_size_t, [vp]
     L.mm2b_ws_set_counting.restype, L.mm2b_ws_set_counting.argtypes = None, [vp, i32]
+    L.mm2b_ws_set_longest_read.restype, L.mm2b_ws_set_longest_read.argtypes = None, [vp, C.c_int64]
     L.mm2b_set_counting.restype, L.mm2b_set_counting.argtypes = None, [i32]
     L.mm2b_chain_batch_device.restype = i32
     L.mm2b_chain_batch_device.argtypes = [vp, C.POINTER(Params), i64, i64] + [vp] * 9 + [vp]

@@ -37,6 +37,7 @@ struct mm2b_workspace {
 	uint8_t *heavy_flag;        // max_reads
 	int heavy_on;               // MM2B_HEAVY (default 1)
 	long long heavy_min_cells;  // MM2B_HEAVY_MIN_CELLS: estimated window cells from which a read counts as heavy
+	int64_t longest_hint;       // mm2b_ws_set_longest_read: longest read of the next batch, or -1
 	int64_t *tile;              // 2 * ceil(max_reads / 2048)
 	int *small;                 // [0] work counter, [2] heavy-read count, [3] heavy-read cursor, [64..320) length buckets
 	unsigned long long *counters;
@@ -76,7 +77,7 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	if (max_reads < 1) max_reads = 1;
 	if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return 0;
 	mm2b_workspace_t *ws = (mm2b_workspace_t*)calloc(1, sizeof(*ws));
-	ws->device = device, ws->max_anchors = max_anchors, ws->max_reads = max_reads;
+	ws->device = device, ws->max_anchors = max_anchors, ws->max_reads = max_reads, ws->longest_hint = -1;
 	{ const char *e = getenv("MM2B_COUNT_CELLS"); ws->count_cells = e && atoi(e) > 0; }
 	{ const char *e = getenv("MM2B_HEAVY"); ws->heavy_on = e ? atoi(e) != 0 : 1; }
 	{ const char *e = getenv("MM2B_HEAVY_MIN_CELLS"); ws->heavy_min_cells = e ? atoll(e) : 16ll << 20; }
@@ -115,6 +116,7 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 
 size_t mm2b_ws_bytes(const mm2b_workspace_t *ws) { return ws ? ws->bytes : 0; }
 void mm2b_ws_set_counting(mm2b_workspace_t *ws, int on) { if (ws) ws->count_cells = on != 0; }
+void mm2b_ws_set_longest_read(mm2b_workspace_t *ws, int64_t n_anchors) { if (ws) ws->longest_hint = n_anchors; }
 const unsigned long long *mm2b_ws_counters_dev(const mm2b_workspace_t *ws) { return ws ? ws->counters : 0; }
 
 int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
@@ -140,7 +142,10 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors, ba.count_cells = ws->count_cells;
 	// Reads with long windows (tandem repeats) go to the heavy-read kernel when the batch's arguments allow its scoring path
 	// (same-segment genomic cost) and its ring holds a whole window; the cell tally is a warp-per-read feature.
-	if (ws->heavy_on && !ws->count_cells && !par->is_cdna && par->gap_scale == 1.0f && par->n_segs <= 1 && par->bw >= 0 && par->bw < (1 << 24)
+	// a window has at most max_iter cells: a batch whose longest read has fewer than heavy_min_cells / max_iter anchors has no heavy read
+	const bool may_have_heavy = ws->longest_hint < 0 || (ws->longest_hint >= 64 && ws->longest_hint * (int64_t)par->max_iter >= ws->heavy_min_cells);
+	ws->longest_hint = -1;
+	if (ws->heavy_on && may_have_heavy && !ws->count_cells && !par->is_cdna && par->gap_scale == 1.0f && par->n_segs <= 1 && par->bw >= 0 && par->bw < (1 << 24)
 	    && par->max_dist_x > 0 && par->max_dist_y > 0 && par->max_iter > heavy_min_window() && (int64_t)par->max_iter + 64 <= heavy_ring_slots()) {
 		ba.heavy_flag = ws->heavy_flag, ba.heavy_list = ws->heavy_list, ba.heavy_count = ws->small + 2, ba.heavy_counter = ws->small + 3;
 		ba.heavy_min_cells = ws->heavy_min_cells, ba.heavy_cap = ws->n_sms;

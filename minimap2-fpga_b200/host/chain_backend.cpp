@@ -182,7 +182,12 @@ bool stage_issue(Slot &s, Job *job, int si)
 	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0], na = job->off[sb.r1] - a0;
 	if (!s.ensure(na, nr)) return false;
 	mm2b_ws_set_counting(s.ws, g.count_cells.load());
-	for (int64_t r = 0; r <= nr; ++r) s.h_off[r] = job->off[sb.r0 + r] - a0;
+	int64_t longest = 0;
+	for (int64_t r = 0; r <= nr; ++r) {
+		s.h_off[r] = job->off[sb.r0 + r] - a0;
+		if (r > 0 && s.h_off[r] - s.h_off[r - 1] > longest) longest = s.h_off[r] - s.h_off[r - 1];
+	}
+	mm2b_ws_set_longest_read(s.ws, longest);          // lets the device call skip the heavy-read kernel when no read can qualify
 	cudaStream_t st = s.stream;
 	bool ok = cuda_ok(cudaEventRecord(s.ev[0], st), "cudaEventRecord")
 	       && cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off")
@@ -423,6 +428,11 @@ void flight_run(Batcher *bt, Flight &f)          // dispatcher thread, no lock h
 	mm2b_ws_set_counting(s.ws, 0);
 	for (int64_t r = 0; r < nr; ++r) s.h_off[r] = f.reqs[r]->a_off;
 	s.h_off[nr] = na;
+	{
+		int64_t longest = 0;
+		for (int64_t r = 0; r < nr; ++r) longest = std::max<int64_t>(longest, s.h_off[r + 1] - s.h_off[r]);
+		mm2b_ws_set_longest_read(s.ws, longest);
+	}
 	cudaStream_t st = s.stream;
 	bool ok = cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off")
 	       && cuda_ok(cudaMemcpyAsync(s.d_a, f.h_a, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
@@ -744,6 +754,7 @@ mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
 	const mm2b_params_t par = {max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
 	memcpy(t->h_a, a, (size_t)n * 16);
 	s.h_off[0] = 0, s.h_off[1] = n;
+	mm2b_ws_set_longest_read(s.ws, n);
 	cudaStream_t st = s.stream;
 	bool ok = cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, 16, cudaMemcpyHostToDevice, st), "H2D off")
 	       && cuda_ok(cudaMemcpyAsync(s.d_a, t->h_a, (size_t)n * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
