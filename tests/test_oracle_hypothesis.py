@@ -9,7 +9,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 def reads(draw):
     n = draw(st.integers(0, 60))
     rng = np.random.default_rng(draw(st.integers(0, 2 ** 32 - 1)))
-    style = draw(st.sampled_from(["cluster", "scatter", "dups", "two_strands"]))
+    style = draw(st.sampled_from(["cluster", "scatter", "dups", "two_strands", "carry"]))
     span = draw(st.sampled_from([1, 15, 19, 255]))
     if style == "cluster":
         r = 1000 + np.cumsum(rng.integers(0, 40, n)); q = span + np.cumsum(rng.integers(0, 40, n))
@@ -17,6 +17,9 @@ def reads(draw):
         r = rng.integers(0, 20000, n); q = rng.integers(span, 20000, n)
     elif style == "dups":
         r = 500 + rng.integers(0, 6, n) * 17; q = span + rng.integers(0, 6, n) * 17
+    elif style == "carry":      # positions just below 2^32 on rid 0, small ones on rid 1: x + max_dist_x carries into the rid word (chain.c:192)
+        top = rng.random(n) < 0.6
+        r = np.where(top, (1 << 32) - 1 - rng.integers(0, 6000, n), (1 << 32) + rng.integers(0, 6000, n)); q = span + rng.integers(0, 6000, n)
     else:
         r = 1000 + np.cumsum(rng.integers(1, 30, n)); q = span + np.cumsum(rng.integers(1, 30, n))
     rev = (rng.integers(0, 2, n) if style == "two_strands" else np.zeros(n, np.int64)).astype(np.uint64)
