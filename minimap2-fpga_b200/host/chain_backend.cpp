@@ -26,6 +26,7 @@
 
 #include "mm2chain_b200.h"
 #include "../csrc/shim_internal.h"
+#include "fiber_for.h"
 
 // kalloc of the host application (kalloc.c); weak so that the library also loads stand-alone (tests, bench)
 extern "C" void *kmalloc(void *km, size_t size) __attribute__((weak));
@@ -710,6 +711,78 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
 	return MM2B_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Batches of the fiber-based kt_for() (fiber_for.h): all reads parked on this OS thread, grouped by chaining arguments, one
+// mm2b_chain_batch call per group from pinned staging that belongs to the thread.
+struct FiberStage {
+	mm2b_anchor_t *a = nullptr, *b = nullptr;
+	uint64_t *u = nullptr;
+	int64_t *off = nullptr, *u_off = nullptr, *b_off = nullptr;
+	int32_t *n_u = nullptr, *n_v = nullptr, *status = nullptr;
+	int64_t cap_a = 0, cap_r = 0;
+	void reserve(int64_t na, int64_t nr)
+	{
+		if (na > cap_a) {
+			mm2b_host_free(a), mm2b_host_free(b), mm2b_host_free(u);
+			cap_a = std::max<int64_t>(na + na / 2, 1 << 20);
+			a = (mm2b_anchor_t*)mm2b_host_alloc((size_t)cap_a * 16), b = (mm2b_anchor_t*)mm2b_host_alloc((size_t)cap_a * 16);
+			u = (uint64_t*)mm2b_host_alloc((size_t)cap_a * 8);
+		}
+		if (nr > cap_r) {
+			mm2b_host_free(off), mm2b_host_free(u_off), mm2b_host_free(b_off), mm2b_host_free(n_u), mm2b_host_free(n_v), mm2b_host_free(status);
+			cap_r = std::max<int64_t>(2 * nr, 1024);
+			off = (int64_t*)mm2b_host_alloc((size_t)cap_r * 16), u_off = (int64_t*)mm2b_host_alloc((size_t)cap_r * 16);
+			b_off = (int64_t*)mm2b_host_alloc((size_t)cap_r * 16);          // (2 entries per read: every group needs one more than it has reads)
+			n_u = (int32_t*)mm2b_host_alloc((size_t)cap_r * 4), n_v = (int32_t*)mm2b_host_alloc((size_t)cap_r * 4);
+			status = (int32_t*)mm2b_host_alloc((size_t)cap_r * 4);
+		}
+		if (!a || !b || !u || !off || !u_off || !b_off || !n_u || !n_v || !status) fatal("pinned staging for kt_for batches");
+	}
+};
+
+void fiber_flush(mm2b::FiberReq **reqs, int n)
+{
+	static thread_local FiberStage st;       // lives as long as the OS thread: results stay valid until its next flush
+	int64_t na = 0;
+	for (int r = 0; r < n; ++r) na += reqs[r]->n;
+	st.reserve(na, n);
+	std::vector<char> done((size_t)n, 0);
+	int64_t a_base = 0, r_base = 0, o_base = 0;
+	for (int first = 0; first < n; ++first) {
+		if (done[first]) continue;
+		const mm2b_params_t par = reqs[first]->par;
+		int64_t cnt = 0, ga = 0;
+		int64_t *off = st.off + o_base;
+		off[0] = 0;
+		std::vector<int> members;
+		for (int r = first; r < n; ++r) {
+			if (done[r] || !same_par(reqs[r]->par, par)) continue;
+			done[r] = 1;
+			members.push_back(r);
+			memcpy(st.a + a_base + ga, reqs[r]->a, (size_t)reqs[r]->n * 16);
+			ga += reqs[r]->n;
+			off[++cnt] = ga;
+		}
+		if (mm2b_chain_batch(&par, cnt, off, st.a + a_base, st.n_u + r_base, st.n_v + r_base, st.status + r_base, st.u_off + o_base, st.b_off + o_base,
+		                     st.u + a_base, std::max<int64_t>(ga, 1), st.b + a_base, std::max<int64_t>(ga, 1), nullptr) != MM2B_OK) fatal("mm2b_chain_batch");
+		for (int64_t k = 0; k < cnt; ++k) {
+			mm2b::FiberReq *q = reqs[members[(size_t)k]];
+			q->n_u = st.n_u[r_base + k], q->n_v = st.n_v[r_base + k], q->status = st.status[r_base + k];
+			q->u = st.u + a_base + st.u_off[o_base + k], q->b = st.b + a_base + st.b_off[o_base + k];
+		}
+		a_base += ga, r_base += cnt, o_base += cnt + 1;
+	}
+}
+
+struct FiberFlushInstaller { FiberFlushInstaller() { mm2b::fiber_set_flush(fiber_flush); } } g_fiber_flush_installer;
+
+}  // namespace
+
+extern "C" {
+
 mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
                            float gap_scale, int is_cdna, int n_segs, int64_t n, mm2b_anchor_t *a, int *n_u_, uint64_t **_u,
                            void *km, int tid)
@@ -721,6 +794,22 @@ mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
 		return 0;
 	}
 	if (!g.up && ensure_up() != MM2B_OK) fatal("mm2b_init");
+	if (mm2b::fiber_active()) {                                       // under the fiber-based kt_for(): park, get chained with the others
+		mm2b::FiberReq req;
+		req.par = mm2b_params_t{max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
+		req.n = n, req.a = a, req.n_u = req.n_v = 0, req.status = MM2B_READ_NO_CHAIN, req.u = nullptr, req.b = nullptr;
+		mm2b::fiber_chain(&req);
+		host_kfree(km, a);                                            // chain.c:356 / :421 — `a` is consumed on every path
+		mm2b_anchor_t *b = nullptr;
+		if (req.status == MM2B_READ_OK) {
+			uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(req.n_u, 1) * 8);
+			b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)req.n_v * 16);
+			if (req.n_u > 0) memcpy(u, req.u, (size_t)req.n_u * 8);
+			if (req.n_v > 0) memcpy(b, req.b, (size_t)req.n_v * 16);
+			*n_u_ = req.n_u, *_u = u;
+		}
+		return b;
+	}
 	if (g.use_batcher) {
 		static thread_local int my_batcher = -1;
 		if (my_batcher < 0 || my_batcher >= (int)g_batchers.size()) my_batcher = g_batcher_rr.fetch_add(1) % (int)g_batchers.size();

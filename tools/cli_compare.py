@@ -16,10 +16,13 @@ def run(exe, t, env=None):
     p = subprocess.run([exe, "-x", "map-ont", "-t", str(t), td + "/ref.mmi", td + "/q.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **(env or {})))
     dt = time.time() - t0
     err = p.stderr.decode().splitlines()
-    tr = [l for l in err if "batcher" in l] + [l for l in err if "mapped" in l or "loaded/built" in l or "Real time" in l]
+    tr = [l for l in err if "batcher" in l or "chaining calls" in l][-2:] + [l for l in err if "mapped" in l or "loaded/built" in l or "Real time" in l]
     return dt, hashlib.md5(p.stdout).hexdigest(), p.stdout.count(b"\n"), tr
-for exe, t, env in (("oracle/_ref/minimap2-sw", 16, None), ("oracle/_ref/minimap2-b200", 16, {"MM2B_TRACE": "1"}), ("oracle/_ref/minimap2-b200", 128, {"MM2B_TRACE": "1"}),
-                    ("oracle/_ref/minimap2-b200", 512, {"MM2B_TRACE": "1"})):
+runs = [("oracle/_ref/minimap2-sw", 16, None), ("oracle/_ref/minimap2-b200", 16, {"MM2B_TRACE": "1"}), ("oracle/_ref/minimap2-b200", 128, {"MM2B_TRACE": "1"}),
+        ("oracle/_ref/minimap2-b200", 512, {"MM2B_TRACE": "1"})]
+if len(sys.argv) > 2 and sys.argv[2] == "fiber":     # the reference CLI on the fiber-based kt_for (host/fiber_for.cpp): -t = reads in flight
+    runs = [("oracle/_ref/minimap2-sw", 16, None), ("oracle/_ref/minimap2-fiber-b200", 512, {"MM2B_TRACE": "1"}), ("oracle/_ref/minimap2-fiber-b200", 2048, {"MM2B_TRACE": "1"})]
+for exe, t, env in runs:
     dt, md5, lines, tr = run(exe, t, env)
     print("%-16s -t %-3d wall %.2f s  %d PAF lines  md5 %s" % (exe.split("/")[-1], t, dt, lines, md5[:8]), flush=True)
     for l in tr: print("      " + l)
