@@ -743,9 +743,33 @@ struct FiberStage {
 	}
 };
 
+// kt_for()'s OS threads live for one call (one mini-batch of reads); the pinned staging outlives them in a pool
+std::mutex g_stage_mu;
+std::vector<FiberStage*> g_stage_pool;
+
+struct StageLease {                          // held by a thread for as long as it lives: its results stay valid until its next flush
+	FiberStage *st = nullptr;
+	FiberStage *get()
+	{
+		if (!st) {
+			std::lock_guard<std::mutex> lk(g_stage_mu);
+			if (!g_stage_pool.empty()) st = g_stage_pool.back(), g_stage_pool.pop_back();
+		}
+		if (!st) st = new FiberStage();
+		return st;
+	}
+	~StageLease()
+	{
+		if (!st) return;
+		std::lock_guard<std::mutex> lk(g_stage_mu);
+		g_stage_pool.push_back(st);
+	}
+};
+
 void fiber_flush(mm2b::FiberReq **reqs, int n)
 {
-	static thread_local FiberStage st;       // lives as long as the OS thread: results stay valid until its next flush
+	static thread_local StageLease lease;
+	FiberStage &st = *lease.get();
 	int64_t na = 0;
 	for (int r = 0; r < n; ++r) na += reqs[r]->n;
 	st.reserve(na, n);
@@ -777,7 +801,64 @@ void fiber_flush(mm2b::FiberReq **reqs, int n)
 	}
 }
 
-struct FiberFlushInstaller { FiberFlushInstaller() { mm2b::fiber_set_flush(fiber_flush); } } g_fiber_flush_installer;
+// MM2B_FIBER_ASYNC=1: the blocking batch call runs on a helper thread of the OS thread, which keeps seeding its other fibers
+// meanwhile (fiber_for.h: submit / wait).  Off by default until it has been timed on the GPU box.
+struct FiberFlusher {
+	std::thread th;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<mm2b::FiberReq*> reqs;
+	bool busy = false, quit = false;
+	void loop()
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		for (;;) {
+			cv.wait(lk, [&] { return busy || quit; });
+			if (quit) return;
+			lk.unlock();
+			fiber_flush(reqs.data(), (int)reqs.size());
+			lk.lock();
+			busy = false;
+			cv.notify_all();
+		}
+	}
+	~FiberFlusher()
+	{
+		if (!th.joinable()) return;
+		{ std::lock_guard<std::mutex> lk(mu); quit = true; }
+		cv.notify_all();
+		th.join();
+	}
+};
+
+void *fiber_submit(mm2b::FiberReq **reqs, int n)
+{
+	static thread_local FiberFlusher fl;     // dies with the OS thread (end of the kt_for() call): joins its helper
+	if (!fl.th.joinable()) fl.th = std::thread([p = &fl] { p->loop(); });
+	{
+		std::lock_guard<std::mutex> lk(fl.mu);
+		fl.reqs.assign(reqs, reqs + n);
+		fl.busy = true;
+	}
+	fl.cv.notify_all();
+	return &fl;
+}
+
+void fiber_wait(void *ticket)
+{
+	FiberFlusher *fl = (FiberFlusher*)ticket;
+	std::unique_lock<std::mutex> lk(fl->mu);
+	fl->cv.wait(lk, [&] { return !fl->busy; });
+}
+
+struct FiberFlushInstaller {
+	FiberFlushInstaller()
+	{
+		mm2b::fiber_set_flush(fiber_flush);
+		const char *e = getenv("MM2B_FIBER_ASYNC");
+		if (e && atoi(e) > 0) mm2b::fiber_set_async(fiber_submit, fiber_wait);
+	}
+} g_fiber_flush_installer;
 
 }  // namespace
 

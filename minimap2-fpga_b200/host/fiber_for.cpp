@@ -45,6 +45,8 @@ struct Sched {                           // one OS thread and the fibers it mult
 
 thread_local Sched *tl_sched = nullptr;
 std::atomic<FiberFlushFn> g_flush{nullptr};
+std::atomic<FiberSubmitFn> g_submit{nullptr};
+std::atomic<FiberWaitFn> g_wait{nullptr};
 
 size_t stack_bytes()
 {
@@ -108,9 +110,38 @@ inline void run(Sched &s, Fiber *f, std::vector<Fiber*> &parked)
 void sched_loop(Sched &s)
 {
 	tl_sched = &s;
-	std::vector<Fiber*> parked, batch;
+	const FiberSubmitFn submit = g_submit.load();
+	const FiberWaitFn wait = g_wait.load();
+	const bool async = submit != nullptr && wait != nullptr && s.fibers.size() >= 2;
+	// with an asynchronous backend a batch goes out as soon as half of the fibers are parked, and the other half keeps the
+	// core busy while it is away; otherwise the batch goes out when nothing else can run
+	const size_t submit_at = async ? (s.fibers.size() + 1) / 2 : s.fibers.size();
+	std::vector<Fiber*> parked, away;        // parked: waiting to be sent; away: sent, not back yet
 	std::vector<FiberReq*> reqs;
+	void *ticket = nullptr;
 	bool more = true;
+	auto send = [&] {
+		reqs.clear();
+		for (Fiber *f : parked) reqs.push_back(f->req);
+		++s.n_flushes, s.n_parked += (long)reqs.size();
+		if (async) {
+			ticket = submit(reqs.data(), (int)reqs.size());
+			away.swap(parked);
+			parked.clear();
+		} else {
+			g_flush.load()(reqs.data(), (int)reqs.size());
+			std::vector<Fiber*> batch;
+			batch.swap(parked);
+			for (Fiber *f : batch) run(s, f, parked);          // a fiber may park again (map.c:338 chains a second time)
+		}
+	};
+	auto receive = [&] {
+		wait(ticket);
+		ticket = nullptr;
+		std::vector<Fiber*> batch;
+		batch.swap(away);
+		for (Fiber *f : batch) run(s, f, parked);
+	};
 	for (;;) {
 		if (more) {                                            // start work on every idle fiber
 			for (Fiber *f : s.fibers) {
@@ -119,22 +150,29 @@ void sched_loop(Sched &s)
 				if (i >= s.sh->n) { more = false; break; }
 				f->job = i;
 				run(s, f, parked);
+				if (async && away.empty() && parked.size() >= submit_at) send();
 			}
 		}
-		if (parked.empty()) {
-			if (!more) break;                                  // nothing parked, nothing left to start: every fiber is idle
+		if (!away.empty()) {                                   // nothing else to start right now: take the batch back
+			receive();
+			if (away.empty() && !parked.empty() && (parked.size() >= submit_at || !more)) send();
 			continue;
 		}
-		// every fiber of this thread is parked in mm_chain_dp (or the work ran out): chain their requests in one go
-		batch.swap(parked);
-		parked.clear();
-		reqs.clear();
-		for (Fiber *f : batch) reqs.push_back(f->req);
-		g_flush.load()(reqs.data(), (int)reqs.size());
-		++s.n_flushes, s.n_parked += (long)reqs.size();
-		for (Fiber *f : batch) run(s, f, parked);              // a fiber may park again (map.c:338 chains a second time)
+		if (parked.empty()) {
+			if (!more) break;                                  // nothing parked, nothing away, nothing left to start
+			continue;
+		}
+		send();                                                // every runnable fiber is parked in mm_chain_dp (or the work ran out)
 	}
 	tl_sched = nullptr;
+}
+
+void fiber_init(Fiber &f)                  // (a function of its own: getcontext() is a returns-twice call)
+{
+	getcontext(&f.ctx);
+	f.ctx.uc_stack.ss_sp = f.stack, f.ctx.uc_stack.ss_size = stack_bytes(), f.ctx.uc_link = nullptr;
+	const uintptr_t p = (uintptr_t)&f;
+	makecontext(&f.ctx, (void (*)())fiber_main, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
 }
 
 int os_threads(int n_threads)
@@ -150,6 +188,7 @@ int os_threads(int n_threads)
 bool fiber_active() { return g_flush.load() != nullptr && tl_sched != nullptr && tl_sched->cur != nullptr; }
 
 void fiber_set_flush(FiberFlushFn fn) { g_flush.store(fn); }
+void fiber_set_async(FiberSubmitFn submit, FiberWaitFn wait) { g_submit.store(submit), g_wait.store(wait); }
 
 void fiber_chain(FiberReq *req)
 {
@@ -179,10 +218,7 @@ extern "C" void kt_for(int n_threads, void (*func)(void*, long, int), void *data
 		Fiber &f = fibers[t];
 		Sched &s = scheds[t % W];
 		f.sched = &s, f.tid = t, f.stack = stack_get();
-		getcontext(&f.ctx);
-		f.ctx.uc_stack.ss_sp = f.stack, f.ctx.uc_stack.ss_size = stack_bytes(), f.ctx.uc_link = nullptr;
-		const uintptr_t p = (uintptr_t)&f;
-		makecontext(&f.ctx, (void (*)())fiber_main, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+		fiber_init(f);
 		s.fibers.push_back(&f);
 	}
 	for (Sched &s : scheds) s.sh = &sh;

@@ -31,6 +31,13 @@ struct FiberReq {                        // one parked mm_chain_dp call
 // Chains all requests (blocking).  Called on the OS thread that owns the fibers.
 typedef void (*FiberFlushFn)(FiberReq **reqs, int n);
 
+// Optional asynchronous pair: submit() starts chaining the requests and returns a ticket at once, wait() blocks until they
+// are done.  With it an OS thread keeps running its other fibers while a batch is on the accelerator (two groups of fibers
+// take turns).  Both are called on the OS thread that owns the fibers.
+typedef void *(*FiberSubmitFn)(FiberReq **reqs, int n);
+typedef void (*FiberWaitFn)(void *ticket);
+void fiber_set_async(FiberSubmitFn submit, FiberWaitFn wait);
+
 bool fiber_active();                     // is the caller running on one of kt_for()'s fibers?
 void fiber_chain(FiberReq *req);         // park the request, run other fibers, return once it has been chained
 void fiber_set_flush(FiberFlushFn fn);   // who chains the batches (the backend installs its own at start-up)

@@ -46,7 +46,49 @@ static void sw_flush(mm2b::FiberReq **reqs, int n)
 	}
 }
 
-static struct Installer { Installer() { mm2b::fiber_set_flush(sw_flush); } } g_installer;
+/* Asynchronous variant (MM2_FIBER_SHIM_ASYNC=1): the same work on a helper thread per ticket, so that the scheduler's two-group
+ * pipelining runs against a backend that really is away while other fibers run. */
+#include <future>
+struct Ticket { std::future<void> done; std::vector<mm2b::FiberReq*> reqs; std::vector<void*> keep; };
+static void *sw_submit(mm2b::FiberReq **reqs, int n)
+{
+	static thread_local std::vector<Ticket*> old;            // results must outlive the fibers' copies: free two tickets late
+	if (old.size() >= 2) {
+		for (void *p : old.front()->keep) free(p);
+		delete old.front();
+		old.erase(old.begin());
+	}
+	Ticket *t = new Ticket;
+	t->reqs.assign(reqs, reqs + n);
+	t->done = std::async(std::launch::async, [t] {
+		for (mm2b::FiberReq *q : t->reqs) {
+			mm128_t *copy = (mm128_t*)malloc((size_t)q->n * sizeof(mm128_t));
+			memcpy(copy, q->a, (size_t)q->n * sizeof(mm128_t));
+			int n_u = 0;
+			uint64_t *u = 0;
+			mm128_t *b = mm_chain_dp_ref(q->par.max_dist_x, q->par.max_dist_y, q->par.bw, q->par.max_skip, q->par.max_iter, q->par.min_cnt, q->par.min_sc,
+			                             q->par.gap_scale, q->par.is_cdna, q->par.n_segs, q->n, copy, &n_u, &u, 0, 0);
+			int64_t n_v = 0;
+			for (int i = 0; i < n_u; ++i) n_v += (int32_t)u[i];
+			q->status = u ? MM2B_READ_OK : MM2B_READ_NO_CHAIN;
+			q->n_u = n_u, q->n_v = (int32_t)n_v, q->u = u, q->b = b;
+			if (u) t->keep.push_back(u);
+			if (b) t->keep.push_back(b);
+		}
+	});
+	old.push_back(t);
+	return t;
+}
+static void sw_wait(void *ticket) { ((Ticket*)ticket)->done.get(); }
+
+static struct Installer {
+	Installer()
+	{
+		mm2b::fiber_set_flush(sw_flush);
+		const char *e = getenv("MM2_FIBER_SHIM_ASYNC");
+		if (e && atoi(e) > 0) mm2b::fiber_set_async(sw_submit, sw_wait);
+	}
+} g_installer;
 
 extern "C" mm128_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
                                 float gap_scale, int is_cdna, int n_segs, int64_t n, mm128_t *a, int *n_u_, uint64_t **_u, void *km, int tid)

@@ -63,6 +63,15 @@ def test_more_fibers_than_reads_and_two_os_threads(cases):
     _check(SW, cases, 7, only=("syn_ccs", "splice", "tandem_iter64"), env={"MM2B_FIBER_OS_THREADS": "3", "MM2B_FIBER_STACK_KB": "256"})
 
 
+@pytest.mark.parametrize("threads", [2, 9, 64])
+def test_two_groups_of_fibers_against_an_asynchronous_backend(cases, threads):
+    """submit() / wait(): a batch goes out when half of an OS thread's fibers are parked, the other half keeps running."""
+    if not os.path.exists(SW):
+        pytest.skip("oracle/_ref/minimap2-fiber-sw was not built (needs /root/reference at build time)")
+    _check(SW, cases, threads, env={"MM2_FIBER_SHIM_ASYNC": "1"})
+    _check(SW, cases, threads, only=("syn_ont", "sr_paired", "tandem_iter64"), env={"MM2_FIBER_SHIM_ASYNC": "1", "MM2B_FIBER_OS_THREADS": "1"})
+
+
 @pytest.mark.gpu
 def test_reference_cli_on_fibers_with_the_b200_backend(cases):
     if not os.path.exists(B200):
