@@ -49,6 +49,17 @@ def _check(exe, cases, threads, only=None, env=None):
     assert not bad, "PAF differs from the reference at -t %d for: %s" % (threads, bad)
 
 
+def test_scheduler_unit(tmp_path):
+    """tests/native/fiber_unit.cpp: every item once, one item per tid at a time, results reach the right fiber; sync and async."""
+    exe = str(tmp_path / "fiber_unit")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "minimap2-fpga_b200", "host"),
+                           os.path.join(ROOT, "tests", "native", "fiber_unit.cpp"), os.path.join(ROOT, "minimap2-fpga_b200", "host", "fiber_for.cpp"),
+                           "-o", exe, "-lpthread"])
+    for env in ({}, {"MM2B_FIBER_OS_THREADS": "1"}, {"MM2B_FIBER_OS_THREADS": "5", "MM2B_FIBER_STACK_KB": "64"}):
+        out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **env), timeout=300)
+        assert out.returncode == 0 and b"FAILED" not in out.stdout and out.stdout.count(b": ok") == 48, (env, out.stdout.decode()[-1500:], out.stderr.decode()[-500:])
+
+
 @pytest.mark.parametrize("threads", [1, 4, 64])
 def test_reference_cli_on_fibers_with_software_chaining(cases, threads):
     if not os.path.exists(SW):
