@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MM2B_ABI_VERSION 2
+#define MM2B_ABI_VERSION 3
 
 /* == mm128_t (minimap.h:53).  x = rev<<63 | rid<<32 | ref_pos;  y = seg_id<<48 | flags(40..43) | q_span<<32 | q_pos */
 typedef struct { uint64_t x, y; } mm2b_anchor_t;
@@ -62,6 +62,10 @@ typedef struct {
 	int64_t n_general_reads;         /* reads that took the general (multi-segment / cDNA / gap_scale != 1) scoring path */
 	double  h2d_ms, kernel_ms, d2h_ms; /* device-side timings of the last host-buffer call (CUDA events), 0 for device calls */
 	int64_t n_heavy_reads;           /* reads chained by the heavy-read kernel (one CTA per read: long windows, e.g. tandem repeats) */
+	/* host-buffer calls only (ABI v3): what crossed PCIe and what the host threads did around it */
+	int64_t h2d_bytes, d2h_bytes;    /* bytes copied host->device / device->host by this call */
+	int64_t n_packed_subs, n_raw_subs; /* sub-batches whose anchors went over as 8-byte words + runs / as 16-byte mm128_t */
+	double  pack_ms, gather_ms;      /* summed wall time of the host-side packing / b[] gathering tasks (over all helper threads) */
 } mm2b_stats_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
@@ -86,21 +90,39 @@ void mm2b_host_free(void *p);
 /* ---- batch chaining, host buffers (the end-to-end path) ------------------------------------------------------- */
 
 /* Chain `n_reads` independent reads.  Read r owns anchors a[off[r] .. off[r+1]) (sorted by x, as map.c:245 leaves them).
- * Reads are sharded over the bound devices by per-device worker threads; results come back in input order:
+ * Reads are sharded over the bound devices by per-device worker threads; per-read results come back in input order:
  *   n_u[r], n_v[r], status[r]                 per read
  *   u[u_off[r] .. u_off[r]+n_u[r])            == the reference's final u[] for read r   (chain.c:419)
  *   b[b_off[r] .. b_off[r]+n_v[r])            == the reference's final b[] for read r   (chain.c:420)
- * u_off/b_off have n_reads+1 entries.  u_cap/b_cap are the capacities of u/b in elements; off[n_reads] always suffices.
- * `stats` may be NULL.  Blocking.  Thread-safe. */
+ * u_off[r] / b_off[r] say where read r's results are; the packing order inside u / b is NOT the read order (every read's warp
+ * reserves its own share of the output).  u_off/b_off have n_reads+1 entries (the last one is off[n_reads], the capacity
+ * actually needed).  u_cap/b_cap are the capacities of u/b in elements; off[n_reads] always suffices.
+ * `stats` may be NULL.  Blocking.  Thread-safe; concurrent calls share the devices. */
 int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
                      int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
                      uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats);
+
+/* The same call with the two PCIe diets spelled out (mm2b_chain_batch uses the defaults: packed input, b[] gathered on the host).
+ *   bi      when non-NULL receives, at the same offsets as b, the INDEX of every chained anchor inside its read
+ *           (b[b_off[r]+k] == a[off[r] + bi[b_off[r]+k]]): 4 bytes instead of 16 come back over PCIe, and a caller that still
+ *           holds a[] (every caller of mm_chain_dp does: map.c:316 passes it in) gathers b itself or uses the indices directly.
+ *           `b` may then be NULL.  With both b and bi the library gathers b on its helper threads.
+ *   flags   MM2B_F_RAW_INPUT      send anchors as 16-byte mm128_t.  Default: the helper threads pack every sub-batch into 8-byte
+ *                                 {x_lo, y_lo} words plus run-length lists of the high words (strand/rid; flags/q_span/segment) on
+ *                                 their way into the pinned staging buffer and the device restores mm128_t in HBM; a sub-batch
+ *                                 whose high words change too often (e.g. a homopolymer-compressed index) is sent raw by itself.
+ *           MM2B_F_DEVICE_GATHER  b[] comes back from the device as 16-byte anchors instead of being gathered on the host.
+ * Environment overrides of the defaults (tuning): MM2B_PACK=0|1, MM2B_GATHER=host|device, MM2B_HOST_THREADS=n. */
+enum { MM2B_F_RAW_INPUT = 1, MM2B_F_DEVICE_GATHER = 2 };
+int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
+                        int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
+                        uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int32_t *bi, int64_t b_cap, unsigned flags, mm2b_stats_t *stats);
 
 /* ---- batch chaining, device buffers (inputs already in HBM) --------------------------------------------------- */
 
 typedef struct mm2b_workspace mm2b_workspace_t;
 
-/* Scratch for batches of up to max_anchors anchors / max_reads reads on `device` (40 B per anchor + 64 B per read). */
+/* Scratch for batches of up to max_anchors anchors / max_reads reads on `device` (32 B per anchor + 9 B per read). */
 mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_reads);
 void mm2b_ws_destroy(mm2b_workspace_t *ws);
 size_t mm2b_ws_bytes(const mm2b_workspace_t *ws);
@@ -114,11 +136,27 @@ void mm2b_ws_set_longest_read(mm2b_workspace_t *ws, int64_t n_anchors);
 
 /* All d_* pointers are device memory on the workspace's device; `stream` is a cudaStream_t passed as void* (NULL = default
  * stream).  Asynchronous: work is enqueued on `stream` and the call returns.  `n_anchors` == off[n_reads] (known to the host).
- * d_u_off/d_b_off: n_reads+1 entries; d_u/d_b: capacity n_anchors elements each is always enough. */
+ * d_u_off/d_b_off: n_reads+1 entries (entry n_reads = total entries written); d_u/d_b: capacity n_anchors elements each is
+ * always enough.  Offsets are per read; the packing order is not the read order (see mm2b_chain_batch). */
 int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
                             const int64_t *d_off, const mm2b_anchor_t *d_a,
                             int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
                             uint64_t *d_u, mm2b_anchor_t *d_b, void *stream);
+
+/* The same with the chained anchors returned as int32 indices inside their read (d_bi, capacity n_anchors) instead of copies. */
+int mm2b_chain_batch_device_idx(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
+                                const int64_t *d_off, const mm2b_anchor_t *d_a,
+                                int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
+                                uint64_t *d_u, int32_t *d_bi, void *stream);
+/* Restore 16-byte anchors in HBM from the packed transfer format: d_lo[n_anchors] = {x_lo, y_lo} (uint32 pairs) and two run
+ * lists of {first anchor of the run, high word} (uint32 pairs, sorted, run 0 starts at anchor 0) for x and y. */
+int mm2b_unpack_anchors_device(int device, int64_t n_anchors, const void *d_lo, const void *d_xruns, int32_t n_xruns,
+                               const void *d_yruns, int32_t n_yruns, mm2b_anchor_t *d_a, void *stream);
+
+/* Host side of that format (pure CPU, what the helper threads of mm2b_chain_batch run per chunk): lo receives n uint32 pairs,
+ * xruns / yruns up to cap_runs uint32 pairs each.  MM2B_ERR_CAPACITY when the high words change more often than cap_runs. */
+int mm2b_pack_anchors(const mm2b_anchor_t *a, int64_t n, void *lo, void *xruns, int32_t *n_xruns, void *yruns, int32_t *n_yruns,
+                      int32_t cap_runs);
 
 /* Counters of the last batch run on this workspace (synchronises the given stream). */
 int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream, mm2b_stats_t *stats);
@@ -135,7 +173,8 @@ int mm2b_ws_copy_fpv(mm2b_workspace_t *ws, void *stream, int64_t n_anchors, int3
  * "this is the checking build", the low bits are violation codes.  Always 0 in the release build. */
 unsigned mm2b_debug_flags(void);
 
-/* Measured INT32 issue peak of `device` in G int-ops/s (IADD3/LOP3/IMNMX mix, all SMs), for the roofline. */
+/* Measured INT32 issue peak of `device` in G lane-instructions/s (LOP3 + VIADDMNMX chains on all SMs; 2 SASS instructions per
+ * source statement of 3 integer operations, so the operation-counted peak is 1.5 x this), for the roofline. */
 double mm2b_measure_int32_peak(int device);
 
 /* ---- the reference's own per-read boundary -------------------------------------------------------------------- */

@@ -20,7 +20,7 @@ READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version", "mm2b_ws_set_longest_read",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
-           "mm2b_chain_batch_device", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
+           "mm2b_chain_batch_device", "mm2b_chain_batch_device_idx", "mm2b_chain_batch_ex", "mm2b_unpack_anchors_device", "mm2b_pack_anchors", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
            "mm_chain_dp"]
 
 
@@ -40,7 +40,8 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "cells_ref", "window_cells", "n_general_reads")] + \
-               [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")] + [("n_heavy_reads", C.c_int64)]
+               [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")] + [("n_heavy_reads", C.c_int64)] + \
+               [(k, C.c_int64) for k in ("h2d_bytes", "d2h_bytes", "n_packed_subs", "n_raw_subs")] + [(k, C.c_double) for k in ("pack_ms", "gather_ms")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -76,6 +77,14 @@ def load():
     L.mm2b_host_free.restype, L.mm2b_host_free.argtypes = None, [vp]
     L.mm2b_chain_batch.restype = i32
     L.mm2b_chain_batch.argtypes = [C.POINTER(Params), i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, C.POINTER(Stats)]
+    L.mm2b_chain_batch_ex.restype = i32
+    L.mm2b_chain_batch_ex.argtypes = [C.POINTER(Params), i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, C.c_uint, C.POINTER(Stats)]
+    L.mm2b_chain_batch_device_idx.restype = i32
+    L.mm2b_chain_batch_device_idx.argtypes = [vp, C.POINTER(Params), i64, i64] + [vp] * 9 + [vp]
+    L.mm2b_unpack_anchors_device.restype = i32
+    L.mm2b_unpack_anchors_device.argtypes = [i32, i64, vp, vp, i32, vp, i32, vp, vp]
+    L.mm2b_pack_anchors.restype = i32
+    L.mm2b_pack_anchors.argtypes = [vp, i64, vp, vp, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32), i32]
     L.mm2b_ws_create.restype, L.mm2b_ws_create.argtypes = vp, [i32, i64, i64]
     L.mm2b_ws_destroy.restype, L.mm2b_ws_destroy.argtypes = None, [vp]
     L.mm2b_ws_bytes.restype, L.mm2b_ws_bytes.argtypes = C.c_size_t, [vp]
@@ -146,11 +155,17 @@ def _p(arr):
     return arr.ctypes.data_as(C.c_void_p)
 
 
-def chain_batch(par, off, a, out=None, want_stats=True):
-    """Chain a CSR batch of reads through mm2b_chain_batch (host buffers; H2D, kernels and D2H inside the call).
+F_RAW_INPUT, F_DEVICE_GATHER = 1, 2
+
+
+def chain_batch(par, off, a, out=None, want_stats=True, mode="default", flags=0):
+    """Chain a CSR batch of reads through the host-buffer batch call (H2D, kernels and D2H inside the call).
 
     off: int64[n_reads+1]; a: ANCHOR[off[-1]].  `out` may carry preallocated (ideally pinned) arrays
-    n_u, n_v, status, u_off, b_off, u, b; otherwise numpy arrays are allocated.  Returns a dict with those plus stats.
+    n_u, n_v, status, u_off, b_off, u, b / bi; otherwise numpy arrays are allocated.  Returns a dict with those plus stats.
+    mode: "default" = mm2b_chain_batch (b[] out, the library's default transfer formats);
+          "b" / "index" / "both" = mm2b_chain_batch_ex with b[], the int32 indices bi[], or both as outputs and `flags`
+          (F_RAW_INPUT, F_DEVICE_GATHER).
     """
     L = load()
     off = np.ascontiguousarray(off, dtype=np.int64)
@@ -163,13 +178,50 @@ def chain_batch(par, off, a, out=None, want_stats=True):
     o.setdefault("u_off", np.empty(n_reads + 1, np.int64))
     o.setdefault("b_off", np.empty(n_reads + 1, np.int64))
     o.setdefault("u", np.empty(max(n_anchors, 1), np.uint64))
-    o.setdefault("b", np.empty(max(n_anchors, 1), ANCHOR))
+    want_b, want_bi = mode in ("default", "b", "both"), mode in ("index", "both")
+    if want_b:
+        o.setdefault("b", np.empty(max(n_anchors, 1), ANCHOR))
+    if want_bi:
+        o.setdefault("bi", np.empty(max(n_anchors, 1), np.int32))
     st = Stats()
-    rc = L.mm2b_chain_batch(C.byref(par), n_reads, _p(off), _p(a), _p(o["n_u"]), _p(o["n_v"]), _p(o["status"]), _p(o["u_off"]),
-                            _p(o["b_off"]), _p(o["u"]), len(o["u"]), _p(o["b"]), len(o["b"]), C.byref(st) if want_stats else None)
+    if mode == "default":
+        rc = L.mm2b_chain_batch(C.byref(par), n_reads, _p(off), _p(a), _p(o["n_u"]), _p(o["n_v"]), _p(o["status"]), _p(o["u_off"]),
+                                _p(o["b_off"]), _p(o["u"]), len(o["u"]), _p(o["b"]), len(o["b"]), C.byref(st) if want_stats else None)
+    else:
+        cap = len(o["b"]) if want_b else len(o["bi"])
+        rc = L.mm2b_chain_batch_ex(C.byref(par), n_reads, _p(off), _p(a), _p(o["n_u"]), _p(o["n_v"]), _p(o["status"]), _p(o["u_off"]),
+                                   _p(o["b_off"]), _p(o["u"]), len(o["u"]), _p(o["b"]) if want_b else None, _p(o["bi"]) if want_bi else None,
+                                   cap, flags, C.byref(st) if want_stats else None)
     _check(rc, "mm2b_chain_batch")
     o["stats"] = st
     return o
+
+
+def gather_b(off, a, res):
+    """b[] from the index output of chain_batch(mode="index"): b[b_off[r]+k] = a[off[r] + bi[b_off[r]+k]] (what a caller that still
+    holds a[] does instead of receiving 16-byte copies over PCIe).  Returns an array laid out like res["b"] would be."""
+    n_v = res["n_v"].astype(np.int64)
+    b = np.zeros(len(res["bi"]), ANCHOR)
+    tot = int(n_v.sum())
+    if tot:
+        rid = np.repeat(np.arange(len(n_v)), n_v)
+        k = np.arange(tot) - np.repeat(np.cumsum(n_v) - n_v, n_v)
+        pos = res["b_off"][:-1][rid] + k
+        b[pos] = a[np.asarray(off[:-1])[rid] + res["bi"][pos]]
+    return b
+
+
+def pack_anchors(a, cap_runs=None):
+    """Host side of the packed transfer format (mm2b_pack_anchors): returns (lo[n,2] uint32, xruns[k,2], yruns[m,2])."""
+    L = load()
+    a = np.ascontiguousarray(a, dtype=ANCHOR)
+    n = len(a)
+    cap = cap_runs if cap_runs is not None else max(n, 1)
+    lo = np.zeros((max(n, 1), 2), np.uint32)
+    xr, yr = np.zeros((cap, 2), np.uint32), np.zeros((cap, 2), np.uint32)
+    nx, ny = C.c_int32(0), C.c_int32(0)
+    _check(L.mm2b_pack_anchors(_p(a), n, _p(lo), _p(xr), C.byref(nx), _p(yr), C.byref(ny), cap), "mm2b_pack_anchors")
+    return lo[:n], xr[:nx.value], yr[:ny.value]
 
 
 def chain_read(par, a):
@@ -209,7 +261,7 @@ class DeviceBatch:
     run() enqueues K0..K3 on the current torch stream through mm2b_chain_batch_device and returns immediately.
     """
 
-    def __init__(self, par, off, a, device=0, keep_fpv=False):
+    def __init__(self, par, off, a, device=0, keep_fpv=False, index_out=False):
         import torch
         self.torch = torch
         self.L = load()
@@ -229,7 +281,11 @@ class DeviceBatch:
             self.d_u_off = torch.empty(self.n_reads + 1, **i64)
             self.d_b_off = torch.empty(self.n_reads + 1, **i64)
             self.d_u = torch.empty(max(self.n_anchors, 1), **i64)
-            self.d_b = torch.empty((max(self.n_anchors, 1), 2), **i64)
+            self.index_out = index_out
+            if index_out:       # chained anchors as int32 indices inside their read (mm2b_chain_batch_device_idx)
+                self.d_bi = torch.empty(max(self.n_anchors, 1), **i32)
+            else:
+                self.d_b = torch.empty((max(self.n_anchors, 1), 2), **i64)
         if keep_fpv:
             os.environ["MM2B_KEEP_FPV"] = "1"
         self.ws = self.L.mm2b_ws_create(device, self.n_anchors, self.n_reads)
@@ -242,10 +298,11 @@ class DeviceBatch:
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     def run(self):
-        rc = self.L.mm2b_chain_batch_device(self.ws, C.byref(self.par), self.n_reads, self.n_anchors,
-                                            self.d_off.data_ptr(), self.d_a.data_ptr(), self.d_n_u.data_ptr(), self.d_n_v.data_ptr(),
-                                            self.d_status.data_ptr(), self.d_u_off.data_ptr(), self.d_b_off.data_ptr(),
-                                            self.d_u.data_ptr(), self.d_b.data_ptr(), self._stream())
+        fn = self.L.mm2b_chain_batch_device_idx if self.index_out else self.L.mm2b_chain_batch_device
+        rc = fn(self.ws, C.byref(self.par), self.n_reads, self.n_anchors,
+                self.d_off.data_ptr(), self.d_a.data_ptr(), self.d_n_u.data_ptr(), self.d_n_v.data_ptr(),
+                self.d_status.data_ptr(), self.d_u_off.data_ptr(), self.d_b_off.data_ptr(),
+                self.d_u.data_ptr(), self.d_bi.data_ptr() if self.index_out else self.d_b.data_ptr(), self._stream())
         _check(rc, "mm2b_chain_batch_device")
 
     def stats(self):
@@ -271,8 +328,27 @@ class DeviceBatch:
         n_v = self.d_n_v[:self.n_reads].cpu().numpy()
         u_off, b_off = self.d_u_off.cpu().numpy(), self.d_b_off.cpu().numpy()
         u = self.d_u[:int(u_off[-1])].cpu().numpy().view(np.uint64)
-        b = self.d_b[:int(b_off[-1])].cpu().numpy().reshape(-1).view(ANCHOR)
-        return dict(n_u=n_u, n_v=n_v, status=self.d_status[:self.n_reads].cpu().numpy(), u_off=u_off, b_off=b_off, u=u, b=b)
+        out = dict(n_u=n_u, n_v=n_v, status=self.d_status[:self.n_reads].cpu().numpy(), u_off=u_off, b_off=b_off, u=u)
+        if self.index_out:
+            out["bi"] = self.d_bi[:int(b_off[-1])].cpu().numpy()
+        else:
+            out["b"] = self.d_b[:int(b_off[-1])].cpu().numpy().reshape(-1).view(ANCHOR)
+        return out
+
+    def unpack_into_place(self, a):
+        """Test hook for the packed transfer format: pack `a` on the host (mm2b_pack_anchors), copy the packed form to the device
+        and let mm2b_unpack_anchors_device overwrite this batch's anchors with the restored mm128_t."""
+        torch = self.torch
+        lo, xr, yr = pack_anchors(a)
+        with torch.cuda.device(self.device):
+            d_lo = torch.from_numpy(lo.copy().view(np.int32)).to(self.device)
+            d_xr = torch.from_numpy(xr.copy().view(np.int32)).to(self.device)
+            d_yr = torch.from_numpy(yr.copy().view(np.int32)).to(self.device)
+            self.d_a.zero_()
+            _check(self.L.mm2b_unpack_anchors_device(self.device.index, len(a), d_lo.data_ptr(), d_xr.data_ptr(), len(xr), d_yr.data_ptr(), len(yr),
+                                                     self.d_a.data_ptr(), self._stream()), "mm2b_unpack_anchors_device")
+            torch.cuda.synchronize(self.device)
+        return self.d_a.cpu().numpy().reshape(-1).view(ANCHOR)[:len(a)]
 
     def close(self):
         if self.ws:

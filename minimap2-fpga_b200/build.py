@@ -22,8 +22,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 INC = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]
 
 CU_SRCS = ["csrc/chain_kernels.cu", "csrc/chain_api.cu"]
-CXX_SRCS = ["host/chain_backend.cpp", "host/fiber_for.cpp"]
-HEADERS = ["csrc/chain_kernels.cuh", "csrc/shim_internal.h", "host/fiber_for.h", "../include/mm2chain_b200.h"]
+CXX_SRCS = ["host/chain_backend.cpp"]
+HEADERS = ["csrc/chain_kernels.cuh", "csrc/shim_internal.h", "../include/mm2chain_b200.h"]
 
 
 def _newer(target, deps):

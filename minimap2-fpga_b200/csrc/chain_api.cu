@@ -38,9 +38,8 @@ struct mm2b_workspace {
 	int heavy_on;               // MM2B_HEAVY (default 1)
 	long long heavy_min_cells;  // MM2B_HEAVY_MIN_CELLS: estimated window cells from which a read counts as heavy
 	int64_t longest_hint;       // mm2b_ws_set_longest_read: longest read of the next batch, or -1
-	int64_t *tile;              // 2 * ceil(max_reads / 2048)
 	int *small;                 // [0] work counter, [2] heavy-read count, [3] heavy-read cursor, [64..320) length buckets
-	unsigned long long *counters;
+	unsigned long long *counters;   // [0..5) statistics, [6..8) output cursors
 	int32_t *dbg_fpv;           // 3 * max_anchors when MM2B_KEEP_FPV=1
 	size_t bytes;
 	cudaEvent_t ev_k1[2];       // around the chaining kernel of the last batch
@@ -84,16 +83,14 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	cudaDeviceGetAttribute(&ws->n_sms, cudaDevAttrMultiProcessorCount, device);
 	const size_t sz_scratch = (size_t)max_anchors * SCRATCH_BYTES_PER_ANCHOR;
 	const size_t sz_order = (size_t)max_reads * sizeof(int32_t);
-	const size_t sz_tile = ((size_t)max_reads / 2048 + 2) * 2 * sizeof(int64_t);
 	const char *keep = getenv("MM2B_KEEP_FPV");
 	bool ok = cuda_ok(cudaMalloc(&ws->scratch, sz_scratch), "cudaMalloc(scratch)")
 	       && cuda_ok(cudaMalloc(&ws->order, sz_order), "cudaMalloc(order)")
 	       && cuda_ok(cudaMalloc(&ws->heavy_list, sz_order), "cudaMalloc(heavy_list)")
 	       && cuda_ok(cudaMalloc(&ws->heavy_flag, (size_t)max_reads), "cudaMalloc(heavy_flag)")
-	       && cuda_ok(cudaMalloc(&ws->tile, sz_tile), "cudaMalloc(tile)")
 	       && cuda_ok(cudaMalloc(&ws->small, 512 * sizeof(int)), "cudaMalloc(small)")
 	       && cuda_ok(cudaMalloc(&ws->counters, 8 * sizeof(unsigned long long)), "cudaMalloc(counters)");
-	ws->bytes = sz_scratch + 2 * sz_order + (size_t)max_reads + sz_tile + 512 * sizeof(int) + 32;
+	ws->bytes = sz_scratch + 2 * sz_order + (size_t)max_reads + 512 * sizeof(int) + 64;
 	if (ok && keep && atoi(keep) > 0) {
 		ok = cuda_ok(cudaMalloc(&ws->dbg_fpv, (size_t)max_anchors * 12), "cudaMalloc(dbg_fpv)");
 		ws->bytes += (size_t)max_anchors * 12;
@@ -110,7 +107,7 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 	cudaSetDevice(ws->device);
 	if (ws->ev_k1[0]) cudaEventDestroy(ws->ev_k1[0]);
 	if (ws->ev_k1[1]) cudaEventDestroy(ws->ev_k1[1]);
-	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->heavy_list), cudaFree(ws->heavy_flag), cudaFree(ws->tile), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
+	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->heavy_list), cudaFree(ws->heavy_flag), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
 	free(ws);
 }
 
@@ -119,12 +116,12 @@ void mm2b_ws_set_counting(mm2b_workspace_t *ws, int on) { if (ws) ws->count_cell
 void mm2b_ws_set_longest_read(mm2b_workspace_t *ws, int64_t n_anchors) { if (ws) ws->longest_hint = n_anchors; }
 const unsigned long long *mm2b_ws_counters_dev(const mm2b_workspace_t *ws) { return ws ? ws->counters : 0; }
 
-int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
-                            const int64_t *d_off, const mm2b_anchor_t *d_a,
-                            int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
-                            uint64_t *d_u, mm2b_anchor_t *d_b, void *stream_)
+static int chain_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
+                        const int64_t *d_off, const mm2b_anchor_t *d_a,
+                        int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
+                        uint64_t *d_u, mm2b_anchor_t *d_b, int32_t *d_bi, void *stream_)
 {
-	if (!ws || !par || n_reads < 0 || n_anchors < 0) { set_error("%s%s", "mm2b_chain_batch_device: bad argument", ""); return MM2B_ERR_ARG; }
+	if (!ws || !par || n_reads < 0 || n_anchors < 0 || (!d_b && !d_bi)) { set_error("%s%s", "mm2b_chain_batch_device: bad argument", ""); return MM2B_ERR_ARG; }
 	if (n_reads > ws->max_reads || n_anchors > ws->max_anchors || n_reads >= (1ll << 31)) {
 		set_error("%s%s", "mm2b_chain_batch_device: batch exceeds workspace capacity", "");
 		return MM2B_ERR_CAPACITY;
@@ -139,6 +136,7 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	memset(&ba, 0, sizeof(ba));
 	ba.par = *par, ba.n_reads = n_reads, ba.off = d_off, ba.a = d_a, ba.scratch = ws->scratch;
 	ba.n_u = d_n_u, ba.n_v = d_n_v, ba.status = d_status, ba.order = ws->order, ba.work_counter = ws->small;
+	ba.out_cursor = ws->counters + 6, ba.u_off = d_u_off, ba.b_off = d_b_off, ba.u = d_u, ba.b = d_bi ? nullptr : d_b, ba.bi = d_bi;
 	ba.counters = ws->counters, ba.dbg_fpv = ws->dbg_fpv, ba.n_anchors = ws->max_anchors, ba.count_cells = ws->count_cells;
 	// Reads with long windows (tandem repeats) go to the heavy-read kernel when the batch's arguments allow its scoring path
 	// (same-segment genomic cost) and its ring holds a whole window; the cell tally is a warp-per-read feature.
@@ -153,16 +151,47 @@ int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int6
 	cudaEventRecord(ws->ev_k1[0], stream);
 	launches += launch_chain(ba, ws->n_sms, stream);
 	cudaEventRecord(ws->ev_k1[1], stream);
-	launches += launch_offsets(n_reads, d_n_u, d_n_v, d_u_off, d_b_off, ws->tile, stream);
-	EmitArgs ea;
-	ea.n_reads = n_reads, ea.off = d_off, ea.a = d_a, ea.scratch = ws->scratch, ea.n_u = d_n_u, ea.n_v = d_n_v;
-	ea.u_off = d_u_off, ea.b_off = d_b_off, ea.u = d_u, ea.b = d_b;
-	launches += launch_emit(ea, ws->n_sms, stream);
+	// totals: the cursors' final values close the offset arrays (entry n_reads), as the prefix sums of the old layout did
+	cudaMemcpyAsync(d_u_off + n_reads, ba.out_cursor, 8, cudaMemcpyDeviceToDevice, stream);
+	cudaMemcpyAsync(d_b_off + n_reads, ba.out_cursor + 1, 8, cudaMemcpyDeviceToDevice, stream);
 	count_launches(launches);
 	ws->last_reads = n_reads, ws->last_anchors = n_anchors;
 	ws->last_n_u = d_n_u, ws->last_n_v = d_n_v, ws->last_u_off = d_u_off, ws->last_b_off = d_b_off;
 	const bool ok = cuda_ok(cudaGetLastError(), "kernel launch");
 	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
+	return ok ? MM2B_OK : MM2B_ERR_CUDA;
+}
+
+int mm2b_chain_batch_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
+                            const int64_t *d_off, const mm2b_anchor_t *d_a,
+                            int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
+                            uint64_t *d_u, mm2b_anchor_t *d_b, void *stream)
+{
+	return chain_device(ws, par, n_reads, n_anchors, d_off, d_a, d_n_u, d_n_v, d_status, d_u_off, d_b_off, d_u, d_b, nullptr, stream);
+}
+
+int mm2b_chain_batch_device_idx(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t n_reads, int64_t n_anchors,
+                                const int64_t *d_off, const mm2b_anchor_t *d_a,
+                                int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
+                                uint64_t *d_u, int32_t *d_bi, void *stream)
+{
+	return chain_device(ws, par, n_reads, n_anchors, d_off, d_a, d_n_u, d_n_v, d_status, d_u_off, d_b_off, d_u, nullptr, d_bi, stream);
+}
+
+int mm2b_unpack_anchors_device(int device, int64_t n_anchors, const void *d_lo, const void *d_xruns, int32_t n_xruns, const void *d_yruns, int32_t n_yruns,
+                               mm2b_anchor_t *d_a, void *stream)
+{
+	if (n_anchors < 0 || n_anchors >= (1ll << 31) || (n_anchors > 0 && (!d_lo || !d_xruns || !d_yruns || !d_a || n_xruns < 1 || n_yruns < 1))) {
+		set_error("%s%s", "mm2b_unpack_anchors_device: bad argument", "");
+		return MM2B_ERR_ARG;
+	}
+	int prev = -1, n_sms = 148;
+	cudaGetDevice(&prev);
+	if (prev != device && !cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return MM2B_ERR_CUDA;
+	cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
+	count_launches(launch_unpack(n_anchors, (const uint2*)d_lo, (const uint2*)d_xruns, n_xruns, (const uint2*)d_yruns, n_yruns, d_a, n_sms, (cudaStream_t)stream));
+	const bool ok = cuda_ok(cudaGetLastError(), "kernel launch");
+	if (prev >= 0 && prev != device) cudaSetDevice(prev);
 	return ok ? MM2B_OK : MM2B_ERR_CUDA;
 }
 

@@ -15,8 +15,8 @@
 //     (Lindley) evaluation of the n_skip counter on the two vote masks;
 //   * chain ends / peaks, the descending sort, the priority backtrack (32 anchors per step by pointer jumping inside
 //     aligned blocks of p[]) and the final order by reference position (including the reference's unstable radix-sort
-//     tie order) run in the same warp right after the fill while f/p/v are still in L1/L2; a scan + gather kernel
-//     pair then packs u[]/b[] in read order.
+//     tie order) run in the same warp right after the fill while f/p/v are still in L1/L2; the warp then reserves its share
+//     of the packed output from two atomic cursors and writes u[] and b[] (or the 4-byte indices of b[]'s anchors) itself.
 //   * the few reads with very long windows (tandem repeats) get a CTA of 16 warps and a ring that holds a whole window;
 //     their long scans are shared by the warps (chain_heavy_kernel, "Heavy reads" below).
 // No tensor cores (nothing here is a contraction) and no collective (reads are independent).
@@ -61,7 +61,7 @@ struct W16 { uint64_t x, y; };          // (first-anchor x, start-in-PATH << 32 
 struct ReadCtx {
 	const ulonglong2 *A;
 	int32_t *F, *P, *V, *T;
-	uint64_t *X, *U, *UF;
+	uint64_t *X, *U;
 	int n;
 };
 
@@ -776,7 +776,18 @@ __device__ void flag_sort_by_x_lane0(W16 *w, int n, int *sm /* >= 768 ints */, i
 // ---------------------------------------------------------------------------------------------------------------
 // Everything after the fill for one read: chain.c:348-422
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int32_t *smem, int lane, int &n_u_out, int &n_v_out, int &status)
+// Output (chain.c:412-420's copies, done once): the read's warp reserves its share of the packed output arrays from two atomic
+// cursors (uo / bo are returned as the read's offsets) and writes u[] and either the chained anchors themselves (b, 16 B each)
+// or their indices inside the read (bi, 4 B each: the caller still holds a[]).  The layout is packed but not in read order.
+struct OutArgs {
+	unsigned long long *cursor;     // [0] entries of u handed out, [1] entries of b / bi handed out
+	uint64_t *u;
+	ulonglong2 *b;                  // or nullptr
+	int32_t *bi;                    // or nullptr
+};
+
+__device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, const OutArgs &out, int32_t *smem, int lane, int &n_u_out, int &n_v_out, int &status,
+                               unsigned long long &uo_out, unsigned long long &bo_out)
 {
 	const int n = rc.n;
 	const int32_t *F = rc.F;
@@ -930,25 +941,36 @@ __device__ void extract_chains(const mm2b_params_t &par, const ReadCtx &rc, int3
 			if (lane < n_u) W[r0] = w0;
 			if (lane + 32 < n_u) W[r1] = w1;
 		} else if (lane == 0) {
-			// worklist of pending (begin, count, shift) ranges lives behind the W array (F+P+X give 16 B per ANCHOR, W uses 16 B per CHAIN)
-			int3 *work = (int3*)(rc.UF);      // UF (8 B per anchor) is not written until the sort is done
-			const int cap = (int)((int64_t)n * 8 / (int64_t)sizeof(int3));
+			// worklist of pending (begin, count, shift) ranges: T is dead once the chain ends have been read off it
+			int3 *work = (int3*)(rc.T);
+			const int cap = (int)((int64_t)n * 4 / (int64_t)sizeof(int3));
 			flag_sort_by_x_lane0(W, n_u, smem, work, cap);
 		}
 		__syncwarp();
 	}
 
-	// chain.c:412-420 restated as index lists: final u[] and, per output slot, the index of the anchor that goes there
-	int32_t *OUTIDX = T;
+	// chain.c:412-420: final u[] and b[] (or the indices of b[]'s anchors), written straight into the packed output
+	unsigned long long uo = 0, bo = 0;
+	if (lane == 0) uo = atomicAdd(&out.cursor[0], (unsigned long long)n_u), bo = atomicAdd(&out.cursor[1], (unsigned long long)n_v);
+	__syncwarp();
+	uo = __shfl_sync(FULL, uo, 0), bo = __shfl_sync(FULL, bo, 0);
+	uo_out = uo, bo_out = bo;
+	uint64_t *u_dst = out.u + uo;
 	int pos = 0;
 	for (int i = 0; i < n_u; ++i) {
 		const W16 w = W[i];
 		const int src = (int32_t)w.y, k0 = (int32_t)(w.y >> 32);
 		const uint64_t uu = U[src];
 		const int len = (int32_t)uu;
-		if (lane == 0) rc.UF[i] = uu;
+		if (lane == 0) u_dst[i] = uu;
 		MM2B_CHK(src >= 0 && src < n_u && k0 >= 0 && len >= 1 && k0 + len <= n_v && pos + len <= n_v, 0x80);
-		for (int j = lane; j < len; j += 32) OUTIDX[pos + j] = PATH[k0 + (len - 1 - j)];
+		if (out.bi) {
+			int32_t *dst = out.bi + bo + pos;
+			for (int j = lane; j < len; j += 32) dst[j] = PATH[k0 + (len - 1 - j)];
+		} else {
+			ulonglong2 *dst = out.b + bo + pos;
+			for (int j = lane; j < len; j += 32) dst[j] = __ldg(rc.A + PATH[k0 + (len - 1 - j)]);
+		}
 		__syncwarp();
 		pos += len;
 	}
@@ -972,7 +994,7 @@ __device__ __forceinline__ void chain_one_read(const BatchArgs &args, int64_t r,
 	const int64_t o = args.off[r];
 	const int64_t n64 = args.off[r + 1] - o;
 	if (n64 <= 0) {                                                               // chain.c:38-41
-		if (lane == 0) args.n_u[r] = 0, args.n_v[r] = 0, args.status[r] = MM2B_READ_EMPTY;
+		if (lane == 0) args.n_u[r] = 0, args.n_v[r] = 0, args.status[r] = MM2B_READ_EMPTY, args.u_off[r] = 0, args.b_off[r] = 0;
 		__syncwarp();
 		return;
 	}
@@ -982,7 +1004,7 @@ __device__ __forceinline__ void chain_one_read(const BatchArgs &args, int64_t r,
 	uint8_t *s = args.scratch + (size_t)o * SCRATCH_BYTES_PER_ANCHOR;
 	const size_t n = (size_t)n64;
 	rc.F = (int32_t*)s, rc.P = (int32_t*)(s + 4 * n), rc.X = (uint64_t*)(s + 8 * n);
-	rc.V = (int32_t*)(s + 16 * n), rc.T = (int32_t*)(s + 20 * n), rc.U = (uint64_t*)(s + 24 * n), rc.UF = (uint64_t*)(s + 32 * n);
+	rc.V = (int32_t*)(s + 16 * n), rc.T = (int32_t*)(s + 20 * n), rc.U = (uint64_t*)(s + 24 * n);
 
 	// chain.c:46-49: zero t[], sum the 8-bit q_span fields; also find out whether every anchor carries the same segment id
 	uint64_t sum = 0;
@@ -1021,8 +1043,11 @@ __device__ __forceinline__ void chain_one_read(const BatchArgs &args, int64_t r,
 		__syncwarp();
 	}
 	int n_u = 0, n_v = 0, status = MM2B_READ_OK;
-	extract_chains(args.par, rc, ring, lane, n_u, n_v, status);
-	if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status;
+	unsigned long long uo = 0, bo = 0;
+	OutArgs out;
+	out.cursor = args.out_cursor, out.u = args.u, out.b = (ulonglong2*)args.b, out.bi = args.bi;
+	extract_chains(args.par, rc, out, ring, lane, n_u, n_v, status, uo, bo);
+	if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status, args.u_off[r] = (int64_t)uo, args.b_off[r] = (int64_t)bo;
 	__syncwarp();
 }
 
@@ -1196,99 +1221,50 @@ __global__ void order_scatter_kernel(int64_t n_reads, const int64_t *off, int *c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2: exclusive prefix sums of n_u / n_v over reads -> u_off / b_off (n_reads+1 entries).  Three small launches.
+// K-unpack: anchors arrive over PCIe as 8 bytes (low words of x and y) plus run-length lists of the high words — in the sorted
+// input the strand/rid word of x changes a few times per read and the flags/q_span/segment word of y hardly ever (it is the
+// k-mer length unless the index is homopolymer-compressed).  This kernel restores the 16-byte mm128_t in HBM (24 B of HBM
+// traffic per anchor, ~0.3 % of the chaining kernel's time) so that everything downstream sees the reference's layout.
+// runs: {first anchor of the run, high word}, sorted by first anchor, run 0 starts at anchor 0.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SCAN_TILE = 2048, SCAN_THREADS = 256, SCAN_PER_THREAD = SCAN_TILE / SCAN_THREADS;
-
-__device__ __forceinline__ void block_scan_pair(int64_t &a, int64_t &b, int64_t *sh /* 2*8 */)   // inclusive -> returns exclusive in a,b; totals in sh[16],sh[17]
+__device__ __forceinline__ int last_run_at_or_before(const uint2 *runs, int lo, int hi, uint32_t i)   // largest r in [lo, hi] with runs[r].x <= i
 {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int64_t ia = a, ib = b;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const int64_t oa = __shfl_up_sync(FULL, ia, d), ob = __shfl_up_sync(FULL, ib, d);
-		if (lane >= d) ia += oa, ib += ob;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (__ldg(&runs[mid].x) <= i) lo = mid;
+		else hi = mid - 1;
 	}
-	if (lane == 31) sh[warp] = ia, sh[8 + warp] = ib;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		int64_t ra = 0, rb = 0;
-		for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-			const int64_t ta = sh[w], tb = sh[8 + w];
-			sh[w] = ra, sh[8 + w] = rb;
-			ra += ta, rb += tb;
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(int64_t n, const uint2 *lo, const uint2 *xruns, int n_xruns, const uint2 *yruns, int n_yruns, ulonglong2 *a)
+{
+	__shared__ int range[4];
+	for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
+		const uint32_t first = (uint32_t)base, last = (uint32_t)(base + 255 < n - 1 ? base + 255 : n - 1);
+		if (threadIdx.x < 4) {          // the runs this block of 256 anchors can touch
+			const uint2 *runs = threadIdx.x < 2 ? xruns : yruns;
+			const int nr = threadIdx.x < 2 ? n_xruns : n_yruns;
+			range[threadIdx.x] = last_run_at_or_before(runs, 0, nr - 1, (threadIdx.x & 1) ? last : first);
 		}
-		sh[16] = ra, sh[17] = rb;
-	}
-	__syncthreads();
-	a = ia - a + sh[warp], b = ib - b + sh[8 + warp];
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) offsets_tile_sums_kernel(int64_t n, const int32_t *n_u, const int32_t *n_v, int64_t *tile)
-{
-	__shared__ int64_t sh[18];
-	const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
-	int64_t a = 0, b = 0;
-	for (int q = 0; q < SCAN_PER_THREAD; ++q) if (base + q < n) a += n_u[base + q], b += n_v[base + q];
-	block_scan_pair(a, b, sh);
-	if (threadIdx.x == 0) tile[2 * blockIdx.x] = sh[16], tile[2 * blockIdx.x + 1] = sh[17];
-}
-__global__ void offsets_scan_tiles_kernel(int n_tiles, int64_t *tile)     // single thread block, serial over tiles in strides
-{
-	__shared__ int64_t sh[18];
-	int64_t ca = 0, cb = 0;
-	for (int base = 0; base < n_tiles; base += SCAN_THREADS) {
-		const int t = base + threadIdx.x;
-		int64_t a = t < n_tiles ? tile[2 * t] : 0, b = t < n_tiles ? tile[2 * t + 1] : 0;
-		block_scan_pair(a, b, sh);
-		if (t < n_tiles) tile[2 * t] = a + ca, tile[2 * t + 1] = b + cb;
-		ca += sh[16], cb += sh[17];
+		__syncthreads();
+		const int64_t i = base + threadIdx.x;
+		if (i < n) {
+			const uint2 w = __ldg(lo + i);
+			const uint32_t xh = __ldg(&xruns[last_run_at_or_before(xruns, range[0], range[1], (uint32_t)i)].y);
+			const uint32_t yh = __ldg(&yruns[last_run_at_or_before(yruns, range[2], range[3], (uint32_t)i)].y);
+			a[i] = make_ulonglong2((uint64_t)xh << 32 | w.x, (uint64_t)yh << 32 | w.y);
+		}
 		__syncthreads();
 	}
 }
-__global__ void __launch_bounds__(SCAN_THREADS) offsets_write_kernel(int64_t n, const int32_t *n_u, const int32_t *n_v, const int64_t *tile, int64_t *u_off, int64_t *b_off)
-{
-	__shared__ int64_t sh[18];
-	const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
-	int64_t va[SCAN_PER_THREAD], vb[SCAN_PER_THREAD], a = 0, b = 0;
-	for (int q = 0; q < SCAN_PER_THREAD; ++q) {
-		va[q] = base + q < n ? n_u[base + q] : 0, vb[q] = base + q < n ? n_v[base + q] : 0;
-		a += va[q], b += vb[q];
-	}
-	block_scan_pair(a, b, sh);
-	a += tile[2 * blockIdx.x], b += tile[2 * blockIdx.x + 1];
-	for (int q = 0; q < SCAN_PER_THREAD; ++q) {
-		if (base + q < n) u_off[base + q] = a, b_off[base + q] = b;
-		a += va[q], b += vb[q];
-		if (base + q == n - 1) u_off[n] = a, b_off[n] = b;
-	}
-}
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: pack u[] and b[] in read order (one warp per read, grid-stride) — chain.c:412-420's copies, done once
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) emit_kernel(const EmitArgs args)
-{
-	const int lane = threadIdx.x & 31;
-	const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-	for (int64_t r = warp0; r < args.n_reads; r += n_warps) {
-		const int n_u = args.n_u[r], n_v = args.n_v[r];
-		if (n_u == 0) continue;
-		const int64_t o = args.off[r];
-		const size_t n = (size_t)(args.off[r + 1] - o);
-		const uint8_t *s = args.scratch + (size_t)o * SCRATCH_BYTES_PER_ANCHOR;
-		const int32_t *outidx = (const int32_t*)(s + 20 * n);
-		const uint64_t *uf = (const uint64_t*)(s + 32 * n);
-		const ulonglong2 *A = (const ulonglong2*)(args.a + o);
-		uint64_t *u = args.u + args.u_off[r];
-		ulonglong2 *b = (ulonglong2*)(args.b + args.b_off[r]);
-		for (int k = lane; k < n_u; k += 32) u[k] = uf[k];
-		for (int k = lane; k < n_v; k += 32) b[k] = __ldg(A + outidx[k]);
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// INT32 issue-rate micro-benchmark (roofline denominator): independent IADD3 / LOP3 / IMNMX chains, all SMs
+// INT32 issue-rate micro-benchmark (roofline denominator): eight independent integer chains per thread, all SMs.  Each source
+// statement `a = max(a + k, b ^ i)` compiles to TWO SASS instructions on sm_100a — LOP3.LUT (the xor) and VIADDMNMX (add and
+// max fused) — so the benchmark counts 2 lane-instructions per statement (SASS excerpt: profiles/int32_peak_sass.txt).  The
+// three source-level operations (add, xor, max) per statement are what SURVEY.md 8d's "30 ops per cell" counts, hence the
+// op-counted peak is 1.5 x the instruction peak; bench.py reports both and says which one each fraction uses.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) int32_peak_kernel(int iters, int *out)
 {
@@ -1326,6 +1302,7 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 	if (args.n_reads <= 0) return 0;
 	cudaMemsetAsync(args.work_counter, 0, sizeof(int), stream);
 	cudaMemsetAsync(args.counters, 0, 5 * sizeof(unsigned long long), stream);
+	cudaMemsetAsync(args.out_cursor, 0, 2 * sizeof(unsigned long long), stream);
 	int64_t ctas = (args.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const int64_t resident = (int64_t)n_sms * CTAS_PER_SM;
 	if (ctas > resident) ctas = resident;
@@ -1352,28 +1329,14 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 int heavy_ring_slots() { return HEAVY_RING; }
 int heavy_min_window() { return COOP_MIN_CELLS; }
 
-int launch_offsets(int64_t n_reads, const int32_t *n_u, const int32_t *n_v, int64_t *u_off, int64_t *b_off,
-                   int64_t *tile_scratch, cudaStream_t stream)
+int launch_unpack(int64_t n_anchors, const uint2 *lo, const uint2 *xruns, int n_xruns, const uint2 *yruns, int n_yruns, mm2b_anchor_t *a,
+                  int n_sms, cudaStream_t stream)
 {
-	if (n_reads <= 0) {
-		cudaMemsetAsync(u_off, 0, sizeof(int64_t), stream);
-		cudaMemsetAsync(b_off, 0, sizeof(int64_t), stream);
-		return 0;
-	}
-	const int n_tiles = (int)((n_reads + SCAN_TILE - 1) / SCAN_TILE);
-	offsets_tile_sums_kernel<<<n_tiles, SCAN_THREADS, 0, stream>>>(n_reads, n_u, n_v, tile_scratch);
-	offsets_scan_tiles_kernel<<<1, SCAN_THREADS, 0, stream>>>(n_tiles, tile_scratch);
-	offsets_write_kernel<<<n_tiles, SCAN_THREADS, 0, stream>>>(n_reads, n_u, n_v, tile_scratch, u_off, b_off);
-	return 3;
-}
-
-int launch_emit(const EmitArgs &args, int n_sms, cudaStream_t stream)
-{
-	if (args.n_reads <= 0) return 0;
-	int64_t blocks = (args.n_reads + 7) / 8;
+	if (n_anchors <= 0) return 0;
+	int64_t blocks = (n_anchors + 255) / 256;
 	const int64_t cap = (int64_t)n_sms * 8;
 	if (blocks > cap) blocks = cap;
-	emit_kernel<<<(int)blocks, 256, 0, stream>>>(args);
+	unpack_kernel<<<(int)blocks, 256, 0, stream>>>(n_anchors, lo, xruns, n_xruns, yruns, n_yruns, (ulonglong2*)a);
 	return 1;
 }
 
@@ -1409,8 +1372,8 @@ double measure_int32_peak(int device)
 		cudaEventSynchronize(e1);
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);
-		// per inner statement: one add, one xor, one min/max = 3 integer ops per lane
-		const double ops = (double)grid * 256.0 * iters * 8.0 * 8.0 * 3.0;
+		// per inner statement: LOP3 + VIADDMNMX = 2 lane-instructions (see the comment at int32_peak_kernel)
+		const double ops = (double)grid * 256.0 * iters * 8.0 * 8.0 * 2.0;
 		const double rate = ops / (ms * 1e-3) / 1e9;
 		if (rate > best) best = rate;
 	}

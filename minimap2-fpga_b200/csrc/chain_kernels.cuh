@@ -8,11 +8,11 @@ namespace mm2b {
 
 // Per-read scratch layout in HBM.  Read r with n anchors starting at global anchor offset o owns the
 // SCRATCH_BYTES_PER_ANCHOR*n bytes at scratch + SCRATCH_BYTES_PER_ANCHOR*o, carved as
-//   [F 4n][P 4n][X 8n][V 4n][T 4n][U 8n][UF 8n]
+//   [F 4n][P 4n][X 8n][V 4n][T 4n][U 8n]
 //   F,P,V  DP state (chain.c:236-237);  T visit stamps / marks;  U chain-end keys, then kept chains
 //   X      second buffer of the radix sort of U;  W (16 B per chain, final order sort) aliases F+P+X once the backtrack is done
-//   V -> PATH (backtrack index list), T -> OUTIDX (anchor indices in output order), UF final u[]
-constexpr int SCRATCH_BYTES_PER_ANCHOR = 40;
+//   V -> PATH (backtrack index list);  T -> worklist of the final sort when a read has more than 64 chains
+constexpr int SCRATCH_BYTES_PER_ANCHOR = 32;
 
 struct BatchArgs {
 	mm2b_params_t par;
@@ -21,6 +21,13 @@ struct BatchArgs {
 	const mm2b_anchor_t *a;
 	uint8_t *scratch;
 	int32_t *n_u, *n_v, *status;
+	// packed output, filled by each read's own warp (no separate scan / gather pass): the warp reserves its share from the two
+	// cursors and records where it wrote in u_off[r] / b_off[r]
+	unsigned long long *out_cursor; // [0] entries of u handed out, [1] entries of b / bi handed out
+	int64_t *u_off, *b_off;
+	uint64_t *u;
+	mm2b_anchor_t *b;               // chained anchors (16 B each), or nullptr when ...
+	int32_t *bi;                    // ... their indices inside the read (4 B each) are wanted instead
 	const int32_t *order;           // processing order (longest reads first) or nullptr
 	int *work_counter;              // persistent-warp work queue
 	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells, [3] window cells, [4] reads taken by the heavy-read kernel
@@ -35,23 +42,12 @@ struct BatchArgs {
 	int heavy_cap;                  // at most this many reads per batch (one wave of CTAs): the kernel buys latency, not throughput
 };
 
-struct EmitArgs {
-	int64_t n_reads;
-	const int64_t *off;
-	const mm2b_anchor_t *a;
-	const uint8_t *scratch;
-	const int32_t *n_u, *n_v;
-	const int64_t *u_off, *b_off;
-	uint64_t *u;
-	mm2b_anchor_t *b;
-};
-
 // launchers (all asynchronous on `stream`); each returns the number of kernels it launched
 int launch_order(int64_t n_reads, const int64_t *off, int32_t *order, int *bucket_scratch, cudaStream_t stream);
 int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream);
-int launch_offsets(int64_t n_reads, const int32_t *n_u, const int32_t *n_v, int64_t *u_off, int64_t *b_off,
-                   int64_t *tile_scratch, cudaStream_t stream);
-int launch_emit(const EmitArgs &args, int n_sms, cudaStream_t stream);
+// anchors packed to 8 B by the host (low words + runs of equal high words, see host/chain_backend.cpp) -> mm128_t in HBM
+int launch_unpack(int64_t n_anchors, const uint2 *lo, const uint2 *xruns, int n_xruns, const uint2 *yruns, int n_yruns, mm2b_anchor_t *a,
+                  int n_sms, cudaStream_t stream);
 double measure_int32_peak(int device);
 int heavy_ring_slots();          // ring capacity of the heavy-read kernel: it needs max_iter + 64 <= this
 int heavy_min_window();          // ... and only pays off for windows longer than this

@@ -9,13 +9,23 @@
 //
 // Reads are independent, so a batch is cut into sub-batches (contiguous read ranges of <= MM2B_SUB_ANCHORS anchors) that the
 // per-device worker threads pull from a shared counter; each worker keeps NSLOT sub-batches in flight on separate streams so
-// H2D copies, kernels and D2H copies of neighbouring sub-batches overlap.  No collective, no NCCL: nothing is exchanged
-// between devices.  Outputs land in the caller's arrays in input order.
+// host packing, H2D copies, kernels, D2H copies and host gathering of neighbouring sub-batches overlap.  Several calls may be
+// in flight at once: a worker serves all of them.  No collective, no NCCL: nothing is exchanged between devices.
+//
+// PCIe is what bounds this path (16 B per anchor in, 16 B per chained anchor out in the reference's layout), so both
+// directions are slimmed down:
+//   in   helper threads pack each sub-batch, on its way into the pinned staging buffer, to 8 B per anchor ({x_lo, y_lo}) plus
+//        run-length lists of the high words; a tiny kernel restores mm128_t in HBM
+//   out  the kernel returns the INDEX of every chained anchor inside its read (4 B); the host, which still holds a[], gathers
+//        b[] from them (or hands the indices to the caller)
 #include <cuda_runtime_api.h>
+#include <vector_functions.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -26,7 +36,6 @@
 
 #include "mm2chain_b200.h"
 #include "../csrc/shim_internal.h"
-#include "fiber_for.h"
 
 // kalloc of the host application (kalloc.c); weak so that the library also loads stand-alone (tests, bench)
 extern "C" void *kmalloc(void *km, size_t size) __attribute__((weak));
@@ -42,6 +51,11 @@ constexpr int NSLOT = 6;
 template <class T> cudaError_t dmalloc(T **p, size_t bytes) { return cudaMalloc((void**)p, bytes ? bytes : 1); }
 template <class T> cudaError_t hmalloc(T **p, size_t bytes, unsigned flags) { return cudaHostAlloc((void**)p, bytes ? bytes : 1, flags); }
 
+double now_ms()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void *host_kmalloc(void *km, size_t size)
 {
 	if (kmalloc) return kmalloc(km, size);
@@ -55,26 +69,84 @@ void host_kfree(void *km, void *p)
 	free(p);
 }
 
+// ---- helper threads: packing on the way in, gathering on the way out ---------------------------------------------------
+// A plain task queue.  The tasks are memory-bound passes over one chunk of a sub-batch; the device workers never run them
+// themselves (they only drive the streams), so a slow host cannot stall the copy engines of sub-batches already issued.
+struct Pool {
+	std::vector<std::thread> th;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<std::function<void()>> q;
+	bool stop = false;
+	void start(int n)
+	{
+		stop = false;
+		for (int i = 0; i < n; ++i) th.emplace_back([this] { loop(); });
+	}
+	void loop()
+	{
+		for (;;) {
+			std::function<void()> fn;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return stop || !q.empty(); });
+				if (q.empty()) return;
+				fn = std::move(q.front());
+				q.pop_front();
+			}
+			fn();
+		}
+	}
+	void submit(std::function<void()> fn)
+	{
+		{ std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(fn)); }
+		cv.notify_one();
+	}
+	void shutdown()
+	{
+		{ std::lock_guard<std::mutex> lk(mu); stop = true; }
+		cv.notify_all();
+		for (auto &t : th) if (t.joinable()) t.join();
+		th.clear();
+		q.clear();
+	}
+};
+
+struct Device;
+
 // Device + pinned buffers for one sub-batch in flight
 struct Slot {
 	int device = -1;
+	Device *owner = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[6] = {};     // 0 start, 1 h2d done, 2 kernels done, 3 counts d2h done, 4 out d2h start, 5 out d2h done
 	mm2b_workspace_t *ws = nullptr;
-	int64_t cap_anchors = 0, cap_reads = 0;
+	int64_t cap_anchors = 0, cap_reads = 0, cap_runs = 0;
 	int64_t *d_off = nullptr, *d_u_off = nullptr, *d_b_off = nullptr;
-	mm2b_anchor_t *d_a = nullptr, *d_b = nullptr;
+	mm2b_anchor_t *d_a = nullptr, *d_b = nullptr;       // d_b only exists once a caller asked for device-side gathering
 	uint64_t *d_u = nullptr;
+	int32_t *d_bi = nullptr;
 	int32_t *d_n_u = nullptr, *d_n_v = nullptr, *d_status = nullptr;
+	uint2 *d_lo = nullptr, *d_xruns = nullptr, *d_yruns = nullptr;
 	int64_t *h_off = nullptr, *h_u_off = nullptr, *h_b_off = nullptr;   // pinned
 	unsigned long long *h_cnt = nullptr;                                // pinned copy of the workspace counters
+	uint2 *h_lo = nullptr, *h_xruns = nullptr, *h_yruns = nullptr;      // pinned: packed anchors of the sub-batch
+	int32_t *h_bi = nullptr;                                            // pinned: indices coming back when the host gathers b[]
 	// the sub-batch currently occupying the slot
+	struct Job *job = nullptr;
 	int sub = -1;
-	int stage = 0;              // 0 free, 1 kernels + counts in flight, 2 outputs in flight
+	int stage = 0;              // 0 free, 1 packing, 2 kernels + counts in flight, 3 outputs in flight, 4 gathering
+	std::atomic<int> sig{0};    // set by the stream callbacks: 1 = counts are on the host, 2 = outputs are on the host
+	std::atomic<int> host_left{0};      // helper tasks of the current stage still running
+	std::atomic<int> pack_overflow{0};  // some chunk had more runs than fit: this sub-batch goes over raw
+	std::vector<int> n_xr, n_yr;        // runs found per chunk
+	int n_xruns = 0, n_yruns = 0;
+	bool packed = false;
+	double t_host0 = 0;
 
-	bool create(int dev)
+	bool create(int dev, Device *own)
 	{
-		device = dev;
+		device = dev, owner = own;
 		if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
 		if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
 		for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
@@ -85,13 +157,15 @@ struct Slot {
 		if (device < 0) return;
 		cudaSetDevice(device);
 		mm2b_ws_destroy(ws), ws = nullptr;
-		cudaFree(d_off), cudaFree(d_u_off), cudaFree(d_b_off), cudaFree(d_a), cudaFree(d_b), cudaFree(d_u);
-		cudaFree(d_n_u), cudaFree(d_n_v), cudaFree(d_status);
+		cudaFree(d_off), cudaFree(d_u_off), cudaFree(d_b_off), cudaFree(d_a), cudaFree(d_b), cudaFree(d_u), cudaFree(d_bi);
+		cudaFree(d_n_u), cudaFree(d_n_v), cudaFree(d_status), cudaFree(d_lo), cudaFree(d_xruns), cudaFree(d_yruns);
 		cudaFreeHost(h_off), cudaFreeHost(h_u_off), cudaFreeHost(h_b_off), cudaFreeHost(h_cnt);
+		cudaFreeHost(h_lo), cudaFreeHost(h_xruns), cudaFreeHost(h_yruns), cudaFreeHost(h_bi);
 		h_cnt = nullptr;
-		d_off = d_u_off = d_b_off = nullptr, d_a = d_b = nullptr, d_u = nullptr, d_n_u = d_n_v = d_status = nullptr;
+		d_off = d_u_off = d_b_off = nullptr, d_a = d_b = nullptr, d_u = nullptr, d_bi = nullptr, d_n_u = d_n_v = d_status = nullptr;
+		d_lo = d_xruns = d_yruns = nullptr, h_lo = h_xruns = h_yruns = nullptr, h_bi = nullptr;
 		h_off = h_u_off = h_b_off = nullptr;
-		cap_anchors = cap_reads = 0;
+		cap_anchors = cap_reads = cap_runs = 0;
 	}
 	void destroy()
 	{
@@ -106,22 +180,34 @@ struct Slot {
 		if (n_anchors <= cap_anchors && n_reads <= cap_reads) return true;
 		const int64_t na = std::max<int64_t>(n_anchors + n_anchors / 4, std::max<int64_t>(cap_anchors, 1024));
 		const int64_t nr = std::max<int64_t>(n_reads + n_reads / 4, std::max<int64_t>(cap_reads, 64));
+		const int64_t nruns = na / 4 + 64;
 		cudaStreamSynchronize(stream);
 		release();
 		ws = mm2b_ws_create(device, na, nr);
 		if (!ws) return false;
 		bool ok = cuda_ok(dmalloc(&d_off, (nr + 1) * 8), "cudaMalloc") && cuda_ok(dmalloc(&d_u_off, (nr + 1) * 8), "cudaMalloc")
 		       && cuda_ok(dmalloc(&d_b_off, (nr + 1) * 8), "cudaMalloc") && cuda_ok(dmalloc(&d_a, na * 16), "cudaMalloc")
-		       && cuda_ok(dmalloc(&d_b, na * 16), "cudaMalloc") && cuda_ok(dmalloc(&d_u, na * 8), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_bi, na * 4), "cudaMalloc") && cuda_ok(dmalloc(&d_u, na * 8), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_lo, na * 8), "cudaMalloc") && cuda_ok(dmalloc(&d_xruns, nruns * 8), "cudaMalloc")
+		       && cuda_ok(dmalloc(&d_yruns, nruns * 8), "cudaMalloc")
 		       && cuda_ok(dmalloc(&d_n_u, nr * 4), "cudaMalloc") && cuda_ok(dmalloc(&d_n_v, nr * 4), "cudaMalloc")
 		       && cuda_ok(dmalloc(&d_status, nr * 4), "cudaMalloc")
 		       && cuda_ok(hmalloc(&h_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
 		       && cuda_ok(hmalloc(&h_u_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
 		       && cuda_ok(hmalloc(&h_b_off, (nr + 1) * 8, cudaHostAllocPortable), "cudaHostAlloc")
-		       && cuda_ok(hmalloc(&h_cnt, 40, cudaHostAllocPortable), "cudaHostAlloc");
+		       && cuda_ok(hmalloc(&h_cnt, 64, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_lo, na * 8, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_xruns, nruns * 8, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_yruns, nruns * 8, cudaHostAllocPortable), "cudaHostAlloc")
+		       && cuda_ok(hmalloc(&h_bi, na * 4, cudaHostAllocPortable), "cudaHostAlloc");
 		if (!ok) return false;
-		cap_anchors = na, cap_reads = nr;
+		cap_anchors = na, cap_reads = nr, cap_runs = nruns;
 		return true;
+	}
+	bool ensure_b()
+	{
+		if (d_b) return true;
+		return cuda_ok(dmalloc(&d_b, cap_anchors * 16), "cudaMalloc(d_b)");
 	}
 };
 
@@ -136,17 +222,22 @@ struct Job {
 	int64_t *u_off, *b_off;
 	uint64_t *u;
 	mm2b_anchor_t *b;
+	int32_t *bi;
+	bool pack = true, device_gather = false;
 	std::vector<SubBatch> subs;
 	std::atomic<int> next{0};
 	std::atomic<int> failed{0};
 	char err[512] = {0};
 	std::mutex mu;
 	std::condition_variable cv;
-	int workers_left = 0;
+	int workers_left = 0;       // guarded by mu; the caller leaves when it reaches 0
 	// stats
 	std::atomic<int64_t> n_chains{0}, n_chained{0}, cells_issued{0}, cells_ref{0}, window_cells{0}, n_general{0}, n_heavy{0};
-	double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;   // guarded by mu
+	std::atomic<int64_t> h2d_bytes{0}, d2h_bytes{0}, n_packed{0}, n_raw{0};
+	double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, pack_ms = 0, gather_ms = 0;   // guarded by mu
 };
+
+struct ActiveJob { Job *job; int in_flight; bool exhausted; };
 
 struct Device {
 	int id = -1;
@@ -155,7 +246,13 @@ struct Device {
 	std::mutex mu;
 	std::condition_variable cv;
 	std::deque<Job*> queue;
+	uint64_t wake = 0;          // bumped (under mu) by stream callbacks and helper tasks: something changed, look again
 	bool stop = false;
+	void poke()
+	{
+		{ std::lock_guard<std::mutex> lk(mu); ++wake; }
+		cv.notify_one();
+	}
 };
 
 struct Backend {
@@ -163,10 +260,12 @@ struct Backend {
 	std::mutex mu;              // guards init/shutdown
 	bool up = false;
 	int64_t sub_anchors = 2 << 20;
+	int64_t pack_chunk = 128 << 10;     // anchors per helper task
 	bool want_stats = true;
 	bool trace = false;
+	bool default_pack = true, default_device_gather = false;
 	std::atomic<int> count_cells{0};
-	bool use_batcher = true;       // MM2B_BATCHER=0: every mm_chain_dp caller drives its own stream instead
+	Pool pool;
 	cudaEvent_t trace_ev0[64] = {};
 } g;
 
@@ -176,12 +275,78 @@ void job_fail(Job *job)
 	if (!job->failed.exchange(1)) snprintf(job->err, sizeof(job->err), "%s", mm2b_last_error());
 }
 
-// enqueue H2D + kernels + D2H of the per-read counts for sub-batch `si` on `s`
-bool stage_issue(Slot &s, Job *job, int si)
+void CUDART_CB slot_signal_counts(void *p) { Slot *s = (Slot*)p; s->sig.store(1, std::memory_order_release); s->owner->poke(); }
+void CUDART_CB slot_signal_outputs(void *p) { Slot *s = (Slot*)p; s->sig.store(2, std::memory_order_release); s->owner->poke(); }
+
+// ---- packing ----------------------------------------------------------------------------------------------------------
+// One chunk [i0, i1) of a sub-batch: low words to lo[], and a run of {first index, high word} whenever a high word differs
+// from the previous anchor's (every chunk opens its own runs, so chunks are independent).  Returns false when the runs do not
+// fit `cap` entries — then the anchors' high words are too varied for this format and the sub-batch goes over as it is.
+bool pack_chunk(const mm2b_anchor_t *a, int64_t i0, int64_t i1, uint2 *lo, uint2 *xr, int &nx, uint2 *yr, int &ny, int cap)
+{
+	nx = ny = 0;
+	if (i0 >= i1) return true;
+	uint32_t px = ~(uint32_t)(a[i0].x >> 32), py = ~(uint32_t)(a[i0].y >> 32);
+	for (int64_t i = i0; i < i1; ++i) {
+		const uint64_t x = a[i].x, y = a[i].y;
+		lo[i] = make_uint2((uint32_t)x, (uint32_t)y);
+		const uint32_t xh = (uint32_t)(x >> 32), yh = (uint32_t)(y >> 32);
+		if (xh != px) {
+			if (nx == cap) return false;
+			xr[nx++] = make_uint2((uint32_t)i, xh), px = xh;
+		}
+		if (yh != py) {
+			if (ny == cap) return false;
+			yr[ny++] = make_uint2((uint32_t)i, yh), py = yh;
+		}
+	}
+	return true;
+}
+
+int n_chunks_of(int64_t na) { return (int)std::max<int64_t>(1, (na + g.pack_chunk - 1) / g.pack_chunk); }
+
+void start_pack(Slot &s, Job *job, int si)
+{
+	const SubBatch sb = job->subs[si];
+	const int64_t a0 = job->off[sb.r0], na = job->off[sb.r1] - a0;
+	const int nc = n_chunks_of(na);
+	const int cap = (int)(s.cap_runs / nc);         // every chunk owns an equal share of the run buffers
+	s.n_xr.assign(nc, 0), s.n_yr.assign(nc, 0);
+	s.pack_overflow.store(0);
+	s.host_left.store(nc);
+	s.t_host0 = now_ms();
+	const mm2b_anchor_t *src = job->a + a0;
+	for (int c = 0; c < nc; ++c) {
+		g.pool.submit([&s, src, na, nc, cap, c] {
+			const int64_t i0 = na * c / nc, i1 = na * (c + 1) / nc;
+			if (!s.pack_overflow.load(std::memory_order_relaxed) &&
+			    !pack_chunk(src, i0, i1, s.h_lo, s.h_xruns + (int64_t)c * cap, s.n_xr[c], s.h_yruns + (int64_t)c * cap, s.n_yr[c], cap))
+				s.pack_overflow.store(1);
+			if (s.host_left.fetch_sub(1, std::memory_order_acq_rel) == 1) s.owner->poke();
+		});
+	}
+}
+
+// close the gaps between the chunks' run lists (a few thousand entries); returns false if the sub-batch must go over raw
+bool finish_pack(Slot &s, int64_t na)
+{
+	if (s.pack_overflow.load()) return false;
+	const int nc = (int)s.n_xr.size();
+	const int cap = (int)(s.cap_runs / nc);
+	int nx = s.n_xr[0], ny = s.n_yr[0];
+	for (int c = 1; c < nc; ++c) {
+		memmove(s.h_xruns + nx, s.h_xruns + (int64_t)c * cap, (size_t)s.n_xr[c] * 8), nx += s.n_xr[c];
+		memmove(s.h_yruns + ny, s.h_yruns + (int64_t)c * cap, (size_t)s.n_yr[c] * 8), ny += s.n_yr[c];
+	}
+	s.n_xruns = nx, s.n_yruns = ny;
+	return na == 0 || (nx > 0 && ny > 0);
+}
+
+// enqueue H2D + kernels + D2H of the per-read counts for the slot's sub-batch
+bool stage_issue(Slot &s, Job *job, int si, bool packed)
 {
 	const SubBatch sb = job->subs[si];
 	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0], na = job->off[sb.r1] - a0;
-	if (!s.ensure(na, nr)) return false;
 	mm2b_ws_set_counting(s.ws, g.count_cells.load());
 	int64_t longest = 0;
 	for (int64_t r = 0; r <= nr; ++r) {
@@ -190,13 +355,33 @@ bool stage_issue(Slot &s, Job *job, int si)
 	}
 	mm2b_ws_set_longest_read(s.ws, longest);          // lets the device call skip the heavy-read kernel when no read can qualify
 	cudaStream_t st = s.stream;
+	s.packed = packed;
 	bool ok = cuda_ok(cudaEventRecord(s.ev[0], st), "cudaEventRecord")
-	       && cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off")
-	       && (na == 0 || cuda_ok(cudaMemcpyAsync(s.d_a, job->a + a0, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors"))
-	       && cuda_ok(cudaEventRecord(s.ev[1], st), "cudaEventRecord");
+	       && cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off");
+	int64_t h2d = (nr + 1) * 8;
+	if (ok && na > 0) {
+		if (packed) {
+			ok = cuda_ok(cudaMemcpyAsync(s.d_lo, s.h_lo, (size_t)na * 8, cudaMemcpyHostToDevice, st), "H2D packed anchors")
+			  && cuda_ok(cudaMemcpyAsync(s.d_xruns, s.h_xruns, (size_t)s.n_xruns * 8, cudaMemcpyHostToDevice, st), "H2D x runs")
+			  && cuda_ok(cudaMemcpyAsync(s.d_yruns, s.h_yruns, (size_t)s.n_yruns * 8, cudaMemcpyHostToDevice, st), "H2D y runs")
+			  && mm2b_unpack_anchors_device(s.device, na, s.d_lo, s.d_xruns, s.n_xruns, s.d_yruns, s.n_yruns, s.d_a, st) == MM2B_OK;
+			h2d += na * 8 + ((int64_t)s.n_xruns + s.n_yruns) * 8;
+		} else {
+			ok = cuda_ok(cudaMemcpyAsync(s.d_a, job->a + a0, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
+			h2d += na * 16;
+		}
+	}
+	ok = ok && cuda_ok(cudaEventRecord(s.ev[1], st), "cudaEventRecord");
 	if (!ok) return false;
-	if (mm2b_chain_batch_device(s.ws, job->par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st) != MM2B_OK)
-		return false;
+	int rc;
+	if (job->device_gather) {
+		if (!s.ensure_b()) return false;
+		rc = mm2b_chain_batch_device(s.ws, job->par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st);
+	} else {
+		rc = mm2b_chain_batch_device_idx(s.ws, job->par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_bi, st);
+	}
+	if (rc != MM2B_OK) return false;
+	s.sig.store(0);
 	ok = cuda_ok(cudaEventRecord(s.ev[2], st), "cudaEventRecord")
 	  && cuda_ok(cudaMemcpyAsync(job->n_u + sb.r0, s.d_n_u, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_u")
 	  && cuda_ok(cudaMemcpyAsync(job->n_v + sb.r0, s.d_n_v, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_v")
@@ -204,39 +389,74 @@ bool stage_issue(Slot &s, Job *job, int si)
 	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
 	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
 	  && cuda_ok(cudaMemcpyAsync(s.h_cnt, mm2b_ws_counters_dev(s.ws), 40, cudaMemcpyDeviceToHost, st), "D2H counters")
-	  && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord");
-	s.sub = si, s.stage = 1;
+	  && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord")
+	  && cuda_ok(cudaLaunchHostFunc(st, slot_signal_counts, &s), "cudaLaunchHostFunc");
+	job->h2d_bytes += h2d, job->d2h_bytes += nr * 12 + (nr + 1) * 16 + 40;
+	if (packed) job->n_packed += 1; else job->n_raw += 1;
 	return ok;
 }
 
-// counts are on the host: publish offsets, enqueue the D2H of exactly the packed u[] / b[] bytes
+// counts are on the host: publish offsets, enqueue the D2H of exactly the packed u[] and b[] / bi[] bytes
 bool stage_outputs(Slot &s, Job *job)
 {
 	const SubBatch sb = job->subs[s.sub];
 	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0];
-	if (!cuda_ok(cudaEventSynchronize(s.ev[3]), "cudaEventSynchronize")) return false;
 	const int64_t tot_u = s.h_u_off[nr], tot_b = s.h_b_off[nr];
 	// sub-batch outputs are packed from the sub-batch's own anchor offset: they always fit there since n_v <= n per read
 	for (int64_t r = 0; r < nr; ++r) job->u_off[sb.r0 + r] = a0 + s.h_u_off[r], job->b_off[sb.r0 + r] = a0 + s.h_b_off[r];
 	cudaStream_t st = s.stream;
 	bool ok = cuda_ok(cudaEventRecord(s.ev[4], st), "cudaEventRecord")
-	       && (tot_u == 0 || cuda_ok(cudaMemcpyAsync(job->u + a0, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"))
-	       && (tot_b == 0 || cuda_ok(cudaMemcpyAsync(job->b + a0, s.d_b, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st), "D2H b"))
-	       && cuda_ok(cudaEventRecord(s.ev[5], st), "cudaEventRecord");
-	job->n_chains += tot_u, job->n_chained += tot_b;
-	s.stage = 2;
+	       && (tot_u == 0 || cuda_ok(cudaMemcpyAsync(job->u + a0, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"));
+	int64_t d2h = tot_u * 8;
+	if (ok && tot_b > 0) {
+		if (job->device_gather) {
+			ok = cuda_ok(cudaMemcpyAsync(job->b + a0, s.d_b, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st), "D2H b");
+			d2h += tot_b * 16;
+		} else {
+			int32_t *dst = job->bi ? job->bi + a0 : s.h_bi;           // indices straight to the caller, or staged for the host gather
+			ok = cuda_ok(cudaMemcpyAsync(dst, s.d_bi, (size_t)tot_b * 4, cudaMemcpyDeviceToHost, st), "D2H bi");
+			d2h += tot_b * 4;
+		}
+	}
+	ok = ok && cuda_ok(cudaEventRecord(s.ev[5], st), "cudaEventRecord")
+	        && cuda_ok(cudaLaunchHostFunc(st, slot_signal_outputs, &s), "cudaLaunchHostFunc");
+	job->n_chains += tot_u, job->n_chained += tot_b, job->d2h_bytes += d2h;
 	return ok;
 }
 
-bool stage_finish(Slot &s, Job *job)
+// b[] = a[bi[]] per read (chain.c:412-420's copies, done where a[] still lives), in chunks of reads on the helper threads
+void start_gather(Slot &s, Job *job)
 {
-	if (!cuda_ok(cudaEventSynchronize(s.ev[5]), "cudaEventSynchronize")) return false;
+	const SubBatch sb = job->subs[s.sub];
+	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0], tot_b = s.h_b_off[nr];
+	const int nc = (int)std::max<int64_t>(1, std::min<int64_t>(nr, (tot_b + g.pack_chunk - 1) / g.pack_chunk));
+	const int32_t *idx = job->bi ? job->bi + a0 : s.h_bi;
+	s.host_left.store(nc);
+	s.t_host0 = now_ms();
+	for (int c = 0; c < nc; ++c) {
+		g.pool.submit([&s, job, sb, a0, nr, nc, c, idx] {
+			const int64_t r0 = nr * c / nc, r1 = nr * (c + 1) / nc;
+			for (int64_t r = r0; r < r1; ++r) {
+				const int32_t nv = job->n_v[sb.r0 + r];
+				if (nv <= 0) continue;
+				const mm2b_anchor_t *src = job->a + job->off[sb.r0 + r];
+				const int32_t *ix = idx + s.h_b_off[r];
+				mm2b_anchor_t *dst = job->b + a0 + s.h_b_off[r];
+				for (int32_t k = 0; k < nv; ++k) dst[k] = src[ix[k]];
+			}
+			if (s.host_left.fetch_sub(1, std::memory_order_acq_rel) == 1) s.owner->poke();
+		});
+	}
+}
+
+void stage_finish(Slot &s, Job *job)
+{
 	if (g.trace) {              // MM2B_TRACE=1: timeline of this sub-batch relative to the first event of the job on this slot's device
 		float t[6];
 		for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], g.trace_ev0[s.device], s.ev[i]);
 		const SubBatch sb = job->subs[s.sub];
-		fprintf(stderr, "[mm2b trace] dev %d sub %3d reads %6lld anchors %8lld | start %8.3f h2d_done %8.3f kern_done %8.3f cnt_done %8.3f out_start %8.3f out_done %8.3f ms\n",
-		        s.device, s.sub, (long long)(sb.r1 - sb.r0), (long long)(job->off[sb.r1] - job->off[sb.r0]), t[0], t[1], t[2], t[3], t[4], t[5]);
+		fprintf(stderr, "[mm2b trace] dev %d sub %3d reads %6lld anchors %8lld %s | start %8.3f h2d_done %8.3f kern_done %8.3f cnt_done %8.3f out_start %8.3f out_done %8.3f ms\n",
+		        s.device, s.sub, (long long)(sb.r1 - sb.r0), (long long)(job->off[sb.r1] - job->off[sb.r0]), s.packed ? "packed" : "raw   ", t[0], t[1], t[2], t[3], t[4], t[5]);
 	}
 	if (g.want_stats) {
 		float h2d = 0, ker = 0, d2h0 = 0, d2h1 = 0;
@@ -247,74 +467,130 @@ bool stage_finish(Slot &s, Job *job)
 		std::lock_guard<std::mutex> lk(job->mu);
 		job->h2d_ms += h2d, job->kernel_ms += ker, job->d2h_ms += d2h0 + d2h1;
 	}
-	s.stage = 0, s.sub = -1;
-	return true;
 }
 
-void run_job_on_device(Device *d, Job *job)
-{
-	cudaSetDevice(d->id);
-	if (g.trace) {
-		if (!g.trace_ev0[d->id]) cudaEventCreate(&g.trace_ev0[d->id]);
-		cudaEventRecord(g.trace_ev0[d->id], d->slots[0].stream);
-	}
-	const int n_subs = (int)job->subs.size();
-	bool more = true;
-	int in_flight = 0;
-	for (;;) {
-		bool progressed = false;
-		// advance whatever is ready, oldest sub-batch first, without blocking: a finished count copy turns into the output
-		// copies, a finished output copy frees the slot
-		for (int k = 0; k < NSLOT; ++k) {
-			Slot &s = d->slots[k];
-			if (s.stage == 0) continue;
-			if (job->failed.load()) { cudaStreamSynchronize(s.stream); s.stage = 0, --in_flight, progressed = true; continue; }
-			const cudaError_t q = cudaEventQuery(s.stage == 1 ? s.ev[3] : s.ev[5]);
-			if (q == cudaErrorNotReady) continue;
-			if (q != cudaSuccess) { mm2b::cuda_ok(q, "cudaEventQuery"); job_fail(job); s.stage = 0, --in_flight; continue; }
-			progressed = true;
-			if (s.stage == 1) {
-				if (!stage_outputs(s, job)) { job_fail(job); s.stage = 0, --in_flight; }
-			} else {
-				if (!stage_finish(s, job)) job_fail(job);
-				s.stage = 0, --in_flight;
-			}
-		}
-		// keep the copy engines fed: every free slot gets the next sub-batch right away
-		while (more && in_flight < NSLOT && !job->failed.load()) {
-			const int si = job->next.fetch_add(1);
-			if (si >= n_subs) { more = false; break; }
-			int k = 0;
-			while (d->slots[k].stage != 0) ++k;
-			if (!stage_issue(d->slots[k], job, si)) { job_fail(job); d->slots[k].stage = 0; break; }
-			++in_flight, progressed = true;
-		}
-		if (in_flight == 0 && (!more || job->failed.load())) break;
-		if (!progressed) {          // nothing ready yet: events of different slots complete in no fixed order, so poll all of them
-			struct timespec ts = {0, 20000};                                   // 20 us
-			nanosleep(&ts, nullptr);
-		}
-	}
-}
-
+// One worker per device.  It never blocks on the GPU or on the helper threads: stream callbacks and helper tasks bump
+// `wake`, the worker sleeps on the condition variable in between (no polling loop, no busy core).
 void device_worker(Device *d)
 {
 	cudaSetDevice(d->id);
+	std::vector<ActiveJob> active;
+	int in_flight = 0;
+	uint64_t seen = 0;
+	auto release_slot = [&](Slot &s) {
+		for (auto &aj : active) if (aj.job == s.job) --aj.in_flight;
+		s.stage = 0, s.sub = -1, s.job = nullptr;
+		--in_flight;
+	};
+	auto fail_slot = [&](Slot &s) {              // nothing of this sub-batch may still be in flight towards the caller's buffers
+		job_fail(s.job);
+		cudaStreamSynchronize(s.stream);
+		while (s.host_left.load() > 0) std::this_thread::yield();
+		release_slot(s);
+	};
 	for (;;) {
-		Job *job = nullptr;
 		{
 			std::unique_lock<std::mutex> lk(d->mu);
-			d->cv.wait(lk, [&] { return d->stop || !d->queue.empty(); });
-			if (d->queue.empty()) return;
-			job = d->queue.front();
-			d->queue.pop_front();
+			if (in_flight == 0 && active.empty())
+				d->cv.wait(lk, [&] { return d->stop || !d->queue.empty(); });
+			else
+				d->cv.wait_for(lk, std::chrono::milliseconds(2), [&] { return d->stop || !d->queue.empty() || d->wake != seen; });
+			seen = d->wake;
+			while (!d->queue.empty()) {
+				active.push_back(ActiveJob{d->queue.front(), 0, false});
+				d->queue.pop_front();
+			}
+			if (d->stop && active.empty() && in_flight == 0) return;
 		}
-		run_job_on_device(d, job);
-		{
-			std::lock_guard<std::mutex> lk(job->mu);
-			--job->workers_left;
+		bool progressed = true;
+		while (progressed) {
+			progressed = false;
+			// advance whatever is ready
+			for (int k = 0; k < NSLOT; ++k) {
+				Slot &s = d->slots[k];
+				if (s.stage == 0) continue;
+				Job *job = s.job;
+				if (s.stage == 1) {                                         // packing
+					if (s.host_left.load(std::memory_order_acquire) > 0) continue;
+					progressed = true;
+					const SubBatch sb = job->subs[s.sub];
+					{
+						std::lock_guard<std::mutex> lk(job->mu);
+						job->pack_ms += now_ms() - s.t_host0;
+					}
+					const bool packed = finish_pack(s, job->off[sb.r1] - job->off[sb.r0]);
+					if (job->failed.load() || !stage_issue(s, job, s.sub, packed)) { fail_slot(s); continue; }
+					s.stage = 2;
+				} else if (s.stage == 2) {                                  // kernels + counts
+					if (s.sig.load(std::memory_order_acquire) < 1) continue;
+					progressed = true;
+					if (job->failed.load() || !cuda_ok(cudaEventQuery(s.ev[3]), "counts copy") || !stage_outputs(s, job)) { fail_slot(s); continue; }
+					s.stage = 3;
+				} else if (s.stage == 3) {                                  // outputs
+					if (s.sig.load(std::memory_order_acquire) < 2) continue;
+					progressed = true;
+					if (job->failed.load() || !cuda_ok(cudaEventQuery(s.ev[5]), "output copy")) { fail_slot(s); continue; }
+					stage_finish(s, job);
+					const SubBatch sb = job->subs[s.sub];
+					if (job->b && !job->device_gather && s.h_b_off[sb.r1 - sb.r0] > 0) {
+						start_gather(s, job);
+						s.stage = 4;
+					} else release_slot(s);
+				} else {                                                    // gathering
+					if (s.host_left.load(std::memory_order_acquire) > 0) continue;
+					progressed = true;
+					{
+						std::lock_guard<std::mutex> lk(job->mu);
+						job->gather_ms += now_ms() - s.t_host0;
+					}
+					release_slot(s);
+				}
+			}
+			// keep the pipeline fed: every free slot gets the next sub-batch of the oldest call that still has some
+			for (int k = 0; k < NSLOT && in_flight < NSLOT; ++k) {
+				Slot &s = d->slots[k];
+				if (s.stage != 0) continue;
+				ActiveJob *pick = nullptr;
+				int si = -1;
+				for (auto &aj : active) {
+					if (aj.exhausted) continue;
+					if (aj.job->failed.load()) { aj.exhausted = true; continue; }
+					si = aj.job->next.fetch_add(1);
+					if (si >= (int)aj.job->subs.size()) { aj.exhausted = true; continue; }
+					pick = &aj;
+					break;
+				}
+				if (!pick) break;
+				Job *job = pick->job;
+				if (g.trace && !g.trace_ev0[d->id]) {
+					cudaEventCreate(&g.trace_ev0[d->id]);
+					cudaEventRecord(g.trace_ev0[d->id], s.stream);
+				}
+				const SubBatch sb = job->subs[si];
+				const int64_t na = job->off[sb.r1] - job->off[sb.r0];
+				s.job = job, s.sub = si;
+				++pick->in_flight, ++in_flight;
+				progressed = true;
+				if (!s.ensure(na, sb.r1 - sb.r0)) { s.stage = 2; fail_slot(s); continue; }
+				if (job->pack && na > 0 && na < (1ll << 31)) {
+					s.stage = 1;
+					start_pack(s, job, si);
+				} else {
+					s.stage = 2;
+					if (!stage_issue(s, job, si, false)) fail_slot(s);
+				}
+			}
+			// calls this device has nothing left to do for: tell the caller (under its lock: it may leave as soon as it sees 0)
+			for (size_t i = 0; i < active.size();) {
+				ActiveJob &aj = active[i];
+				if (aj.exhausted && aj.in_flight == 0) {
+					Job *job = aj.job;
+					active.erase(active.begin() + (long)i);
+					std::lock_guard<std::mutex> lk(job->mu);
+					if (--job->workers_left == 0) job->cv.notify_all();
+				} else ++i;
+			}
 		}
-		job->cv.notify_all();
 	}
 }
 
@@ -330,33 +606,6 @@ int parse_device_list(const char *s, std::vector<int> &out)
 	return (int)out.size();
 }
 
-// ---- per-thread single-read path (mm_chain_dp) -------------------------------------------------------------------
-struct ThreadCtx {
-	Slot slot;
-	int32_t *h_cnt = nullptr;           // pinned: n_u, n_v, status
-	mm2b_anchor_t *h_a = nullptr, *h_b = nullptr;   // pinned staging, cap_anchors
-	uint64_t *h_u = nullptr;
-	int64_t h_cap = 0;
-	bool live = false;
-};
-std::mutex g_tctx_mu;
-std::vector<ThreadCtx*> g_tctx;
-std::atomic<int> g_tctx_rr{0};
-
-ThreadCtx *thread_ctx()
-{
-	static thread_local ThreadCtx *t = nullptr;
-	if (t && t->live) return t;
-	t = new ThreadCtx();
-	const int dev = g.devs[g_tctx_rr.fetch_add(1) % g.devs.size()]->id;
-	if (!t->slot.create(dev)) { fprintf(stderr, "[mm2b] %s\n", mm2b_last_error()); exit(1); }
-	hmalloc(&t->h_cnt, 64, cudaHostAllocPortable);
-	t->live = true;
-	std::lock_guard<std::mutex> lk(g_tctx_mu);
-	g_tctx.push_back(t);
-	return t;
-}
-
 [[noreturn]] void fatal(const char *what)
 {
 	fprintf(stderr, "[mm2b] fatal: %s: %s\n", what, mm2b_last_error());     // same behaviour as checkError (chain_hardware.cpp:208)
@@ -367,7 +616,8 @@ ThreadCtx *thread_ctx()
 // mm_chain_dp is a synchronous per-read call made by n_threads kt_for workers (map.c:561).  One GPU launch per read would
 // be dominated by launch/sync latency, so concurrent callers are aggregated: each caller copies its anchors into the open
 // flight's pinned buffer and sleeps; a dispatcher thread per device closes the flight as soon as the GPU is free, runs it as
-// ONE device batch and wakes the callers, which copy their own results out.  While a flight is on the GPU the next one fills,
+// ONE device batch and wakes the callers, which gather their own chains from the anchors they still hold (only the 4-byte
+// indices come back over PCIe).  While a flight is on the GPU the next one fills,
 // so the batch size adapts to the load (1 read with -t 1, hundreds with an oversubscribed -t).  This is the CUDA counterpart
 // of the reference's hw_queue / mutex arbitration (chain_hardware.cpp:45-98), which admitted ONE read at a time.
 struct Req {
@@ -378,7 +628,8 @@ struct Req {
 
 struct Flight {
 	Slot slot;
-	mm2b_anchor_t *h_a = nullptr, *h_b = nullptr;
+	mm2b_anchor_t *h_a = nullptr;
+	int32_t *h_bi = nullptr;
 	uint64_t *h_u = nullptr;
 	int32_t *h_cnt = nullptr;       // 3 x max_reqs: n_u, n_v, status
 	int64_t cap = 0;                // anchors
@@ -409,9 +660,9 @@ bool flight_grow(Flight &f, int dev, int64_t need)
 {
 	const int64_t cap = std::max<int64_t>(need + need / 4, 1 << 21);
 	cudaSetDevice(dev);
-	cudaFreeHost(f.h_a), cudaFreeHost(f.h_b), cudaFreeHost(f.h_u);
-	f.h_a = f.h_b = nullptr, f.h_u = nullptr;
-	if (!cuda_ok(hmalloc(&f.h_a, cap * 16, cudaHostAllocPortable), "cudaHostAlloc") || !cuda_ok(hmalloc(&f.h_b, cap * 16, cudaHostAllocPortable), "cudaHostAlloc") ||
+	cudaFreeHost(f.h_a), cudaFreeHost(f.h_bi), cudaFreeHost(f.h_u);
+	f.h_a = nullptr, f.h_bi = nullptr, f.h_u = nullptr;
+	if (!cuda_ok(hmalloc(&f.h_a, cap * 16, cudaHostAllocPortable), "cudaHostAlloc") || !cuda_ok(hmalloc(&f.h_bi, cap * 4, cudaHostAllocPortable), "cudaHostAlloc") ||
 	    !cuda_ok(hmalloc(&f.h_u, cap * 8, cudaHostAllocPortable), "cudaHostAlloc")) return false;
 	if (!f.h_cnt && !cuda_ok(hmalloc(&f.h_cnt, FLIGHT_MAX_REQS * 12, cudaHostAllocPortable), "cudaHostAlloc")) return false;
 	f.cap = cap;
@@ -437,7 +688,7 @@ void flight_run(Batcher *bt, Flight &f)          // dispatcher thread, no lock h
 	cudaStream_t st = s.stream;
 	bool ok = cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off")
 	       && cuda_ok(cudaMemcpyAsync(s.d_a, f.h_a, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
-	if (!ok || mm2b_chain_batch_device(s.ws, &f.par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st) != MM2B_OK)
+	if (!ok || mm2b_chain_batch_device_idx(s.ws, &f.par, nr, na, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_bi, st) != MM2B_OK)
 		fatal("enqueue");
 	ok = cuda_ok(cudaMemcpyAsync(f.h_cnt, s.d_n_u, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_u")
 	  && cuda_ok(cudaMemcpyAsync(f.h_cnt + FLIGHT_MAX_REQS, s.d_n_v, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_v")
@@ -448,7 +699,7 @@ void flight_run(Batcher *bt, Flight &f)          // dispatcher thread, no lock h
 	if (!ok) fatal("chain");
 	const int64_t tot_u = s.h_u_off[nr], tot_b = s.h_b_off[nr];
 	ok = (tot_u == 0 || cuda_ok(cudaMemcpyAsync(f.h_u, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"))
-	  && (tot_b == 0 || cuda_ok(cudaMemcpyAsync(f.h_b, s.d_b, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st), "D2H b"))
+	  && (tot_b == 0 || cuda_ok(cudaMemcpyAsync(f.h_bi, s.d_bi, (size_t)tot_b * 4, cudaMemcpyDeviceToHost, st), "D2H bi"))
 	  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
 	if (!ok) fatal("copy back");
 	for (int64_t r = 0; r < nr; ++r) {
@@ -519,6 +770,36 @@ void batcher_release(Batcher *bt, Flight *f)
 	}
 }
 
+// undo whatever mm2b_init built so far (g.mu held): a failed start-up leaves no device without a worker and no thread behind
+void teardown_locked()
+{
+	for (Device *d : g.devs) {
+		{ std::lock_guard<std::mutex> l2(d->mu); d->stop = true; }
+		d->cv.notify_all();
+	}
+	for (Device *d : g.devs) {
+		if (d->worker.joinable()) d->worker.join();
+		for (auto &s : d->slots) s.destroy();
+		delete d;
+	}
+	g.devs.clear();
+	for (Batcher *bt : g_batchers) {
+		{ std::lock_guard<std::mutex> l2(bt->mu); bt->stop = true; }
+		bt->cv_disp.notify_all();
+		if (bt->th.joinable()) bt->th.join();
+		if (g.trace) fprintf(stderr, "[mm2b trace] batcher dev %d: %lld reads in %lld flights\n", bt->dev, (long long)bt->n_reqs.load(), (long long)bt->n_flights.load());
+		for (auto &f : bt->fl) {
+			f.slot.destroy();
+			cudaFreeHost(f.h_a), cudaFreeHost(f.h_bi), cudaFreeHost(f.h_u), cudaFreeHost(f.h_cnt);
+		}
+		delete bt;
+	}
+	g_batchers.clear();
+	g.pool.shutdown();
+	for (auto &e : g.trace_ev0) if (e) { cudaEventDestroy(e); e = nullptr; }
+	g.up = false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -552,28 +833,47 @@ int mm2b_init(int n_devices, const int *devices)
 	else if (n_devices > 0) for (int i = 0; i < n_devices; ++i) ids.push_back(i);
 	else if (!parse_device_list(getenv("MM2B_DEVICES"), ids)) for (int i = 0; i < visible; ++i) ids.push_back(i);
 	for (int id : ids) if (id < 0 || id >= visible) { set_error("%s%s", "mm2b_init: device id out of range", ""); return MM2B_ERR_ARG; }
-	if (const char *s = getenv("MM2B_TRACE")) g.trace = atoi(s) > 0;
-	if (const char *s = getenv("MM2B_BATCHER")) g.use_batcher = atoi(s) != 0;
+	bool use_batcher = true;
+	if (const char *s = getenv("MM2B_BATCHER")) use_batcher = atoi(s) != 0;
 	if (const char *s = getenv("MM2B_COUNT_CELLS")) g.count_cells.store(atoi(s) > 0);
 	if (const char *s = getenv("MM2B_SUB_ANCHORS")) { const long long v = atoll(s); if (v > 0) g.sub_anchors = v; }
+	if (const char *s = getenv("MM2B_PACK_CHUNK")) { const long long v = atoll(s); if (v > 0) g.pack_chunk = v; }
+	if (const char *s = getenv("MM2B_PACK")) g.default_pack = atoi(s) != 0;
+	if (const char *s = getenv("MM2B_GATHER")) g.default_device_gather = strcmp(s, "device") == 0;
+	int n_helpers = (int)std::thread::hardware_concurrency() - 2;
+	n_helpers = std::max(2, std::min(n_helpers, 16));
+	if (const char *s = getenv("MM2B_HOST_THREADS")) { const int v = atoi(s); if (v > 0) n_helpers = std::min(v, 256); }
+	bool ok = true;
 	for (int id : ids) {
 		Device *d = new Device();
 		d->id = id;
-		for (auto &s : d->slots) if (!s.create(id)) return MM2B_ERR_CUDA;
 		g.devs.push_back(d);
+		for (auto &s : d->slots) if (!s.create(id, d)) { ok = false; break; }
+		if (!ok) break;
 	}
 	lap("contexts, streams, events");
-	for (Device *d : g.devs) d->worker = std::thread(device_worker, d);
-	if (g.use_batcher) {
-		for (Device *d : g.devs) {
-			Batcher *bt = new Batcher();
-			bt->dev = d->id;
-			for (auto &f : bt->fl) if (!f.slot.create(d->id)) return MM2B_ERR_CUDA;
-			bt->th = std::thread(batcher_loop, bt);
-			g_batchers.push_back(bt);
+	if (ok) {
+		for (Device *d : g.devs) d->worker = std::thread(device_worker, d);
+		g.pool.start(n_helpers);
+		if (use_batcher) {
+			for (Device *d : g.devs) {
+				Batcher *bt = new Batcher();
+				bt->dev = d->id;
+				g_batchers.push_back(bt);
+				for (auto &f : bt->fl) if (!f.slot.create(d->id, d)) { ok = false; break; }
+				if (!ok) break;
+				bt->th = std::thread(batcher_loop, bt);
+			}
 		}
 	}
-	lap("worker + batcher threads");
+	if (!ok) {                       // leave nothing half-built behind: a later call starts from scratch
+		char keep[512];
+		snprintf(keep, sizeof(keep), "%s", mm2b_last_error());
+		teardown_locked();
+		set_error("%s%s", keep, "");
+		return MM2B_ERR_CUDA;
+	}
+	lap("worker + helper + batcher threads");
 	g.up = true;
 	return MM2B_OK;
 }
@@ -620,46 +920,30 @@ void mm2b_shutdown(void)
 	}
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.up) return;
-	for (Device *d : g.devs) {
-		{ std::lock_guard<std::mutex> l2(d->mu); d->stop = true; }
-		d->cv.notify_all();
-	}
-	for (Device *d : g.devs) {
-		if (d->worker.joinable()) d->worker.join();
-		for (auto &s : d->slots) s.destroy();
-		delete d;
-	}
-	g.devs.clear();
-	for (Batcher *bt : g_batchers) {
-		{ std::lock_guard<std::mutex> l2(bt->mu); bt->stop = true; }
-		bt->cv_disp.notify_all();
-		if (bt->th.joinable()) bt->th.join();
-		if (g.trace) fprintf(stderr, "[mm2b trace] batcher dev %d: %lld reads in %lld flights\n", bt->dev, (long long)bt->n_reqs.load(), (long long)bt->n_flights.load());
-		for (auto &f : bt->fl) {
-			f.slot.destroy();
-			cudaFreeHost(f.h_a), cudaFreeHost(f.h_b), cudaFreeHost(f.h_u), cudaFreeHost(f.h_cnt);
-		}
-		delete bt;
-	}
-	g_batchers.clear();
-	{
-		std::lock_guard<std::mutex> l3(g_tctx_mu);
-		for (ThreadCtx *t : g_tctx) {
-			t->slot.destroy();
-			cudaFreeHost(t->h_cnt), cudaFreeHost(t->h_a), cudaFreeHost(t->h_b), cudaFreeHost(t->h_u);
-			t->live = false;    // the owning thread re-creates it on next use
-		}
-		g_tctx.clear();
-	}
-	g.up = false;
+	teardown_locked();
 }
 
 int mm2b_num_devices(void) { return g.up ? (int)g.devs.size() : 0; }
+
+int mm2b_pack_anchors(const mm2b_anchor_t *a, int64_t n, void *lo, void *xruns, int32_t *n_xruns, void *yruns, int32_t *n_yruns, int32_t cap_runs)
+{
+	if (n < 0 || n >= (1ll << 31) || (n > 0 && (!a || !lo)) || !xruns || !yruns || !n_xruns || !n_yruns || cap_runs < 1) {
+		set_error("%s%s", "mm2b_pack_anchors: bad argument", "");
+		return MM2B_ERR_ARG;
+	}
+	int nx = 0, ny = 0;
+	if (!pack_chunk(a, 0, n, (uint2*)lo, (uint2*)xruns, nx, (uint2*)yruns, ny, cap_runs)) {
+		set_error("%s%s", "mm2b_pack_anchors: more runs of high words than cap_runs", "");
+		return MM2B_ERR_CAPACITY;
+	}
+	*n_xruns = nx, *n_yruns = ny;
+	return MM2B_OK;
+}
 void mm2b_set_counting(int on) { g.count_cells.store(on != 0); }
 
-int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
-                     int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
-                     uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats)
+int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
+                        int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
+                        uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int32_t *bi, int64_t b_cap, unsigned flags, mm2b_stats_t *stats)
 {
 	if (!g.up) {
 		const int rc = ensure_up();
@@ -667,11 +951,13 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
 	}
 	if (!par || n_reads < 0 || !off || !n_u || !n_v || !status || !u_off || !b_off) { set_error("%s%s", "mm2b_chain_batch: NULL argument", ""); return MM2B_ERR_ARG; }
 	const int64_t n_anchors = n_reads > 0 ? off[n_reads] : 0;
-	if (n_anchors > 0 && (!a || !u || !b)) { set_error("%s%s", "mm2b_chain_batch: NULL buffer", ""); return MM2B_ERR_ARG; }
+	if (n_anchors > 0 && (!a || !u || (!b && !bi))) { set_error("%s%s", "mm2b_chain_batch: NULL buffer", ""); return MM2B_ERR_ARG; }
 	if (u_cap < n_anchors || b_cap < n_anchors) { set_error("%s%s", "mm2b_chain_batch: u_cap and b_cap must be >= off[n_reads]", ""); return MM2B_ERR_CAPACITY; }
 	Job job;
 	job.par = par, job.n_reads = n_reads, job.off = off, job.a = a;
-	job.n_u = n_u, job.n_v = n_v, job.status = status, job.u_off = u_off, job.b_off = b_off, job.u = u, job.b = b;
+	job.n_u = n_u, job.n_v = n_v, job.status = status, job.u_off = u_off, job.b_off = b_off, job.u = u, job.b = b, job.bi = bi;
+	job.pack = !(flags & MM2B_F_RAW_INPUT);
+	job.device_gather = b && !bi && (flags & MM2B_F_DEVICE_GATHER);
 	// Cut into sub-batches of <= sub_anchors anchors (a larger single read stands alone).  The first and last few are smaller:
 	// the first copy and the last kernel + copy-back are the only stages nothing overlaps with, so they should be short.
 	for (int64_t r0 = 0; r0 < n_reads;) {
@@ -706,163 +992,21 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
 		stats->cells_issued = job.cells_issued, stats->cells_ref = job.cells_ref, stats->window_cells = job.window_cells, stats->n_general_reads = job.n_general;
 		stats->n_heavy_reads = job.n_heavy;
 		stats->h2d_ms = job.h2d_ms, stats->kernel_ms = job.kernel_ms, stats->d2h_ms = job.d2h_ms;
+		stats->h2d_bytes = job.h2d_bytes, stats->d2h_bytes = job.d2h_bytes, stats->n_packed_subs = job.n_packed, stats->n_raw_subs = job.n_raw;
+		stats->pack_ms = job.pack_ms, stats->gather_ms = job.gather_ms;
 	}
 	if (job.failed.load()) { set_error("%s%s", job.err, ""); return MM2B_ERR_CUDA; }
 	return MM2B_OK;
 }
 
-}  // extern "C"
-
-namespace {
-
-// Batches of the fiber-based kt_for() (fiber_for.h): all reads parked on this OS thread, grouped by chaining arguments, one
-// mm2b_chain_batch call per group from pinned staging that belongs to the thread.
-struct FiberStage {
-	mm2b_anchor_t *a = nullptr, *b = nullptr;
-	uint64_t *u = nullptr;
-	int64_t *off = nullptr, *u_off = nullptr, *b_off = nullptr;
-	int32_t *n_u = nullptr, *n_v = nullptr, *status = nullptr;
-	int64_t cap_a = 0, cap_r = 0;
-	void reserve(int64_t na, int64_t nr)
-	{
-		if (na > cap_a) {
-			mm2b_host_free(a), mm2b_host_free(b), mm2b_host_free(u);
-			cap_a = std::max<int64_t>(na + na / 2, 1 << 20);
-			a = (mm2b_anchor_t*)mm2b_host_alloc((size_t)cap_a * 16), b = (mm2b_anchor_t*)mm2b_host_alloc((size_t)cap_a * 16);
-			u = (uint64_t*)mm2b_host_alloc((size_t)cap_a * 8);
-		}
-		if (nr > cap_r) {
-			mm2b_host_free(off), mm2b_host_free(u_off), mm2b_host_free(b_off), mm2b_host_free(n_u), mm2b_host_free(n_v), mm2b_host_free(status);
-			cap_r = std::max<int64_t>(2 * nr, 1024);
-			off = (int64_t*)mm2b_host_alloc((size_t)cap_r * 16), u_off = (int64_t*)mm2b_host_alloc((size_t)cap_r * 16);
-			b_off = (int64_t*)mm2b_host_alloc((size_t)cap_r * 16);          // (2 entries per read: every group needs one more than it has reads)
-			n_u = (int32_t*)mm2b_host_alloc((size_t)cap_r * 4), n_v = (int32_t*)mm2b_host_alloc((size_t)cap_r * 4);
-			status = (int32_t*)mm2b_host_alloc((size_t)cap_r * 4);
-		}
-		if (!a || !b || !u || !off || !u_off || !b_off || !n_u || !n_v || !status) fatal("pinned staging for kt_for batches");
-	}
-};
-
-// kt_for()'s OS threads live for one call (one mini-batch of reads); the pinned staging outlives them in a pool
-std::mutex g_stage_mu;
-std::vector<FiberStage*> g_stage_pool;
-
-struct StageLease {                          // held by a thread for as long as it lives: its results stay valid until its next flush
-	FiberStage *st = nullptr;
-	FiberStage *get()
-	{
-		if (!st) {
-			std::lock_guard<std::mutex> lk(g_stage_mu);
-			if (!g_stage_pool.empty()) st = g_stage_pool.back(), g_stage_pool.pop_back();
-		}
-		if (!st) st = new FiberStage();
-		return st;
-	}
-	~StageLease()
-	{
-		if (!st) return;
-		std::lock_guard<std::mutex> lk(g_stage_mu);
-		g_stage_pool.push_back(st);
-	}
-};
-
-void fiber_flush(mm2b::FiberReq **reqs, int n)
+int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
+                     int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
+                     uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats)
 {
-	static thread_local StageLease lease;
-	FiberStage &st = *lease.get();
-	int64_t na = 0;
-	for (int r = 0; r < n; ++r) na += reqs[r]->n;
-	st.reserve(na, n);
-	std::vector<char> done((size_t)n, 0);
-	int64_t a_base = 0, r_base = 0, o_base = 0;
-	for (int first = 0; first < n; ++first) {
-		if (done[first]) continue;
-		const mm2b_params_t par = reqs[first]->par;
-		int64_t cnt = 0, ga = 0;
-		int64_t *off = st.off + o_base;
-		off[0] = 0;
-		std::vector<int> members;
-		for (int r = first; r < n; ++r) {
-			if (done[r] || !same_par(reqs[r]->par, par)) continue;
-			done[r] = 1;
-			members.push_back(r);
-			memcpy(st.a + a_base + ga, reqs[r]->a, (size_t)reqs[r]->n * 16);
-			ga += reqs[r]->n;
-			off[++cnt] = ga;
-		}
-		if (mm2b_chain_batch(&par, cnt, off, st.a + a_base, st.n_u + r_base, st.n_v + r_base, st.status + r_base, st.u_off + o_base, st.b_off + o_base,
-		                     st.u + a_base, std::max<int64_t>(ga, 1), st.b + a_base, std::max<int64_t>(ga, 1), nullptr) != MM2B_OK) fatal("mm2b_chain_batch");
-		for (int64_t k = 0; k < cnt; ++k) {
-			mm2b::FiberReq *q = reqs[members[(size_t)k]];
-			q->n_u = st.n_u[r_base + k], q->n_v = st.n_v[r_base + k], q->status = st.status[r_base + k];
-			q->u = st.u + a_base + st.u_off[o_base + k], q->b = st.b + a_base + st.b_off[o_base + k];
-		}
-		a_base += ga, r_base += cnt, o_base += cnt + 1;
-	}
+	const unsigned flags = (g.default_pack ? 0u : (unsigned)MM2B_F_RAW_INPUT) | (g.default_device_gather ? (unsigned)MM2B_F_DEVICE_GATHER : 0u);
+	if (!b && n_reads > 0 && off && off[n_reads] > 0) { set_error("%s%s", "mm2b_chain_batch: NULL buffer", ""); return MM2B_ERR_ARG; }
+	return mm2b_chain_batch_ex(par, n_reads, off, a, n_u, n_v, status, u_off, b_off, u, u_cap, b, nullptr, b_cap, flags, stats);
 }
-
-// MM2B_FIBER_ASYNC=1: the blocking batch call runs on a helper thread of the OS thread, which keeps seeding its other fibers
-// meanwhile (fiber_for.h: submit / wait).  Off by default until it has been timed on the GPU box.
-struct FiberFlusher {
-	std::thread th;
-	std::mutex mu;
-	std::condition_variable cv;
-	std::vector<mm2b::FiberReq*> reqs;
-	bool busy = false, quit = false;
-	void loop()
-	{
-		std::unique_lock<std::mutex> lk(mu);
-		for (;;) {
-			cv.wait(lk, [&] { return busy || quit; });
-			if (quit) return;
-			lk.unlock();
-			fiber_flush(reqs.data(), (int)reqs.size());
-			lk.lock();
-			busy = false;
-			cv.notify_all();
-		}
-	}
-	~FiberFlusher()
-	{
-		if (!th.joinable()) return;
-		{ std::lock_guard<std::mutex> lk(mu); quit = true; }
-		cv.notify_all();
-		th.join();
-	}
-};
-
-void *fiber_submit(mm2b::FiberReq **reqs, int n)
-{
-	static thread_local FiberFlusher fl;     // dies with the OS thread (end of the kt_for() call): joins its helper
-	if (!fl.th.joinable()) fl.th = std::thread([p = &fl] { p->loop(); });
-	{
-		std::lock_guard<std::mutex> lk(fl.mu);
-		fl.reqs.assign(reqs, reqs + n);
-		fl.busy = true;
-	}
-	fl.cv.notify_all();
-	return &fl;
-}
-
-void fiber_wait(void *ticket)
-{
-	FiberFlusher *fl = (FiberFlusher*)ticket;
-	std::unique_lock<std::mutex> lk(fl->mu);
-	fl->cv.wait(lk, [&] { return !fl->busy; });
-}
-
-struct FiberFlushInstaller {
-	FiberFlushInstaller()
-	{
-		mm2b::fiber_set_flush(fiber_flush);
-		const char *e = getenv("MM2B_FIBER_ASYNC");
-		if (e && atoi(e) > 0) mm2b::fiber_set_async(fiber_submit, fiber_wait);
-	}
-} g_fiber_flush_installer;
-
-}  // namespace
-
-extern "C" {
 
 mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
                            float gap_scale, int is_cdna, int n_segs, int64_t n, mm2b_anchor_t *a, int *n_u_, uint64_t **_u,
@@ -875,82 +1019,43 @@ mm2b_anchor_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
 		return 0;
 	}
 	if (!g.up && ensure_up() != MM2B_OK) fatal("mm2b_init");
-	if (mm2b::fiber_active()) {                                       // under the fiber-based kt_for(): park, get chained with the others
-		mm2b::FiberReq req;
-		req.par = mm2b_params_t{max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
-		req.n = n, req.a = a, req.n_u = req.n_v = 0, req.status = MM2B_READ_NO_CHAIN, req.u = nullptr, req.b = nullptr;
-		mm2b::fiber_chain(&req);
-		host_kfree(km, a);                                            // chain.c:356 / :421 — `a` is consumed on every path
-		mm2b_anchor_t *b = nullptr;
-		if (req.status == MM2B_READ_OK) {
-			uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(req.n_u, 1) * 8);
-			b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)req.n_v * 16);
-			if (req.n_u > 0) memcpy(u, req.u, (size_t)req.n_u * 8);
-			if (req.n_v > 0) memcpy(b, req.b, (size_t)req.n_v * 16);
-			*n_u_ = req.n_u, *_u = u;
-		}
-		return b;
-	}
-	if (g.use_batcher) {
+	const mm2b_params_t par = {max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
+	mm2b_anchor_t *b = nullptr;
+	if (!g_batchers.empty()) {
 		static thread_local int my_batcher = -1;
 		if (my_batcher < 0 || my_batcher >= (int)g_batchers.size()) my_batcher = g_batcher_rr.fetch_add(1) % (int)g_batchers.size();
 		Batcher *bt = g_batchers[my_batcher];
-		const mm2b_params_t par = {max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
 		Req req;
 		Flight *f = batcher_submit(bt, par, n, a, req);
-		host_kfree(km, a);                                            // chain.c:356 / :421 — `a` is consumed on every path
-		mm2b_anchor_t *b = nullptr;
 		if (req.status == MM2B_READ_OK) {                             // otherwise chain.c:355-358: NULL, *_u = NULL, *n_u_ = 0
+			// chain.c:359, :397: u has the size of the chain-END list in the reference; only its first n_u entries are defined, so
+			// an allocation of max(n_u,1) entries is indistinguishable to the caller (map.c:344-379 reads u[0..n_u) and frees it)
 			uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(req.n_u, 1) * 8);
 			b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)req.n_v * 16);   // kmalloc(km, 0) == NULL, as at chain.c:397
 			if (req.n_u > 0) memcpy(u, f->h_u + req.u_off, (size_t)req.n_u * 8);
-			if (req.n_v > 0) memcpy(b, f->h_b + req.b_off, (size_t)req.n_v * 16);
+			const int32_t *ix = f->h_bi + req.b_off;
+			for (int32_t k = 0; k < req.n_v; ++k) b[k] = a[ix[k]];      // chain.c:412-420: the caller still holds a[]
 			*n_u_ = req.n_u, *_u = u;
 		}
 		batcher_release(bt, f);
+		host_kfree(km, a);                                            // chain.c:356 / :421 — `a` is consumed on every path
 		return b;
 	}
-	ThreadCtx *t = thread_ctx();
-	Slot &s = t->slot;
-	cudaSetDevice(s.device);
-	if (!s.ensure(n, 1)) fatal("workspace allocation");
-	if (n > t->h_cap) {
-		cudaFreeHost(t->h_a), cudaFreeHost(t->h_b), cudaFreeHost(t->h_u);
-		t->h_cap = s.cap_anchors;
-		if (!cuda_ok(hmalloc(&t->h_a, t->h_cap * 16, cudaHostAllocPortable), "cudaHostAlloc") ||
-		    !cuda_ok(hmalloc(&t->h_b, t->h_cap * 16, cudaHostAllocPortable), "cudaHostAlloc") ||
-		    !cuda_ok(hmalloc(&t->h_u, t->h_cap * 8, cudaHostAllocPortable), "cudaHostAlloc")) fatal("pinned staging");
+	// MM2B_BATCHER=0: no aggregation across threads; every call is a one-read batch through the sub-batch pipeline
+	const int64_t off[2] = {0, n};
+	int32_t nu = 0, nv = 0, status = 0;
+	int64_t uo[2], bo[2];
+	std::vector<uint64_t> u_tmp((size_t)n);
+	std::vector<int32_t> bi((size_t)n);
+	if (mm2b_chain_batch_ex(&par, 1, off, a, &nu, &nv, &status, uo, bo, u_tmp.data(), n, nullptr, bi.data(), n, MM2B_F_RAW_INPUT, nullptr) != MM2B_OK) fatal("mm2b_chain_batch");
+	if (status == MM2B_READ_OK) {
+		uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(nu, 1) * 8);
+		b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)nv * 16);
+		if (nu > 0) memcpy(u, u_tmp.data() + uo[0], (size_t)nu * 8);
+		for (int32_t k = 0; k < nv; ++k) b[k] = a[bi[(size_t)bo[0] + (size_t)k]];
+		*n_u_ = nu, *_u = u;
 	}
-	const mm2b_params_t par = {max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, is_cdna, n_segs, gap_scale};
-	memcpy(t->h_a, a, (size_t)n * 16);
-	s.h_off[0] = 0, s.h_off[1] = n;
-	mm2b_ws_set_longest_read(s.ws, n);
-	cudaStream_t st = s.stream;
-	bool ok = cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, 16, cudaMemcpyHostToDevice, st), "H2D off")
-	       && cuda_ok(cudaMemcpyAsync(s.d_a, t->h_a, (size_t)n * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
-	if (!ok || mm2b_chain_batch_device(s.ws, &par, 1, n, s.d_off, s.d_a, s.d_n_u, s.d_n_v, s.d_status, s.d_u_off, s.d_b_off, s.d_u, s.d_b, st) != MM2B_OK)
-		fatal("enqueue");
-	ok = cuda_ok(cudaMemcpyAsync(t->h_cnt, s.d_n_u, 4, cudaMemcpyDeviceToHost, st), "D2H")
-	  && cuda_ok(cudaMemcpyAsync(t->h_cnt + 1, s.d_n_v, 4, cudaMemcpyDeviceToHost, st), "D2H")
-	  && cuda_ok(cudaMemcpyAsync(t->h_cnt + 2, s.d_status, 4, cudaMemcpyDeviceToHost, st), "D2H")
-	  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
-	if (!ok) fatal("chain");
-	const int n_u = t->h_cnt[0], n_v = t->h_cnt[1], status = t->h_cnt[2];
-	if (n_u > 0) {
-		ok = cuda_ok(cudaMemcpyAsync(t->h_u, s.d_u, (size_t)n_u * 8, cudaMemcpyDeviceToHost, st), "D2H u")
-		  && cuda_ok(cudaMemcpyAsync(t->h_b, s.d_b, (size_t)n_v * 16, cudaMemcpyDeviceToHost, st), "D2H b")
-		  && cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize");
-		if (!ok) fatal("copy back");
-	}
-	host_kfree(km, a);                                                // chain.c:356 / :421 — `a` is consumed on every path
-	if (status != MM2B_READ_OK) return 0;                             // chain.c:355-358
-	// chain.c:359, :397: u has the size of the chain-END list in the reference; only its first n_u entries are defined, so
-	// an allocation of max(n_u,1) entries is indistinguishable to the caller (map.c:344-379 reads u[0..n_u) and frees it)
-	uint64_t *u = (uint64_t*)host_kmalloc(km, (size_t)std::max(n_u, 1) * 8);
-	mm2b_anchor_t *b = (mm2b_anchor_t*)host_kmalloc(km, (size_t)n_v * 16);      // kmalloc(km, 0) == NULL, as at chain.c:397
-	if (n_u > 0) memcpy(u, t->h_u, (size_t)n_u * 8);
-	if (n_v > 0) memcpy(b, t->h_b, (size_t)n_v * 16);
-	*n_u_ = n_u, *_u = u;
+	host_kfree(km, a);
 	return b;
 }
 

@@ -4,7 +4,7 @@
  * reference CLI built into oracle/_ref/minimap2-sw resolves its two call sites
  * (map.c:316, map.c:338) to the wrapper below.  With MM2_DUMP=<path> in the environment every
  * call is appended to <path> in the format of oracle/dump_format.h; otherwise it is a pure
- * pass-through.  The f/p/v arrays come from the hook the Makefile splices in after the DP fill
+ * pass-through.  MM2_DUMP_NO_FPV=1 leaves the f/p/v arrays out (bench workloads: 12 B/anchor less).  The f/p/v arrays come from the hook the Makefile splices in after the DP fill
  * (chain.c:346).  Nothing here is on the product path.
  */
 #include <stdio.h>
@@ -31,6 +31,7 @@ void mm2_ref_hook_fpv(int64_t n, const int32_t *f, const int32_t *p, const int32
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static FILE *g_fp;
 static int g_state; /* 0 = unknown, 1 = dumping, -1 = off */
+static int g_no_fpv;
 
 static __thread int32_t *t_fpv;   /* 3*n int32 captured by the hook for the call in flight */
 static __thread int64_t t_fpv_n;
@@ -52,6 +53,8 @@ static int dumping(void)
 		pthread_mutex_lock(&g_lock);
 		if (g_state == 0) {
 			const char *fn = getenv("MM2_DUMP");
+			const char *nf = getenv("MM2_DUMP_NO_FPV");
+			g_no_fpv = nf && *nf && *nf != '0';
 			if (fn && *fn && (g_fp = fopen(fn, "wb")) != 0) g_state = 1;
 			else g_state = -1;
 		}
@@ -70,7 +73,7 @@ mm128_t *mm_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int m
 		return mm_chain_dp_ref(max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, gap_scale, is_cdna, n_segs, n, a, n_u_, _u, km, tid);
 	a_copy = (mm128_t*)malloc((size_t)n * sizeof(mm128_t));
 	memcpy(a_copy, a, (size_t)n * sizeof(mm128_t)); /* the reference frees `a` (chain.c:39,356,421) */
-	t_armed = 1, t_fpv = 0, t_fpv_n = 0;
+	t_armed = !g_no_fpv, t_fpv = 0, t_fpv_n = 0;
 	b = mm_chain_dp_ref(max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc, gap_scale, is_cdna, n_segs, n, a, n_u_, _u, km, tid);
 	t_armed = 0;
 	memset(&h, 0, sizeof(h));

@@ -22,6 +22,7 @@ typedef struct {
 	int64_t *n_v;
 	uint64_t *u;
 	mm2o_anchor_t *b;
+	mm2o_anchor_t **a_copy;     /* per read: a private malloc'd copy of its anchors, made BEFORE the clock starts (the reference consumes `a`) */
 	volatile int64_t next;
 } job_t;
 
@@ -38,12 +39,12 @@ static void *worker(void *arg)
 		int32_t n_u = 0;
 		int64_t n_v = 0;
 		if (jb->ref_fn) {
-			/* the reference consumes `a` (chain.c:421) and returns kmalloc'd b/u; km == NULL => malloc/free (kalloc.c) */
+			/* the reference consumes `a` (chain.c:421: kfree) and returns kmalloc'd b/u; km == NULL => malloc/free (kalloc.c:133-149).
+			 * The copy it consumes was made before the timed region (mm2o_replay), as the seeding stage would have left it. */
 			const mm2o_params_t *q = jb->par;
-			mm2o_anchor_t *ac = 0, *b;
+			mm2o_anchor_t *ac = jb->a_copy[r], *b;
 			uint64_t *u = 0;
 			int i;
-			if (n > 0) { ac = (mm2o_anchor_t*)malloc((size_t)n * 16); memcpy(ac, jb->a + o, (size_t)n * 16); }
 			b = jb->ref_fn(q->max_dist_x, q->max_dist_y, q->bw, q->max_skip, q->max_iter, q->min_cnt, q->min_sc, q->gap_scale,
 			               q->is_cdna, q->n_segs, n, ac, &n_u, &u, 0, w->tid);
 			for (i = 0; i < n_u; ++i) n_v += (int32_t)u[i];
@@ -80,6 +81,14 @@ double mm2o_replay(const mm2o_params_t *par, int64_t n_reads, const int64_t *off
 	jb.n_u = n_u, jb.n_v = n_v, jb.u = u, jb.b = b;
 	w = (worker_t*)calloc((size_t)n_threads, sizeof(worker_t));
 	th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+	if (ref_fn) {           /* untimed: the per-read input copies the reference will free */
+		int64_t r;
+		jb.a_copy = (mm2o_anchor_t**)calloc((size_t)(n_reads > 0 ? n_reads : 1), sizeof(mm2o_anchor_t*));
+		for (r = 0; r < n_reads; ++r) {
+			const int64_t n = off[r + 1] - off[r];
+			if (n > 0) { jb.a_copy[r] = (mm2o_anchor_t*)malloc((size_t)n * 16); memcpy(jb.a_copy[r], a + off[r], (size_t)n * 16); }
+		}
+	}
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	for (i = 0; i < n_threads; ++i) { w[i].job = &jb, w[i].tid = i; pthread_create(&th[i], 0, worker, &w[i]); }
 	for (i = 0; i < n_threads; ++i) pthread_join(th[i], 0);
@@ -91,6 +100,6 @@ double mm2o_replay(const mm2o_params_t *par, int64_t n_reads, const int64_t *off
 			st->n_anchors += w[i].st.n_anchors, st->n_chains += w[i].st.n_chains, st->n_chained += w[i].st.n_chained;
 		}
 	}
-	free(w), free(th);
+	free(w), free(th), free(jb.a_copy);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }

@@ -22,12 +22,12 @@ def test_library_exports_every_declared_symbol(pkg):
     assert os.path.exists(lib)
     L = ctypes.CDLL(lib)
     names = _declared_functions(os.path.join(ROOT, "include", "mm2chain_b200.h"))
-    assert "mm_chain_dp" in names and "mm2b_chain_batch" in names and len(names) >= 18
+    assert "mm_chain_dp" in names and "mm2b_chain_batch" in names and len(names) >= 22
     for n in names:
         assert hasattr(L, n), "C ABI symbol missing from the library: " + n
     binding = pkg("binding")
     assert sorted(binding.EXPORTS) == names, "binding.EXPORTS out of sync with the header"
-    assert binding.load().mm2b_abi_version() == 2
+    assert binding.load().mm2b_abi_version() == 3
 
 
 def test_params_struct_layout_matches_oracle(pkg, oracle):
@@ -62,3 +62,38 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"import oracle|from oracle|oracle_py|oracle/|mm2o_|liboracle|libmm2ref|chain_oracle", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def _unpack_model(lo, xr, yr):
+    """numpy model of unpack_kernel (csrc/chain_kernels.cu): every anchor takes the high words of the last run starting at or before it."""
+    import numpy as np
+    n = len(lo)
+    i = np.arange(n, dtype=np.uint32)
+    xh = xr[np.searchsorted(xr[:, 0], i, side="right") - 1, 1].astype(np.uint64)
+    yh = yr[np.searchsorted(yr[:, 0], i, side="right") - 1, 1].astype(np.uint64)
+    return (xh << np.uint64(32)) | lo[:, 0], (yh << np.uint64(32)) | lo[:, 1]
+
+
+def test_host_packer_round_trips(pkg):
+    """mm2b_pack_anchors is pure host code: 8-byte words + runs of the high words restore every anchor bit for bit."""
+    import numpy as np
+    binding = pkg("binding")
+    wl = pkg("workload")
+    rng = np.random.default_rng(3)
+    _, a = wl.synth_anchor_batch(40, seed=11)
+    cases = [a, a[:1], a[:2]]
+    wild = np.zeros(5000, binding.ANCHOR)                      # high words changing at random places, flags and segment ids in y
+    wild["x"] = (rng.integers(0, 3, 5000).astype(np.uint64) << np.uint64(32)) | rng.integers(0, 2**32, 5000).astype(np.uint64)
+    wild["x"] |= rng.integers(0, 2, 5000).astype(np.uint64) << np.uint64(63)
+    wild["y"] = (rng.integers(0, 4, 5000).astype(np.uint64) << np.uint64(48)) | (rng.integers(10, 30, 5000).astype(np.uint64) << np.uint64(32)) \
+        | rng.integers(0, 2**32, 5000).astype(np.uint64)
+    cases.append(wild)
+    for arr in cases:
+        lo, xr, yr = binding.pack_anchors(arr)
+        assert xr[0, 0] == 0 and yr[0, 0] == 0 and np.all(np.diff(xr[:, 0].astype(np.int64)) > 0) and np.all(np.diff(yr[:, 0].astype(np.int64)) > 0)
+        x, y = _unpack_model(lo, xr, yr)
+        assert np.array_equal(x, arr["x"]) and np.array_equal(y, arr["y"])
+    lo, xr, yr = binding.pack_anchors(a)
+    assert len(yr) == 1 and len(xr) < len(a) / 50              # the format's premise on real-shaped input
+    with pytest.raises(binding.Mm2bError):                    # high words too varied for the run budget: reported, not truncated
+        binding.pack_anchors(wild, cap_runs=16)
