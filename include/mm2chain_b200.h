@@ -102,18 +102,23 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
                      int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
                      uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats);
 
-/* The same call with the two PCIe diets spelled out (mm2b_chain_batch uses the defaults: packed input, b[] gathered on the host).
+/* The same call with the two PCIe diets spelled out.
  *   bi      when non-NULL receives, at the same offsets as b, the INDEX of every chained anchor inside its read
  *           (b[b_off[r]+k] == a[off[r] + bi[b_off[r]+k]]): 4 bytes instead of 16 come back over PCIe, and a caller that still
  *           holds a[] (every caller of mm_chain_dp does: map.c:316 passes it in) gathers b itself or uses the indices directly.
  *           `b` may then be NULL.  With both b and bi the library gathers b on its helper threads.
- *   flags   MM2B_F_RAW_INPUT      send anchors as 16-byte mm128_t.  Default: the helper threads pack every sub-batch into 8-byte
+ *   flags   MM2B_F_RAW_INPUT      send anchors as 16-byte mm128_t.  Default: helper threads pack sub-batches into 8-byte
  *                                 {x_lo, y_lo} words plus run-length lists of the high words (strand/rid; flags/q_span/segment) on
- *                                 their way into the pinned staging buffer and the device restores mm128_t in HBM; a sub-batch
- *                                 whose high words change too often (e.g. a homopolymer-compressed index) is sent raw by itself.
- *           MM2B_F_DEVICE_GATHER  b[] comes back from the device as 16-byte anchors instead of being gathered on the host.
- * Environment overrides of the defaults (tuning): MM2B_PACK=0|1, MM2B_GATHER=host|device, MM2B_HOST_THREADS=n. */
-enum { MM2B_F_RAW_INPUT = 1, MM2B_F_DEVICE_GATHER = 2 };
+ *                                 their way into the pinned staging buffer and the device restores mm128_t in HBM.  Packing is a
+ *                                 pass over host memory, so only as many sub-batches are packed as the helper threads keep up with
+ *                                 (MM2B_PACK_INFLIGHT at a time, default 1); the others, and any sub-batch whose high words change
+ *                                 too often (e.g. a homopolymer-compressed index), go over raw by themselves.
+ *           MM2B_F_DEVICE_GATHER  b[] comes back from the device as 16-byte anchors (the default when only b is asked for).
+ *           MM2B_F_HOST_GATHER    b[] is gathered on the host's helper threads from 4-byte indices (pays off only where host
+ *                                 memory bandwidth is plentiful compared with the PCIe link).
+ * Environment overrides of the defaults of mm2b_chain_batch (tuning): MM2B_PACK=0|1, MM2B_PACK_INFLIGHT=n, MM2B_GATHER=host|device,
+ * MM2B_HOST_THREADS=n. */
+enum { MM2B_F_RAW_INPUT = 1, MM2B_F_DEVICE_GATHER = 2, MM2B_F_HOST_GATHER = 4 };
 int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
                         int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
                         uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int32_t *bi, int64_t b_cap, unsigned flags, mm2b_stats_t *stats);

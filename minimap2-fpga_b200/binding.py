@@ -155,7 +155,7 @@ def _p(arr):
     return arr.ctypes.data_as(C.c_void_p)
 
 
-F_RAW_INPUT, F_DEVICE_GATHER = 1, 2
+F_RAW_INPUT, F_DEVICE_GATHER, F_HOST_GATHER = 1, 2, 4
 
 
 def chain_batch(par, off, a, out=None, want_stats=True, mode="default", flags=0):

@@ -121,11 +121,12 @@ static int chain_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t 
                         int32_t *d_n_u, int32_t *d_n_v, int32_t *d_status, int64_t *d_u_off, int64_t *d_b_off,
                         uint64_t *d_u, mm2b_anchor_t *d_b, int32_t *d_bi, void *stream_)
 {
-	if (!ws || !par || n_reads < 0 || n_anchors < 0 || (!d_b && !d_bi)) { set_error("%s%s", "mm2b_chain_batch_device: bad argument", ""); return MM2B_ERR_ARG; }
+	if (!ws || !par || n_reads < 0 || n_anchors < 0) { set_error("%s%s", "mm2b_chain_batch_device: bad argument", ""); return MM2B_ERR_ARG; }
 	if (n_reads > ws->max_reads || n_anchors > ws->max_anchors || n_reads >= (1ll << 31)) {
 		set_error("%s%s", "mm2b_chain_batch_device: batch exceeds workspace capacity", "");
 		return MM2B_ERR_CAPACITY;
 	}
+	if (n_anchors > 0 && !d_b && !d_bi) { set_error("%s%s", "mm2b_chain_batch_device: no output buffer for the chained anchors", ""); return MM2B_ERR_ARG; }
 	cudaStream_t stream = (cudaStream_t)stream_;
 	int prev = -1;
 	cudaGetDevice(&prev);

@@ -114,200 +114,258 @@ struct DpConst {
 //    with closed form x_t = S_t - min(0, min_{s<=t} S_s), S_t = n_skip + sum d.  S only drops at records, so the running
 //    minimum is a minimum over the record lanes: scalar work on the two vote masks, no shuffles;
 //  * the loop breaks at the first hit lane with x > max_skip; the new (max_f, max_j) is the last record before it.
+// Scores of one chunk: the 32 predecessors j = jt - lane (chain.c:199-220) and what the bookkeeping needs of them.  Nothing in
+// here depends on the state of the scan (max_f, n_skip).
+struct Chunk {
+	int n_act;              // cells of the reference loop covered by this chunk
+	int j, s;               // this lane's predecessor and its ring slot
+	int32_t sc;             // score through j, INT_MIN when the reference `continue`s (or the lane is past the window)
+	int32_t pj, tj_deep;    // p[j]; the memory stamp of j when it was fetched with the cell (deep chunks)
+	bool valid, in_ring;
+};
+
+template <int RING, bool GENERAL, bool DEEP>
+__device__ __forceinline__ void score_chunk(Chunk &k, const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo, int jt,
+                                            int32_t xi, int32_t qi, int32_t q_span, int32_t sidi)
+{
+	k.n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;
+	const bool act = lane < k.n_act;
+	k.j = jt - lane;
+	k.s = k.j & (RING - 1);
+	const int j = k.j, s = k.s;
+	int32_t xj, yj, fj, pj, sidj = sidi;
+	k.tj_deep = -1;
+	k.in_ring = !DEEP || jt - k.n_act + 1 >= ring_lo;          // warp-uniform: the whole chunk is resident in the ring
+	if (k.in_ring) {
+		const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
+		xj = q.x, yj = q.y, fj = q.z, pj = q.w;
+		if (GENERAL) {
+			sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
+			__syncwarp();
+		}
+	} else {
+		// (never the first chunk of a scan: that one is always resident.)  The cell's memory stamp is fetched together with
+		// the cell: the stamps of earlier chunks are in place by now (end of their loop body) and the ones from inside this
+		// chunk come through the one-hot OR, so a deep chunk costs one round trip to L2, not two.
+		xj = 0, yj = 0, fj = 0, pj = -1;
+		if (act) {
+			if (j >= ring_lo) {
+				const int4 q = ring.a[s];
+				xj = q.x, yj = q.y, fj = q.z, pj = q.w;
+				k.tj_deep = ring.b[s].y;
+				if (GENERAL) sidj = (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff);
+			} else {                                           // deep look-back: L1/L2
+				MM2B_CHK(j >= 0 && j < i, 0x1);
+				const ulonglong2 t = __ldg(rc.A + j);
+				xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j];
+				k.tj_deep = rc.T[j];
+				sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
+			}
+		}
+		__syncwarp();
+	}
+	k.pj = pj;
+	// inside the window 0 <= dr <= max_dist_x, so the low words give dr exactly (chain.c:199)
+	const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)xj);
+	const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)yj);                // chain.c:200
+	const int32_t diff = dr - dq;
+	const int32_t dd = diff < 0 ? -diff : diff;                              // chain.c:204
+	bool valid;
+	int32_t sc;
+	if (!GENERAL) {
+		valid = act && dr != 0 && (uint32_t)(dq - 1) < (uint32_t)c.max_dq_same && dd <= c.bw;   // chain.c:202-205
+		const int32_t md = dq < dr ? dq : dr;
+		sc = md < q_span ? md : q_span;                                       // chain.c:207-208
+		const float fdd = __int2float_rn(dd);                                 // exact: dd <= bw < 2^24 on this path
+		const int c_lin = __float2int_rz(__fmul_rn(fdd, c.avg));              // chain.c:218
+		int lg = (__float_as_int(fdd) >> 23) - 127;                           // ilog2_32(dd) read off the float exponent (chain.c:209) ...
+		lg = lg < 0 ? 0 : lg;                                                 // ... and 0 for dd == 0
+		sc = sc - (c_lin + (lg >> 1)) + fj;
+	} else {
+		const bool same = sidi == sidj;
+		valid = act && !((same && dr == 0) || dq <= 0)                        // chain.c:202
+		            && !((same && dq > c.max_dist_y) || dq > c.max_dist_x)     // chain.c:203
+		            && !(same && dd > c.bw)                                    // chain.c:205
+		            && !(c.cap_dr && same && dr > c.max_dist_y);               // chain.c:206
+		const int32_t md = dq < dr ? dq : dr;
+		sc = md > q_span ? q_span : md;
+		const int lg = dd ? 31 - __clz(dd) : 0;
+		int gap = 0;
+		if (c.is_cdna || !same) {                                             // chain.c:211-217
+			const int c_lin = f2i_x86(__fmul_rn(__int2float_rn(dd), c.avg));
+			if (!same && dr == 0) ++sc;
+			else if (dr > dq || !same) gap = c_lin < lg ? c_lin : lg;
+			else gap = c_lin + (lg >> 1);
+		} else gap = f2i_x86(__fmul_rn(__int2float_rn(dd), c.avg)) + (lg >> 1);
+		sc -= d2i_x86(__dadd_rn(__dmul_rn((double)gap, c.gap_scale), .499));  // chain.c:219
+		sc += fj;
+	}
+	k.sc = valid ? sc : INT_MIN;
+	k.valid = valid;
+	if (GENERAL) __syncwarp();                            // the cost switch above branches per lane
+}
+
+// The scan goes on to the next chunk: stamps (chain.c:233) for the cells of later chunks go to memory now.
+template <int RING, bool DEEP>
+__device__ __forceinline__ void stamp_later_chunks(const Chunk &k, const ReadCtx &rc, const Ring &ring, int i, int st, int ring_lo, int jt)
+{
+	const int32_t pj = k.pj;
+	if (k.valid && pj >= st && pj < jt - 31) {
+		MM2B_CHK(pj < k.j && pj > i - RING - 32 - 5000000, 0x2);
+		MM2B_CHK(DEEP || pj >= ring_lo, 0x4);
+		if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i;
+		else rc.T[pj] = i;
+	}
+	__syncwarp();
+}
+
+// The order-dependent part for one chunk: hits, records, the n_skip counter, the break (chain.c:226-233).  Returns whether the
+// reference's loop ends inside this chunk.  FIRST = the chunk next to anchor i: no stamp of this scan can be in memory yet, and
+// max_f / max_j / n_skip still hold their initial values (q_span, -1, 0), which the compiler folds.
+// Every case ends in its own `return` (no common tail): once inlined, "the loop ends here" is a branch, never a flag in a register.
+template <int RING, bool DEEP, bool COUNT, bool FIRST>
+__device__ __forceinline__ bool resolve_chunk(const Chunk &k, const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo, int jt,
+                                              int32_t &max_f, int32_t &max_j, int &n_skip, unsigned &n_cells)
+{
+	// hits (chain.c:229,233): cell j was stamped by an earlier-visited valid cell whose predecessor it is.  A stamp from
+	// inside this chunk is a bit in a one-hot OR over the lanes (lane of the target = jt - p[j]); memory stamps are only
+	// written when the scan moves on to another chunk (stamp_later_chunks), so the usual single-chunk scan has no
+	// store -> load round trip at all.  `hitv` still includes the record lanes; they are masked out below.
+	unsigned hot;
+	asm("shl.b32 %0, 1, %1;" : "=r"(hot) : "r"(jt - k.pj));      // PTX shl clamps: 0 for targets beyond this chunk (distance >= 32)
+	hot = __reduce_or_sync(FULL, k.valid ? hot : 0u);
+	unsigned hitv;
+	if (FIRST) hitv = __ballot_sync(FULL, k.valid) & hot;
+	else {
+		const int32_t tj = k.in_ring ? ring.b[k.s].y : k.tj_deep;
+		hitv = __ballot_sync(FULL, k.valid && (tj == i || (hot >> lane & 1u)));
+	}
+	// records (chain.c:226, strict '>'), n_skip, whether the loop breaks in this chunk, and the last record before the
+	// break = the new running max.  The largest score of the chunk (first occurrence) is the LAST record.
+	// (the branch is on a vote result, not on `top <= max_f`: ptxas must see a warp-uniform condition — convergence note below)
+	const unsigned cand = __ballot_sync(FULL, k.sc > max_f);
+#define MM2B_TALLY(broke_, brk_) if (COUNT) n_cells += (broke_) ? (brk_) + 1 : k.n_act
+	if (cand == 0) {                                      // (i) no record: the counter only goes up
+		const int x0 = n_skip;
+		n_skip += __popc(hitv);
+		if (n_skip > c.max_skip) {
+			if (COUNT) {
+				const unsigned le = lanemask_lt(lane) | (1u << lane);
+				MM2B_TALLY(true, lowest_lane(__ballot_sync(FULL, ((hitv >> lane) & 1u) && x0 + __popc(hitv & le) == c.max_skip + 1)));
+			}
+			return true;
+		}
+		MM2B_TALLY(false, 0);
+		stamp_later_chunks<RING, DEEP>(k, rc, ring, i, st, ring_lo, jt);
+		return false;
+	}
+	const int32_t top = __reduce_max_sync(FULL, k.sc);
+	// the nearest lane holding the maximum = the lane with the largest j among them: a second REDUX instead of vote + bit scan
+	const int32_t top_j = __reduce_max_sync(FULL, k.sc == top ? k.j : INT_MIN);
+	const int last = jt - top_j;
+	unsigned recmask = 1u << last;
+	const unsigned before = recmask - 1u;
+	if ((cand & before) == 0) {                           // (ii) one record: a run of hits before it and one after it
+		const unsigned h1 = hitv & before;
+		const int x1 = n_skip + __popc(h1);                                    // counter when the record is reached
+		if (x1 > c.max_skip) {                                                 // the loop ends before it reaches the record
+			if (COUNT) {
+				const unsigned le = lanemask_lt(lane) | (1u << lane);
+				int kk = c.max_skip + 1 - n_skip;
+				kk = kk < 1 ? 1 : kk;
+				MM2B_TALLY(true, lowest_lane(__ballot_sync(FULL, ((h1 >> lane) & 1u) && __popc(h1 & le) == kk)));
+			}
+			return true;
+		}
+		max_f = top, max_j = top_j;
+		const unsigned h2 = hitv & ~(before | recmask);
+		const int x2 = max(x1 - 1, 0);                                         // ... after the record
+		n_skip = x2 + __popc(h2);                                              // ... at the end of the chunk
+		if (n_skip > c.max_skip) {
+			if (COUNT) {
+				const unsigned le = lanemask_lt(lane) | (1u << lane);
+				int kk = c.max_skip + 1 - x2;
+				kk = kk < 1 ? 1 : kk;
+				MM2B_TALLY(true, lowest_lane(__ballot_sync(FULL, ((h2 >> lane) & 1u) && __popc(h2 & le) == kk)));
+			}
+			return true;
+		}
+		MM2B_TALLY(false, 0);
+		stamp_later_chunks<RING, DEEP>(k, rc, ring, i, st, ring_lo, jt);
+		return false;
+	}
+	// (iii) several records (rare)
+	for (int r = lowest_lane(cand); r != last;) {
+		recmask |= 1u << r;
+		const int32_t t = __shfl_sync(FULL, k.sc, r);
+		r = lowest_lane(__ballot_sync(FULL, k.sc > t) & (0xfffffffeu << r));
+	}
+	const unsigned hm = hitv & ~recmask;
+	bool broke = false;
+	int brk = 32;
+	unsigned take = recmask;                              // records visited before the break
+	if (hm == 0) {                                        // only decrements: saturating subtraction
+		n_skip -= __popc(recmask);
+		n_skip = n_skip > 0 ? n_skip : 0;
+	} else {
+		int corr = 0, floor_all = 0, done = 0;            // corr: min(0, min S over the records at or before this lane)
+		for (unsigned rm = recmask; rm; rm &= rm - 1) {
+			const unsigned below = (rm - 1u) & ~rm;       // lanes before this record
+			const int S_r = n_skip + __popc(hm & below) - (++done);
+			floor_all = S_r < floor_all ? S_r : floor_all;
+			if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
+		}
+		const unsigned le = lanemask_lt(lane) | (1u << lane);
+		const int x = n_skip + __popc(hm & le) - __popc(recmask & le) - corr;
+		const unsigned over = __ballot_sync(FULL, ((hm >> lane) & 1u) && x > c.max_skip);
+		if (over) broke = true, brk = lowest_lane(over), take = recmask & bits_below(brk);
+		else n_skip = n_skip + __popc(hm) - done - floor_all;
+	}
+	// records are strictly increasing and ties went to the nearest j, so the last one taken is the new running max
+	if (take) {
+		const int l2 = 31 - __clz(take);
+		max_f = __shfl_sync(FULL, k.sc, l2);
+		max_j = jt - l2;
+	}
+	MM2B_TALLY(broke, brk);
+	if (broke) return true;
+	stamp_later_chunks<RING, DEEP>(k, rc, ring, i, st, ring_lo, jt);
+	return false;
+#undef MM2B_TALLY
+}
+
 template <int RING, bool GENERAL, bool DEEP, bool COUNT>
 __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCtx &rc, const Ring &ring, int lane, int i, int st, int ring_lo,
                                                   int32_t xi, int32_t qi, int32_t q_span, int32_t sidi,
                                                   int32_t &max_f, int32_t &max_j, unsigned &n_chunks, unsigned &n_cells)
 {
-	int n_skip = 0;
-	int jt = i - 1;
-	// end of a chunk, spelled out at the end of each path so that `broke` is a branch and never a register:
-	// the cell tally (iterations of chain.c:197 the reference executes here), then the break of chain.c:230-231
-#define MM2B_CHUNK_END(broke_, brk_) { \
-		if (COUNT) n_cells += (broke_) ? (brk_) + 1 : n_act; \
-		if (broke_) break; \
-		if (valid && pj >= st && pj < jt - 31) {          /* the scan goes on: stamps for the cells of later chunks */ \
-			MM2B_CHK(pj < j && pj > i - RING - 32 - 5000000, 0x2); \
-			MM2B_CHK(DEEP || pj >= ring_lo, 0x4); \
-			if (!DEEP || pj >= ring_lo) ring.b[pj & (RING - 1)].y = i; \
-			else rc.T[pj] = i; \
-		} \
-		__syncwarp(); \
-		continue; }
-	do {                                                         // the caller only comes here with a non-empty window (st < i)
-		if (COUNT) ++n_chunks;
-		const int n_act = jt - st + 1 < 32 ? jt - st + 1 : 32;     // cells of the reference loop covered by this chunk
-		const bool act = lane < n_act;
-		const int j = jt - lane;
-		const int s = j & (RING - 1);
-		int32_t xj, yj, fj, pj, sidj = sidi, tj_deep = -1;
-		const bool in_ring = !DEEP || jt - n_act + 1 >= ring_lo;   // warp-uniform: the whole chunk is resident in the ring
-		if (in_ring) {
-			const int4 q = ring.a[s];                              // lanes past the window read a stale slot; masked by `act`
-			xj = q.x, yj = q.y, fj = q.z, pj = q.w;
-			if (GENERAL) {
-				sidj = act ? (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff) : sidi;
-				__syncwarp();
-			}
-		} else {
-			// (never the first chunk of a scan: that one is always resident.)  The cell's memory stamp is fetched together with
-			// the cell: the stamps of earlier chunks are in place by now (end of their loop body) and the ones from inside this
-			// chunk come through the one-hot OR, so a deep chunk costs one round trip to L2, not two.
-			xj = 0, yj = 0, fj = 0, pj = -1;
-			if (act) {
-				if (j >= ring_lo) {
-					const int4 q = ring.a[s];
-					xj = q.x, yj = q.y, fj = q.z, pj = q.w;
-					tj_deep = ring.b[s].y;
-					if (GENERAL) sidj = (int32_t)(__ldg(&rc.A[j].y) >> SEG_SHIFT & 0xff);
-				} else {                                           // deep look-back: L1/L2
-					MM2B_CHK(j >= 0 && j < i, 0x1);
-					const ulonglong2 t = __ldg(rc.A + j);
-					xj = (int32_t)t.x, yj = (int32_t)t.y, fj = rc.F[j], pj = rc.P[j];
-					tj_deep = rc.T[j];
-					sidj = (int32_t)(t.y >> SEG_SHIFT & 0xff);
-				}
-			}
-			__syncwarp();
-		}
-		// inside the window 0 <= dr <= max_dist_x, so the low words give dr exactly (chain.c:199)
-		const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)xj);
-		const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)yj);                // chain.c:200
-		const int32_t diff = dr - dq;
-		const int32_t dd = diff < 0 ? -diff : diff;                              // chain.c:204
-		bool valid;
-		int32_t sc;
-		if (!GENERAL) {
-			valid = act && dr != 0 && (uint32_t)(dq - 1) < (uint32_t)c.max_dq_same && dd <= c.bw;   // chain.c:202-205
-			const int32_t md = dq < dr ? dq : dr;
-			sc = md < q_span ? md : q_span;                                       // chain.c:207-208
-			const float fdd = __int2float_rn(dd);                                 // exact: dd <= bw < 2^24 on this path
-			const int c_lin = __float2int_rz(__fmul_rn(fdd, c.avg));              // chain.c:218
-			int lg = (__float_as_int(fdd) >> 23) - 127;                           // ilog2_32(dd) read off the float exponent (chain.c:209) ...
-			lg = lg < 0 ? 0 : lg;                                                 // ... and 0 for dd == 0
-			sc = sc - (c_lin + (lg >> 1)) + fj;
-		} else {
-			const bool same = sidi == sidj;
-			valid = act && !((same && dr == 0) || dq <= 0)                        // chain.c:202
-			            && !((same && dq > c.max_dist_y) || dq > c.max_dist_x)     // chain.c:203
-			            && !(same && dd > c.bw)                                    // chain.c:205
-			            && !(c.cap_dr && same && dr > c.max_dist_y);               // chain.c:206
-			const int32_t md = dq < dr ? dq : dr;
-			sc = md > q_span ? q_span : md;
-			const int lg = dd ? 31 - __clz(dd) : 0;
-			int gap = 0;
-			if (c.is_cdna || !same) {                                             // chain.c:211-217
-				const int c_lin = f2i_x86(__fmul_rn(__int2float_rn(dd), c.avg));
-				if (!same && dr == 0) ++sc;
-				else if (dr > dq || !same) gap = c_lin < lg ? c_lin : lg;
-				else gap = c_lin + (lg >> 1);
-			} else gap = f2i_x86(__fmul_rn(__int2float_rn(dd), c.avg)) + (lg >> 1);
-			sc -= d2i_x86(__dadd_rn(__dmul_rn((double)gap, c.gap_scale), .499));  // chain.c:219
-			sc += fj;
-		}
-		if (!valid) sc = INT_MIN;
-		if (GENERAL) __syncwarp();                            // the cost switch above branches per lane
-
-		// Quiet tail: n_skip grows by at most one per visited cell, so once n_skip + (cells left in the window) <= max_skip the
-		// break of chain.c:230 cannot fire any more.  Then stamps, hits and n_skip cannot change the outcome and only the running
-		// maximum matters (strict '>', nearest first = the largest j among the lanes holding the chunk's maximum).  Short
-		// windows — most of a noisy read — are quiet from their first chunk.
-		if (n_skip + (jt - st + 1) <= c.max_skip) {
-			const int32_t best = __reduce_max_sync(FULL, sc);
-			const int32_t best_j = __reduce_max_sync(FULL, sc == best ? j : INT_MIN);   // unconditional: keeps the warp converged by construction
+	int jt = i - 1;                                          // the caller only comes here with a non-empty window (st < i)
+	Chunk k;
+	// Quiet scan: n_skip grows by at most one per visited cell, so a window of at most max_skip cells cannot trigger the break of
+	// chain.c:230.  Then stamps, hits and n_skip cannot change the outcome and only the running maximum matters (strict '>',
+	// nearest first = the largest j among the lanes holding a chunk's maximum).  Short windows are a large part of a noisy read.
+	if (i - st <= c.max_skip) {
+#pragma unroll 1
+		do {
+			if (COUNT) ++n_chunks;
+			score_chunk<RING, GENERAL, DEEP>(k, c, rc, ring, lane, i, st, ring_lo, jt, xi, qi, q_span, sidi);
+			const int32_t best = __reduce_max_sync(FULL, k.sc);
+			const int32_t best_j = __reduce_max_sync(FULL, k.sc == best ? k.j : INT_MIN);   // unconditional: keeps the warp converged by construction
 			if (best > max_f) max_f = best, max_j = best_j;
-			if (COUNT) n_cells += n_act;
-			continue;
-		}
-
-		// hits (chain.c:229,233): cell j was stamped by an earlier-visited valid cell whose predecessor it is.  A stamp from
-		// inside this chunk is a bit in a one-hot OR over the lanes (lane of the target = jt - p[j]); memory stamps are only
-		// written when the scan moves on to another chunk (end of the loop body), so the usual single-chunk scan has no
-		// store -> load round trip at all.  `hitv` still includes the record lanes; they are masked out below.
-		unsigned hot;
-		asm("shl.b32 %0, 1, %1;" : "=r"(hot) : "r"(jt - pj));       // PTX shl clamps: 0 for targets beyond this chunk (distance >= 32)
-		hot = __reduce_or_sync(FULL, valid ? hot : 0u);
-		unsigned hitv;
-		if (jt == i - 1) hitv = __ballot_sync(FULL, valid) & hot;
-		else {
-			const int32_t tj = in_ring ? ring.b[s].y : tj_deep;
-			hitv = __ballot_sync(FULL, valid && (tj == i || (hot >> lane & 1u)));
-		}
-		// records (chain.c:226, strict '>'), n_skip, whether the loop breaks in this chunk, and the last record before the
-		// break = the new running max.  Three cases, the first two branch-free:
-		const unsigned cand = __ballot_sync(FULL, sc > max_f);
-		int brk = 32;                                         // break lane; only tracked exactly when it is needed (cell tally)
-		if (cand == 0) {                                      // (i) no record: the counter only goes up
-			const int x0 = n_skip;
-			n_skip += __popc(hitv);
-			const bool broke = n_skip > c.max_skip;
-			if (COUNT && broke) {
-				const unsigned le = lanemask_lt(lane) | (1u << lane);
-				brk = lowest_lane(__ballot_sync(FULL, ((hitv >> lane) & 1u) && x0 + __popc(hitv & le) == c.max_skip + 1));
-			}
-			MM2B_CHUNK_END(broke, brk);
-		}
-		// The largest score of the chunk (first occurrence) is the LAST record; usually it is also the first lane above
-		// max_f, i.e. the only one.  Otherwise (`multi`) walk from the first candidate up to it.
-		const int32_t top = __reduce_max_sync(FULL, sc);
-		// the nearest lane holding the maximum = the lane with the largest j among them: a second REDUX instead of vote + bit scan
-		const int32_t top_j = __reduce_max_sync(FULL, sc == top ? j : INT_MIN);
-		const int last = jt - top_j;
-		unsigned recmask = 1u << last;
-		const unsigned hitmask = hitv & ~recmask;
-		if ((cand & (recmask - 1u)) == 0) {                   // (ii) one record: a run of hits before it and one after it
-			const unsigned h1 = hitmask & (recmask - 1u), h2 = hitmask & ~(recmask - 1u);
-			const int x1 = n_skip + __popc(h1);                                // counter when the record is reached
-			const int x2 = x1 > 0 ? x1 - 1 : 0;                                // ... after it
-			const int x3 = x2 + __popc(h2);                                    // ... at the end of the chunk
-			const bool early = x1 > c.max_skip;                                // the loop ends before it reaches the record
-			const bool broke = early || x3 > c.max_skip;
-			if (!early) max_f = top, max_j = top_j;
-			if (COUNT && broke) {                             // the exact lane only matters for the cell tally
-				const unsigned run = early ? h1 : h2;         // the run of hits in which the counter first exceeds max_skip ...
-				int k = c.max_skip + 1 - (early ? n_skip : x2);                // ... at its k-th hit
-				k = k < 1 ? 1 : k;
-				const unsigned le = lanemask_lt(lane) | (1u << lane);
-				brk = lowest_lane(__ballot_sync(FULL, ((run >> lane) & 1u) && __popc(run & le) == k));
-			}
-			n_skip = x3;
-			MM2B_CHUNK_END(broke, brk);
-		} else {                                              // (iii) several records (rare)
-			for (int r = lowest_lane(cand); r != last;) {
-				recmask |= 1u << r;
-				const int32_t t = __shfl_sync(FULL, sc, r);
-				r = lowest_lane(__ballot_sync(FULL, sc > t) & (0xfffffffeu << r));
-			}
-			const unsigned hm = hitv & ~recmask;
-			bool broke = false;
-			unsigned take = recmask;                          // records visited before the break
-			if (hm == 0) {                               // only decrements: saturating subtraction
-				n_skip -= __popc(recmask);
-				n_skip = n_skip > 0 ? n_skip : 0;
-			} else {
-				int corr = 0, floor_all = 0, done = 0;        // corr: min(0, min S over the records at or before this lane)
-				for (unsigned rm = recmask; rm; rm &= rm - 1) {
-					const unsigned below = (rm - 1u) & ~rm;   // lanes before this record
-					const int S_r = n_skip + __popc(hm & below) - (++done);
-					floor_all = S_r < floor_all ? S_r : floor_all;
-					if ((below >> lane & 1u) == 0 && S_r < corr) corr = S_r;
-				}
-				const unsigned le = lanemask_lt(lane) | (1u << lane);
-				const int x = n_skip + __popc(hm & le) - __popc(recmask & le) - corr;
-				const unsigned over = __ballot_sync(FULL, ((hm >> lane) & 1u) && x > c.max_skip);
-				if (over) broke = true, brk = lowest_lane(over), take = recmask & bits_below(brk);
-				else n_skip = n_skip + __popc(hm) - done - floor_all;
-			}
-			// records are strictly increasing and ties went to the nearest j, so the last one taken is the new running max
-			if (take) {
-				const int l2 = 31 - __clz(take);
-				max_f = __shfl_sync(FULL, sc, l2);
-				max_j = jt - l2;
-			}
-			MM2B_CHUNK_END(broke, brk);
-		}
-	} while ((jt -= 32) >= st);
-#undef MM2B_CHUNK_END
+			if (COUNT) n_cells += k.n_act;
+		} while ((jt -= 32) >= st);
+		return;
+	}
+	int n_skip = 0;
+	if (COUNT) ++n_chunks;
+	score_chunk<RING, GENERAL, false>(k, c, rc, ring, lane, i, st, ring_lo, jt, xi, qi, q_span, sidi);      // the nearest chunk is always resident
+	if (resolve_chunk<RING, DEEP, COUNT, true>(k, c, rc, ring, lane, i, st, ring_lo, jt, max_f, max_j, n_skip, n_cells)) return;
+#pragma unroll 1
+	while ((jt -= 32) >= st) {
+		if (COUNT) ++n_chunks;
+		score_chunk<RING, GENERAL, DEEP>(k, c, rc, ring, lane, i, st, ring_lo, jt, xi, qi, q_span, sidi);
+		if (resolve_chunk<RING, DEEP, COUNT, false>(k, c, rc, ring, lane, i, st, ring_lo, jt, max_f, max_j, n_skip, n_cells)) return;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -502,7 +560,7 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 		// f[i], p[i] (chain.c:236): one lane publishes them to the anchor's slot; untouched if no predecessor won.
 		// v[i] is not needed by the scan at all; it is filled in per block afterwards (dp_fill).
 		MM2B_CHK(max_j < i && max_j >= -1 && (max_j < 0 || max_j >= st) && (DEEP || max_j < 0 || max_j >= ring_lo), 0x8);
-		if (lane == 0 && max_j >= 0) *(int2*)&slot->z = make_int2(max_f, max_j);
+		if (lane == 0) *(int2*)&slot->z = make_int2(max_f, max_j);      // (when nothing won these are the defaults the slot already holds)
 		__syncwarp();
 	} while (todo);
 }

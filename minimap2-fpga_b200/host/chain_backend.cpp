@@ -33,6 +33,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "mm2chain_b200.h"
 #include "../csrc/shim_internal.h"
@@ -263,7 +266,13 @@ struct Backend {
 	int64_t pack_chunk = 128 << 10;     // anchors per helper task
 	bool want_stats = true;
 	bool trace = false;
-	bool default_pack = true, default_device_gather = false;
+	bool default_pack = true, default_device_gather = true;
+	// Packing is a pass over host memory, and on the hosts measured it runs at about the speed of the PCIe link itself: packing every
+	// sub-batch just moves the bottleneck from the link to the host's memory system.  So at most `pack_inflight` sub-batches are
+	// being packed at any time; a sub-batch that finds the helper threads busy goes over raw (16 B/anchor) right away, and link
+	// and host memory work side by side.  0 = never pack, large = always pack.
+	int pack_inflight = 1;
+	std::atomic<int> packing_now{0};
 	std::atomic<int> count_cells{0};
 	Pool pool;
 	cudaEvent_t trace_ev0[64] = {};
@@ -282,25 +291,74 @@ void CUDART_CB slot_signal_outputs(void *p) { Slot *s = (Slot*)p; s->sig.store(2
 // One chunk [i0, i1) of a sub-batch: low words to lo[], and a run of {first index, high word} whenever a high word differs
 // from the previous anchor's (every chunk opens its own runs, so chunks are independent).  Returns false when the runs do not
 // fit `cap` entries — then the anchors' high words are too varied for this format and the sub-batch goes over as it is.
+struct PackState { uint32_t px, py; int nx, ny; };
+
+// anchors [i, e) one at a time; false when the run lists are full
+inline bool pack_scalar(const mm2b_anchor_t *a, int64_t i, int64_t e, uint2 *lo, uint2 *xr, uint2 *yr, int cap, PackState &st)
+{
+	for (; i < e; ++i) {
+		const uint64_t x = a[i].x, y = a[i].y;
+		lo[i] = make_uint2((uint32_t)x, (uint32_t)y);
+		const uint32_t xh = (uint32_t)(x >> 32), yh = (uint32_t)(y >> 32);
+		if (xh != st.px) {
+			if (st.nx == cap) return false;
+			xr[st.nx++] = make_uint2((uint32_t)i, xh), st.px = xh;
+		}
+		if (yh != st.py) {
+			if (st.ny == cap) return false;
+			yr[st.ny++] = make_uint2((uint32_t)i, yh), st.py = yh;
+		}
+	}
+	return true;
+}
+
+#if defined(__x86_64__)
+// Four anchors per step: the low words leave with one non-temporal 32-byte store (the packed buffer is written once and read
+// by the copy engine, so it should not displace the source in the cache nor be read for ownership), the high words are compared
+// with their predecessors' in one go and only a change drops to the scalar code.  The pass is bound by host memory bandwidth.
+__attribute__((target("avx2"))) bool pack_avx2(const mm2b_anchor_t *a, int64_t i, int64_t e, uint2 *lo, uint2 *xr, uint2 *yr, int cap, PackState &st)
+{
+	while (i < e && ((uintptr_t)(lo + i) & 31)) {                  // up to the first 32-byte boundary of the output
+		if (!pack_scalar(a, i, i + 1, lo, xr, yr, cap, st)) return false;
+		++i;
+	}
+	const __m256i pick_lo = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6), pick_hi = _mm256_setr_epi32(1, 3, 5, 7, 1, 3, 5, 7);
+	for (; i + 4 <= e; i += 4) {
+		const __m256i v0 = _mm256_loadu_si256((const __m256i*)(a + i)), v1 = _mm256_loadu_si256((const __m256i*)(a + i + 2));
+		const __m256i l0 = _mm256_permutevar8x32_epi32(v0, pick_lo), l1 = _mm256_permutevar8x32_epi32(v1, pick_lo);
+		_mm256_stream_si256((__m256i*)(lo + i), _mm256_permute2x128_si256(l0, l1, 0x20));
+		const __m256i h0 = _mm256_permutevar8x32_epi32(v0, pick_hi), h1 = _mm256_permutevar8x32_epi32(v1, pick_hi);
+		const __m256i hi = _mm256_permute2x128_si256(h0, h1, 0x20);       // xh0 yh0 xh1 yh1 xh2 yh2 xh3 yh3
+		const __m256i first = _mm256_setr_epi32((int)st.px, (int)st.py, 0, 0, 0, 0, 0, 0);
+		// the predecessors' high words: hi shifted up by one anchor, the state's words in front
+		const __m256i prev = _mm256_blend_epi32(_mm256_permutevar8x32_epi32(hi, _mm256_setr_epi32(0, 1, 0, 1, 2, 3, 4, 5)), first, 0x03);
+		if (_mm256_movemask_epi8(_mm256_cmpeq_epi32(hi, prev)) != -1) {   // some high word changes inside these four
+			PackState t = st;
+			// (the low words are already stored; the scalar pass stores them again, which is harmless)
+			if (!pack_scalar(a, i, i + 4, lo, xr, yr, cap, t)) return false;
+			st = t;
+		}
+	}
+	_mm_sfence();
+	return pack_scalar(a, i, e, lo, xr, yr, cap, st);
+}
+#endif
+
 bool pack_chunk(const mm2b_anchor_t *a, int64_t i0, int64_t i1, uint2 *lo, uint2 *xr, int &nx, uint2 *yr, int &ny, int cap)
 {
 	nx = ny = 0;
 	if (i0 >= i1) return true;
-	uint32_t px = ~(uint32_t)(a[i0].x >> 32), py = ~(uint32_t)(a[i0].y >> 32);
-	for (int64_t i = i0; i < i1; ++i) {
-		const uint64_t x = a[i].x, y = a[i].y;
-		lo[i] = make_uint2((uint32_t)x, (uint32_t)y);
-		const uint32_t xh = (uint32_t)(x >> 32), yh = (uint32_t)(y >> 32);
-		if (xh != px) {
-			if (nx == cap) return false;
-			xr[nx++] = make_uint2((uint32_t)i, xh), px = xh;
-		}
-		if (yh != py) {
-			if (ny == cap) return false;
-			yr[ny++] = make_uint2((uint32_t)i, yh), py = yh;
-		}
-	}
-	return true;
+	PackState st;
+	st.px = ~(uint32_t)(a[i0].x >> 32), st.py = ~(uint32_t)(a[i0].y >> 32), st.nx = st.ny = 0;
+	bool ok;
+#if defined(__x86_64__)
+	static const bool have_avx2 = __builtin_cpu_supports("avx2");
+	if (have_avx2) ok = pack_avx2(a, i0, i1, lo, xr, yr, cap, st);
+	else
+#endif
+	ok = pack_scalar(a, i0, i1, lo, xr, yr, cap, st);
+	nx = st.nx, ny = st.ny;
+	return ok;
 }
 
 int n_chunks_of(int64_t na) { return (int)std::max<int64_t>(1, (na + g.pack_chunk - 1) / g.pack_chunk); }
@@ -315,6 +373,7 @@ void start_pack(Slot &s, Job *job, int si)
 	s.pack_overflow.store(0);
 	s.host_left.store(nc);
 	s.t_host0 = now_ms();
+	g.packing_now.fetch_add(1);
 	const mm2b_anchor_t *src = job->a + a0;
 	for (int c = 0; c < nc; ++c) {
 		g.pool.submit([&s, src, na, nc, cap, c] {
@@ -330,6 +389,7 @@ void start_pack(Slot &s, Job *job, int si)
 // close the gaps between the chunks' run lists (a few thousand entries); returns false if the sub-batch must go over raw
 bool finish_pack(Slot &s, int64_t na)
 {
+	g.packing_now.fetch_sub(1);
 	if (s.pack_overflow.load()) return false;
 	const int nc = (int)s.n_xr.size();
 	const int cap = (int)(s.cap_runs / nc);
@@ -572,7 +632,7 @@ void device_worker(Device *d)
 				++pick->in_flight, ++in_flight;
 				progressed = true;
 				if (!s.ensure(na, sb.r1 - sb.r0)) { s.stage = 2; fail_slot(s); continue; }
-				if (job->pack && na > 0 && na < (1ll << 31)) {
+				if (job->pack && na > 0 && na < (1ll << 31) && g.packing_now.load() < g.pack_inflight) {
 					s.stage = 1;
 					start_pack(s, job, si);
 				} else {
@@ -839,7 +899,8 @@ int mm2b_init(int n_devices, const int *devices)
 	if (const char *s = getenv("MM2B_SUB_ANCHORS")) { const long long v = atoll(s); if (v > 0) g.sub_anchors = v; }
 	if (const char *s = getenv("MM2B_PACK_CHUNK")) { const long long v = atoll(s); if (v > 0) g.pack_chunk = v; }
 	if (const char *s = getenv("MM2B_PACK")) g.default_pack = atoi(s) != 0;
-	if (const char *s = getenv("MM2B_GATHER")) g.default_device_gather = strcmp(s, "device") == 0;
+	if (const char *s = getenv("MM2B_PACK_INFLIGHT")) g.pack_inflight = atoi(s);
+	if (const char *s = getenv("MM2B_GATHER")) g.default_device_gather = strcmp(s, "host") != 0;
 	int n_helpers = (int)std::thread::hardware_concurrency() - 2;
 	n_helpers = std::max(2, std::min(n_helpers, 16));
 	if (const char *s = getenv("MM2B_HOST_THREADS")) { const int v = atoi(s); if (v > 0) n_helpers = std::min(v, 256); }
@@ -957,7 +1018,7 @@ int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t
 	job.par = par, job.n_reads = n_reads, job.off = off, job.a = a;
 	job.n_u = n_u, job.n_v = n_v, job.status = status, job.u_off = u_off, job.b_off = b_off, job.u = u, job.b = b, job.bi = bi;
 	job.pack = !(flags & MM2B_F_RAW_INPUT);
-	job.device_gather = b && !bi && (flags & MM2B_F_DEVICE_GATHER);
+	job.device_gather = b && !bi && ((flags & MM2B_F_DEVICE_GATHER) || !(flags & MM2B_F_HOST_GATHER));
 	// Cut into sub-batches of <= sub_anchors anchors (a larger single read stands alone).  The first and last few are smaller:
 	// the first copy and the last kernel + copy-back are the only stages nothing overlaps with, so they should be short.
 	for (int64_t r0 = 0; r0 < n_reads;) {
@@ -1003,7 +1064,7 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
                      int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
                      uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats)
 {
-	const unsigned flags = (g.default_pack ? 0u : (unsigned)MM2B_F_RAW_INPUT) | (g.default_device_gather ? (unsigned)MM2B_F_DEVICE_GATHER : 0u);
+	const unsigned flags = (g.default_pack ? 0u : (unsigned)MM2B_F_RAW_INPUT) | (g.default_device_gather ? (unsigned)MM2B_F_DEVICE_GATHER : (unsigned)MM2B_F_HOST_GATHER);
 	if (!b && n_reads > 0 && off && off[n_reads] > 0) { set_error("%s%s", "mm2b_chain_batch: NULL buffer", ""); return MM2B_ERR_ARG; }
 	return mm2b_chain_batch_ex(par, n_reads, off, a, n_u, n_v, status, u_off, b_off, u, u_cap, b, nullptr, b_cap, flags, stats);
 }

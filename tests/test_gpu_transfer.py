@@ -22,11 +22,13 @@ def binding(pkg):
     import os
     os.environ["MM2B_SUB_ANCHORS"] = "150000"       # several sub-batches per call, several packing chunks per sub-batch
     os.environ["MM2B_PACK_CHUNK"] = "20000"
+    os.environ["MM2B_PACK_INFLIGHT"] = "99"         # pack every sub-batch (the default packs only what the helper threads keep up with)
     b.init(1)
     yield b
     b.shutdown()
     os.environ.pop("MM2B_SUB_ANCHORS", None)
     os.environ.pop("MM2B_PACK_CHUNK", None)
+    os.environ.pop("MM2B_PACK_INFLIGHT", None)
 
 
 def _per_read(res, off, key):
@@ -73,11 +75,11 @@ def test_all_transfer_variants_agree_with_the_oracle(binding, oracle, pkg, seed)
     assert len(a) > 3 * 150000
     par = binding.Params()
     ref = oracle.replay(oracle.Params(), off, a, n_threads=8)
-    res = binding.chain_batch(par, off, a)                                   # defaults: packed in, indices out, host gather
+    res = binding.chain_batch(par, off, a, mode="b", flags=binding.F_HOST_GATHER)     # packed in, indices out, b[] gathered on the host
     _check_against(res, ref, off)
     assert res["stats"].n_packed_subs >= 3 and res["stats"].n_raw_subs == 0
     assert res["stats"].h2d_bytes < 9 * len(a) + 64 * len(off) and res["stats"].d2h_bytes < 4 * int(ref["n_v"].sum()) + 8 * int(ref["n_u"].sum()) + 64 * len(off)
-    for mode, flags in (("b", binding.F_RAW_INPUT), ("b", binding.F_DEVICE_GATHER), ("b", binding.F_RAW_INPUT | binding.F_DEVICE_GATHER), ("both", 0)):
+    for mode, flags in (("b", binding.F_RAW_INPUT), ("b", binding.F_HOST_GATHER), ("b", binding.F_RAW_INPUT | binding.F_HOST_GATHER), ("both", 0)):
         r2 = binding.chain_batch(par, off, a, mode=mode, flags=flags)
         _check_against(r2, ref, off)
         if flags & binding.F_RAW_INPUT:
@@ -90,6 +92,30 @@ def test_all_transfer_variants_agree_with_the_oracle(binding, oracle, pkg, seed)
     for r in range(len(off) - 1):                                            # indices and anchors describe the same chains
         bo, nv = int(rb["b_off"][r]), int(rb["n_v"][r])
         assert np.array_equal(a[int(off[r]) + rb["bi"][bo:bo + nv]], rb["b"][bo:bo + nv])
+
+
+def test_default_mixes_packed_and_raw_subbatches(binding, pkg, oracle):
+    """The library's default: at most MM2B_PACK_INFLIGHT sub-batches are being packed at a time, the others go over raw."""
+    import os
+    b = binding
+    b.shutdown()
+    saved = {k: os.environ.pop(k, None) for k in ("MM2B_PACK_INFLIGHT", "MM2B_PACK_CHUNK")}
+    os.environ["MM2B_SUB_ANCHORS"] = "60000"
+    try:
+        b.init(1)
+        off, a = pkg("workload").synth_anchor_batch(1200, seed=9)
+        ref = oracle.replay(oracle.Params(), off, a, n_threads=8)
+        res = b.chain_batch(b.Params(), off, a)
+        _check_against(res, ref, off)
+        st = res["stats"]
+        assert st.n_packed_subs + st.n_raw_subs >= 10 and st.n_packed_subs >= 1
+    finally:
+        b.shutdown()
+        for k, v in saved.items():
+            if v is not None:
+                os.environ[k] = v
+        os.environ["MM2B_SUB_ANCHORS"] = "150000"
+        b.init(1)
 
 
 def test_high_words_too_varied_fall_back_to_raw_per_subbatch(binding, oracle):
