@@ -163,6 +163,10 @@ int mm2b_unpack_anchors_device(int device, int64_t n_anchors, const void *d_lo, 
 int mm2b_pack_anchors(const mm2b_anchor_t *a, int64_t n, void *lo, void *xruns, int32_t *n_xruns, void *yruns, int32_t *n_yruns,
                       int32_t cap_runs);
 
+/* Host memory bandwidth as n_threads concurrent memcpy's see it (GB/s, bytes read + bytes written): the ceiling of any host-side
+ * pass over the anchors (packing, gathering), reported by bench.py next to the PCIe copy rates. */
+double mm2b_measure_host_copy(int n_threads, size_t bytes_per_thread);
+
 /* Counters of the last batch run on this workspace (synchronises the given stream). */
 int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream, mm2b_stats_t *stats);
 /* Device time of the dominant kernel (the warp-per-read chaining kernel) in the last batch run on this workspace, in ms,

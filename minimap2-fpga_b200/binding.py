@@ -20,7 +20,7 @@ READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version", "mm2b_ws_set_longest_read",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
-           "mm2b_chain_batch_device", "mm2b_chain_batch_device_idx", "mm2b_chain_batch_ex", "mm2b_unpack_anchors_device", "mm2b_pack_anchors", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
+           "mm2b_chain_batch_device", "mm2b_chain_batch_device_idx", "mm2b_chain_batch_ex", "mm2b_unpack_anchors_device", "mm2b_pack_anchors", "mm2b_measure_host_copy", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
            "mm_chain_dp"]
 
 
@@ -83,6 +83,7 @@ def load():
     L.mm2b_chain_batch_device_idx.argtypes = [vp, C.POINTER(Params), i64, i64] + [vp] * 9 + [vp]
     L.mm2b_unpack_anchors_device.restype = i32
     L.mm2b_unpack_anchors_device.argtypes = [i32, i64, vp, vp, i32, vp, i32, vp, vp]
+    L.mm2b_measure_host_copy.restype, L.mm2b_measure_host_copy.argtypes = C.c_double, [i32, C.c_size_t]
     L.mm2b_pack_anchors.restype = i32
     L.mm2b_pack_anchors.argtypes = [vp, i64, vp, vp, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32), i32]
     L.mm2b_ws_create.restype, L.mm2b_ws_create.argtypes = vp, [i32, i64, i64]

@@ -144,7 +144,7 @@ struct Slot {
 	std::atomic<int> pack_overflow{0};  // some chunk had more runs than fit: this sub-batch goes over raw
 	std::vector<int> n_xr, n_yr;        // runs found per chunk
 	int n_xruns = 0, n_yruns = 0;
-	bool packed = false;
+	bool packed = false, ring_copied = false;   // ring_copied: the helper threads have already enqueued the copies of the packed words
 	double t_host0 = 0;
 
 	bool create(int dev, Device *own)
@@ -263,7 +263,7 @@ struct Backend {
 	std::mutex mu;              // guards init/shutdown
 	bool up = false;
 	int64_t sub_anchors = 2 << 20;
-	int64_t pack_chunk = 128 << 10;     // anchors per helper task
+	int64_t pack_chunk = 64 << 10;      // anchors per helper task (= per staging piece: 512 KB packed)
 	bool want_stats = true;
 	bool trace = false;
 	bool default_pack = true, default_device_gather = true;
@@ -273,6 +273,11 @@ struct Backend {
 	// and host memory work side by side.  0 = never pack, large = always pack.
 	int pack_inflight = 1;
 	std::atomic<int> packing_now{0};
+	// Cache-resident staging: every helper thread packs its chunk into a small pinned piece of its own (two per thread, taking
+	// turns) and enqueues that piece's H2D copy itself, so the copy engine reads the packed words out of the CPU's cache: they
+	// are never written to nor read from host DRAM, which is what the packing pass is bound by.  0 = one big staging buffer
+	// per sub-batch, written with non-temporal stores and copied in one piece.
+	bool pack_ring = true;
 	std::atomic<int> count_cells{0};
 	Pool pool;
 	cudaEvent_t trace_ev0[64] = {};
@@ -316,6 +321,7 @@ inline bool pack_scalar(const mm2b_anchor_t *a, int64_t i, int64_t e, uint2 *lo,
 // Four anchors per step: the low words leave with one non-temporal 32-byte store (the packed buffer is written once and read
 // by the copy engine, so it should not displace the source in the cache nor be read for ownership), the high words are compared
 // with their predecessors' in one go and only a change drops to the scalar code.  The pass is bound by host memory bandwidth.
+template <bool NT>
 __attribute__((target("avx2"))) bool pack_avx2(const mm2b_anchor_t *a, int64_t i, int64_t e, uint2 *lo, uint2 *xr, uint2 *yr, int cap, PackState &st)
 {
 	while (i < e && ((uintptr_t)(lo + i) & 31)) {                  // up to the first 32-byte boundary of the output
@@ -326,7 +332,8 @@ __attribute__((target("avx2"))) bool pack_avx2(const mm2b_anchor_t *a, int64_t i
 	for (; i + 4 <= e; i += 4) {
 		const __m256i v0 = _mm256_loadu_si256((const __m256i*)(a + i)), v1 = _mm256_loadu_si256((const __m256i*)(a + i + 2));
 		const __m256i l0 = _mm256_permutevar8x32_epi32(v0, pick_lo), l1 = _mm256_permutevar8x32_epi32(v1, pick_lo);
-		_mm256_stream_si256((__m256i*)(lo + i), _mm256_permute2x128_si256(l0, l1, 0x20));
+		if (NT) _mm256_stream_si256((__m256i*)(lo + i), _mm256_permute2x128_si256(l0, l1, 0x20));
+		else _mm256_store_si256((__m256i*)(lo + i), _mm256_permute2x128_si256(l0, l1, 0x20));
 		const __m256i h0 = _mm256_permutevar8x32_epi32(v0, pick_hi), h1 = _mm256_permutevar8x32_epi32(v1, pick_hi);
 		const __m256i hi = _mm256_permute2x128_si256(h0, h1, 0x20);       // xh0 yh0 xh1 yh1 xh2 yh2 xh3 yh3
 		const __m256i first = _mm256_setr_epi32((int)st.px, (int)st.py, 0, 0, 0, 0, 0, 0);
@@ -339,12 +346,14 @@ __attribute__((target("avx2"))) bool pack_avx2(const mm2b_anchor_t *a, int64_t i
 			st = t;
 		}
 	}
-	_mm_sfence();
+	if (NT) _mm_sfence();
 	return pack_scalar(a, i, e, lo, xr, yr, cap, st);
 }
 #endif
 
-bool pack_chunk(const mm2b_anchor_t *a, int64_t i0, int64_t i1, uint2 *lo, uint2 *xr, int &nx, uint2 *yr, int &ny, int cap)
+// nt: the packed words leave with non-temporal stores (a big staging buffer that only the copy engine reads) or with ordinary
+// ones (a small staging piece that should still be in the cache when the copy engine comes for it)
+bool pack_chunk(const mm2b_anchor_t *a, int64_t i0, int64_t i1, uint2 *lo, uint2 *xr, int &nx, uint2 *yr, int &ny, int cap, bool nt = true)
 {
 	nx = ny = 0;
 	if (i0 >= i1) return true;
@@ -353,7 +362,7 @@ bool pack_chunk(const mm2b_anchor_t *a, int64_t i0, int64_t i1, uint2 *lo, uint2
 	bool ok;
 #if defined(__x86_64__)
 	static const bool have_avx2 = __builtin_cpu_supports("avx2");
-	if (have_avx2) ok = pack_avx2(a, i0, i1, lo, xr, yr, cap, st);
+	if (have_avx2) ok = nt ? pack_avx2<true>(a, i0, i1, lo, xr, yr, cap, st) : pack_avx2<false>(a, i0, i1, lo, xr, yr, cap, st);
 	else
 #endif
 	ok = pack_scalar(a, i0, i1, lo, xr, yr, cap, st);
@@ -362,6 +371,22 @@ bool pack_chunk(const mm2b_anchor_t *a, int64_t i0, int64_t i1, uint2 *lo, uint2
 }
 
 int n_chunks_of(int64_t na) { return (int)std::max<int64_t>(1, (na + g.pack_chunk - 1) / g.pack_chunk); }
+
+// the staging pieces of one helper thread (cache-resident staging)
+struct Pieces {
+	uint2 *buf[2] = {nullptr, nullptr};
+	int64_t cap = 0;
+	cudaEvent_t ev[2][64] = {};             // per piece and device: recorded behind the piece's last copy
+	int busy_dev[2] = {-1, -1};
+	int next = 0;
+	~Pieces()
+	{
+		for (int k = 0; k < 2; ++k) {
+			cudaFreeHost(buf[k]);
+			for (auto &e : ev[k]) if (e) cudaEventDestroy(e);
+		}
+	}
+};
 
 void start_pack(Slot &s, Job *job, int si)
 {
@@ -375,12 +400,37 @@ void start_pack(Slot &s, Job *job, int si)
 	s.t_host0 = now_ms();
 	g.packing_now.fetch_add(1);
 	const mm2b_anchor_t *src = job->a + a0;
+	const bool ring = g.pack_ring && s.device < 64;
+	s.ring_copied = ring;
 	for (int c = 0; c < nc; ++c) {
-		g.pool.submit([&s, src, na, nc, cap, c] {
+		g.pool.submit([&s, src, na, nc, cap, c, ring] {
 			const int64_t i0 = na * c / nc, i1 = na * (c + 1) / nc;
-			if (!s.pack_overflow.load(std::memory_order_relaxed) &&
-			    !pack_chunk(src, i0, i1, s.h_lo, s.h_xruns + (int64_t)c * cap, s.n_xr[c], s.h_yruns + (int64_t)c * cap, s.n_yr[c], cap))
-				s.pack_overflow.store(1);
+			if (!ring) {
+				if (!s.pack_overflow.load(std::memory_order_relaxed) &&
+				    !pack_chunk(src, i0, i1, s.h_lo, s.h_xruns + (int64_t)c * cap, s.n_xr[c], s.h_yruns + (int64_t)c * cap, s.n_yr[c], cap))
+					s.pack_overflow.store(1);
+			} else if (!s.pack_overflow.load(std::memory_order_relaxed)) {
+				static thread_local Pieces pc;
+				const int64_t n = i1 - i0;
+				if (n > pc.cap) {
+					for (int k = 0; k < 2; ++k) {
+						if (pc.busy_dev[k] >= 0) cudaEventSynchronize(pc.ev[k][pc.busy_dev[k]]), pc.busy_dev[k] = -1;
+						cudaFreeHost(pc.buf[k]), pc.buf[k] = nullptr;
+					}
+					pc.cap = std::max<int64_t>(n, g.pack_chunk + 64);
+					if (!cuda_ok(hmalloc(&pc.buf[0], pc.cap * 8, cudaHostAllocPortable), "cudaHostAlloc") || !cuda_ok(hmalloc(&pc.buf[1], pc.cap * 8, cudaHostAllocPortable), "cudaHostAlloc"))
+						s.pack_overflow.store(2);
+				}
+				const int k = pc.next ^= 1;
+				if (pc.buf[k] && pc.busy_dev[k] >= 0) cudaEventSynchronize(pc.ev[k][pc.busy_dev[k]]), pc.busy_dev[k] = -1;     // its previous copy has left
+				if (pc.buf[k] && pack_chunk(src, i0, i1, pc.buf[k] - i0, s.h_xruns + (int64_t)c * cap, s.n_xr[c], s.h_yruns + (int64_t)c * cap, s.n_yr[c], cap, false)) {
+					cudaSetDevice(s.device);
+					if (!pc.ev[k][s.device]) cudaEventCreateWithFlags(&pc.ev[k][s.device], cudaEventDisableTiming);
+					if (cudaMemcpyAsync(s.d_lo + i0, pc.buf[k], (size_t)n * 8, cudaMemcpyHostToDevice, s.stream) != cudaSuccess ||
+					    cudaEventRecord(pc.ev[k][s.device], s.stream) != cudaSuccess) s.pack_overflow.store(2);
+					else pc.busy_dev[k] = s.device;
+				} else s.pack_overflow.store(1);
+			}
 			if (s.host_left.fetch_sub(1, std::memory_order_acq_rel) == 1) s.owner->poke();
 		});
 	}
@@ -421,7 +471,7 @@ bool stage_issue(Slot &s, Job *job, int si, bool packed)
 	int64_t h2d = (nr + 1) * 8;
 	if (ok && na > 0) {
 		if (packed) {
-			ok = cuda_ok(cudaMemcpyAsync(s.d_lo, s.h_lo, (size_t)na * 8, cudaMemcpyHostToDevice, st), "H2D packed anchors")
+			ok = (s.ring_copied || cuda_ok(cudaMemcpyAsync(s.d_lo, s.h_lo, (size_t)na * 8, cudaMemcpyHostToDevice, st), "H2D packed anchors"))
 			  && cuda_ok(cudaMemcpyAsync(s.d_xruns, s.h_xruns, (size_t)s.n_xruns * 8, cudaMemcpyHostToDevice, st), "H2D x runs")
 			  && cuda_ok(cudaMemcpyAsync(s.d_yruns, s.h_yruns, (size_t)s.n_yruns * 8, cudaMemcpyHostToDevice, st), "H2D y runs")
 			  && mm2b_unpack_anchors_device(s.device, na, s.d_lo, s.d_xruns, s.n_xruns, s.d_yruns, s.n_yruns, s.d_a, st) == MM2B_OK;
@@ -900,6 +950,7 @@ int mm2b_init(int n_devices, const int *devices)
 	if (const char *s = getenv("MM2B_PACK_CHUNK")) { const long long v = atoll(s); if (v > 0) g.pack_chunk = v; }
 	if (const char *s = getenv("MM2B_PACK")) g.default_pack = atoi(s) != 0;
 	if (const char *s = getenv("MM2B_PACK_INFLIGHT")) g.pack_inflight = atoi(s);
+	if (const char *s = getenv("MM2B_PACK_RING")) g.pack_ring = atoi(s) != 0;
 	if (const char *s = getenv("MM2B_GATHER")) g.default_device_gather = strcmp(s, "host") != 0;
 	int n_helpers = (int)std::thread::hardware_concurrency() - 2;
 	n_helpers = std::max(2, std::min(n_helpers, 16));
@@ -985,6 +1036,29 @@ void mm2b_shutdown(void)
 }
 
 int mm2b_num_devices(void) { return g.up ? (int)g.devs.size() : 0; }
+
+double mm2b_measure_host_copy(int n_threads, size_t bytes_per_thread)
+{
+	if (n_threads < 1) n_threads = 1;
+	if (bytes_per_thread < (1u << 20)) bytes_per_thread = 1u << 20;
+	std::vector<char*> src((size_t)n_threads), dst((size_t)n_threads);
+	for (int t = 0; t < n_threads; ++t) {
+		src[t] = (char*)malloc(bytes_per_thread), dst[t] = (char*)malloc(bytes_per_thread);
+		if (!src[t] || !dst[t]) return -1.0;
+		memset(src[t], 1, bytes_per_thread), memset(dst[t], 2, bytes_per_thread);      // touch every page first
+	}
+	double best = 0;
+	for (int rep = 0; rep < 3; ++rep) {
+		std::vector<std::thread> th;
+		const double t0 = now_ms();
+		for (int t = 0; t < n_threads; ++t) th.emplace_back([&, t] { memcpy(dst[t], src[t], bytes_per_thread); });
+		for (auto &x : th) x.join();
+		const double gbs = 2.0 * (double)bytes_per_thread * n_threads / ((now_ms() - t0) * 1e-3) / 1e9;     // bytes read + bytes written
+		if (gbs > best) best = gbs;
+	}
+	for (int t = 0; t < n_threads; ++t) free(src[t]), free(dst[t]);
+	return best;
+}
 
 int mm2b_pack_anchors(const mm2b_anchor_t *a, int64_t n, void *lo, void *xruns, int32_t *n_xruns, void *yruns, int32_t *n_yruns, int32_t cap_runs)
 {

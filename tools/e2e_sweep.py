@@ -16,16 +16,17 @@ h_a = b.PinnedArray(n, b.ANCHOR); h_a.array[:] = a
 pin = {"u": b.PinnedArray(n, np.uint64), "n_u": b.PinnedArray(n_reads, np.int32), "n_v": b.PinnedArray(n_reads, np.int32), "status": b.PinnedArray(n_reads, np.int32),
        "u_off": b.PinnedArray(n_reads + 1, np.int64), "b_off": b.PinnedArray(n_reads + 1, np.int64)}
 h_b, h_bi = b.PinnedArray(n, b.ANCHOR), b.PinnedArray(n, np.int32)
-settings = [dict(MM2B_PACK_INFLIGHT=str(k)) for k in (0, 1, 2, 3, 99)]
-settings += [dict(MM2B_PACK_INFLIGHT="1", MM2B_HOST_THREADS=str(t)) for t in (4, 8, 24)]
-settings += [dict(MM2B_PACK_INFLIGHT="1", MM2B_SUB_ANCHORS=str(s)) for s in (1 << 20, 4 << 20)]
-settings += [dict(MM2B_PACK_INFLIGHT="2", MM2B_PACK_CHUNK=str(512 << 10))]
+settings = [dict(MM2B_PACK_INFLIGHT="0")]
+settings += [dict(MM2B_PACK_INFLIGHT=str(k), MM2B_PACK_RING=str(r)) for r in (1, 0) for k in (1, 2, 99)]
+settings += [dict(MM2B_PACK_INFLIGHT=str(k), MM2B_PACK_RING="1", MM2B_SUB_ANCHORS=str(4 << 20)) for k in (1, 2, 99)]
+settings += [dict(MM2B_PACK_INFLIGHT=str(k), MM2B_PACK_RING="1", MM2B_PACK_CHUNK=str(c << 10)) for k in (2, 99) for c in (16, 32, 256)]
+settings += [dict(MM2B_PACK_INFLIGHT="99", MM2B_PACK_RING="1", MM2B_HOST_THREADS=str(t)) for t in (6, 10)]
 for env in settings:
     for k, v in env.items():
         os.environ[k] = v
     b.init(1)
     row = []
-    for name, mode, flags in (("index", "index", 0), ("b_dev", "b", b.F_DEVICE_GATHER), ("b_host", "b", b.F_HOST_GATHER)):
+    for name, mode, flags in (("index", "index", 0), ("b_dev", "b", b.F_DEVICE_GATHER)):
         out = {k: v.array for k, v in pin.items()}
         out["bi" if mode == "index" else "b"] = (h_bi if mode == "index" else h_b).array
         for _ in range(2):
