@@ -253,6 +253,7 @@ def e2e_variants(torch, binding, w, steps, warmup, sync, which, keep_res=True):
                 "u_off": pin(n_reads + 1, np.int64), "b_off": pin(n_reads + 1, np.int64)}
         h_b, h_bi = pin(n_anchors, binding.ANCHOR), pin(n_anchors, np.int32)
         modes = {"default": ("default", 0, True, False), "index": ("index", 0, False, True),
+                 "host_gather": ("b", binding.F_HOST_GATHER, True, False),
                  "round1_format": ("b", binding.F_RAW_INPUT | binding.F_DEVICE_GATHER, True, False)}
         for name in which:
             mode, flags, want_b, want_bi = modes[name]
@@ -403,7 +404,7 @@ def main():
     value = tot_cells / (ms_value * 1e-3) / 1e9
 
     # ---- e2e: pinned host buffers through the host-buffer batch call, one process per GPU ------------------------
-    ev = e2e_variants(torch, binding, w, args.steps, args.warmup, barrier, ["default", "index", "round1_format"] if world == 1 else ["default", "index"])
+    ev = e2e_variants(torch, binding, w, args.steps, args.warmup, barrier, ["default", "index", "host_gather", "round1_format"] if world == 1 else ["default", "index"])
     ms_e2e = {k: max_over_ranks(v["ms"]) for k, v in ev.items()}
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (value and e2e)
     est = ev["default"]["stats"]
@@ -419,6 +420,7 @@ def main():
     apis = {"default": "mm2b_chain_batch: pinned mm128_t anchors in, u[] and b[] (mm128_t) out; inside the call the library packs the input to 8 B/anchor on its helper threads, "
                        "receives 4-byte indices and gathers b[] on the host",
             "index": "mm2b_chain_batch_ex with bi[]: same input path, the chained anchors come back as int32 indices into the caller's a[] (no b[] gather)",
+            "host_gather": "mm2b_chain_batch_ex(MM2B_F_HOST_GATHER): packed input, int32 indices over PCIe, b[] gathered from the caller's a[] by the library's helper threads",
             "round1_format": "mm2b_chain_batch_ex(MM2B_F_RAW_INPUT | MM2B_F_DEVICE_GATHER): 16 B/anchor in, 16 B/chained anchor out (round 1's transfer format)"}
     e2e = e2e_obj("default", apis["default"])
     e2e["variants"] = {k: e2e_obj(k, apis[k]) for k in ev if k != "default"}

@@ -110,9 +110,9 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
  *   flags   MM2B_F_RAW_INPUT      send anchors as 16-byte mm128_t.  Default: helper threads pack sub-batches into 8-byte
  *                                 {x_lo, y_lo} words plus run-length lists of the high words (strand/rid; flags/q_span/segment) on
  *                                 their way into the pinned staging buffer and the device restores mm128_t in HBM.  Packing is a
- *                                 pass over host memory, so only as many sub-batches are packed as the helper threads keep up with
- *                                 (MM2B_PACK_INFLIGHT at a time, default 1); the others, and any sub-batch whose high words change
- *                                 too often (e.g. a homopolymer-compressed index), go over raw by themselves.
+ *                                 pass over host memory; MM2B_PACK_INFLIGHT (default 99 = every sub-batch) bounds how many sub-batches are packed
+ *                                 at a time, the others — and any sub-batch whose high words change too often (e.g. a
+ *                                 homopolymer-compressed index) — go over raw by themselves.
  *           MM2B_F_DEVICE_GATHER  b[] comes back from the device as 16-byte anchors (the default when only b is asked for).
  *           MM2B_F_HOST_GATHER    b[] is gathered on the host's helper threads from 4-byte indices (pays off only where host
  *                                 memory bandwidth is plentiful compared with the PCIe link).

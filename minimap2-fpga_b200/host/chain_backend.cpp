@@ -263,15 +263,16 @@ struct Backend {
 	std::mutex mu;              // guards init/shutdown
 	bool up = false;
 	int64_t sub_anchors = 2 << 20;
-	int64_t pack_chunk = 64 << 10;      // anchors per helper task (= per staging piece: 512 KB packed)
+	int64_t pack_chunk = 256 << 10;     // anchors per helper task (= per staging piece: 2 MB packed; measured best of 16k..256k, profiles/r2b_e2e_sweep.txt)
 	bool want_stats = true;
 	bool trace = false;
 	bool default_pack = true, default_device_gather = true;
-	// Packing is a pass over host memory, and on the hosts measured it runs at about the speed of the PCIe link itself: packing every
-	// sub-batch just moves the bottleneck from the link to the host's memory system.  So at most `pack_inflight` sub-batches are
-	// being packed at any time; a sub-batch that finds the helper threads busy goes over raw (16 B/anchor) right away, and link
-	// and host memory work side by side.  0 = never pack, large = always pack.
-	int pack_inflight = 1;
+	// Packing is a pass over host memory (24 B of host traffic per anchor against 8 B saved on the link).  At most `pack_inflight`
+	// sub-batches are being packed at any time; a sub-batch that finds the limit reached goes over raw (16 B/anchor) right away.
+	// Measured on this pool's hosts (16 vCPUs, ~160 GB/s of memcpy traffic, 55 GB/s H2D; profiles/r2b_e2e_sweep.txt): packing
+	// everything wins (15.4 ms per 100k reads against 19.4 ms raw; limits of 1-2 in flight were slower than either), so that is
+	// the default.  0 = never pack.
+	int pack_inflight = 99;
 	std::atomic<int> packing_now{0};
 	// Cache-resident staging: every helper thread packs its chunk into a small pinned piece of its own (two per thread, taking
 	// turns) and enqueues that piece's H2D copy itself, so the copy engine reads the packed words out of the CPU's cache: they

@@ -94,13 +94,14 @@ def test_all_transfer_variants_agree_with_the_oracle(binding, oracle, pkg, seed)
         assert np.array_equal(a[int(off[r]) + rb["bi"][bo:bo + nv]], rb["b"][bo:bo + nv])
 
 
-def test_default_mixes_packed_and_raw_subbatches(binding, pkg, oracle):
-    """The library's default: at most MM2B_PACK_INFLIGHT sub-batches are being packed at a time, the others go over raw."""
+def test_bounded_packing_mixes_packed_and_raw_subbatches(binding, pkg, oracle):
+    """MM2B_PACK_INFLIGHT=1: at most one sub-batch is being packed at a time, the others go over raw; results do not change."""
     import os
     b = binding
     b.shutdown()
     saved = {k: os.environ.pop(k, None) for k in ("MM2B_PACK_INFLIGHT", "MM2B_PACK_CHUNK")}
     os.environ["MM2B_SUB_ANCHORS"] = "60000"
+    os.environ["MM2B_PACK_INFLIGHT"] = "1"
     try:
         b.init(1)
         off, a = pkg("workload").synth_anchor_batch(1200, seed=9)
@@ -111,6 +112,7 @@ def test_default_mixes_packed_and_raw_subbatches(binding, pkg, oracle):
         assert st.n_packed_subs + st.n_raw_subs >= 10 and st.n_packed_subs >= 1
     finally:
         b.shutdown()
+        os.environ.pop("MM2B_PACK_INFLIGHT", None)
         for k, v in saved.items():
             if v is not None:
                 os.environ[k] = v
