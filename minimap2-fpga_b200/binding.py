@@ -21,7 +21,10 @@ EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", 
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
            "mm2b_chain_batch_device", "mm2b_chain_batch_device_idx", "mm2b_chain_batch_ex", "mm2b_unpack_anchors_device", "mm2b_pack_anchors", "mm2b_measure_host_copy", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
-           "mm_chain_dp"]
+           "mm_chain_dp",
+           # include/mm2seed_b200.h: the seeding front end
+           "mm2b_index_create", "mm2b_index_destroy", "mm2b_index_lookup", "mm2b_map_supported", "mm2b_map_batch", "mm2b_map_result_release",
+           "mm2b_seed_debug", "mm2b_free"]
 
 
 class Params(C.Structure):
@@ -45,6 +48,24 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class IndexDesc(C.Structure):
+    """mm2b_index_desc_t (include/mm2seed_b200.h): the reference's minimizer index as flat arrays."""
+    _fields_ = [(k, C.c_int32) for k in ("k", "w", "is_hpc", "n_seq")] + [("n_keys", C.c_int64), ("n_pos", C.c_int64)] + [(k, C.c_void_p) for k in ("keys", "vals", "pos")]
+
+
+class SeedParams(C.Structure):
+    _fields_ = [("max_occ", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MapResult(C.Structure):
+    """mm2b_map_result_t"""
+    _fields_ = [("n_reads", C.c_int64)] + [(k, C.POINTER(C.c_int32)) for k in ("status", "n_u", "n_v", "rep_len", "n_mini_pos", "n_mini", "seg")] + \
+               [(k, C.POINTER(C.c_int64)) for k in ("n_a", "u_off", "b_off", "mp_off")] + [("n_segs", C.c_int32)] + \
+               [("seg_u", C.POINTER(C.c_void_p)), ("seg_b", C.POINTER(C.c_void_p)), ("seg_mini_pos", C.POINTER(C.c_void_p))] + \
+               [(k, C.c_int64) for k in ("tot_mini", "tot_anchors", "tot_chains", "tot_chained", "n_tie_reads", "h2d_bytes", "d2h_bytes")] + \
+               [(k, C.c_double) for k in ("sketch_ms", "seed_ms", "sort_ms", "chain_ms")] + [("cells_ref", C.c_int64), ("priv", C.c_void_p)]
 
 
 class Mm2bError(RuntimeError):
@@ -102,6 +123,16 @@ def load():
     L.mm2b_measure_int32_peak.restype, L.mm2b_measure_int32_peak.argtypes = C.c_double, [i32]
     L.mm_chain_dp.restype = vp
     L.mm_chain_dp.argtypes = [i32] * 7 + [C.c_float, i32, i32, i64, vp, C.POINTER(i32), C.POINTER(vp), vp, i32]
+    L.mm2b_index_create.restype, L.mm2b_index_create.argtypes = vp, [C.POINTER(IndexDesc)]
+    L.mm2b_index_destroy.restype, L.mm2b_index_destroy.argtypes = None, [vp]
+    L.mm2b_index_lookup.restype, L.mm2b_index_lookup.argtypes = i32, [vp, i64, vp, vp, vp]
+    L.mm2b_map_supported.restype, L.mm2b_map_supported.argtypes = i32, [i32, i32, i32, i32, i64, i32]
+    L.mm2b_map_batch.restype = i32
+    L.mm2b_map_batch.argtypes = [vp, C.POINTER(SeedParams), C.POINTER(Params), i64, vp, vp, C.POINTER(C.POINTER(MapResult))]
+    L.mm2b_map_result_release.restype, L.mm2b_map_result_release.argtypes = None, [C.POINTER(MapResult)]
+    L.mm2b_seed_debug.restype = i32
+    L.mm2b_seed_debug.argtypes = [vp, C.POINTER(SeedParams), i64, vp, vp] + [C.POINTER(vp)] * 7 + [C.POINTER(i64)]
+    L.mm2b_free.restype, L.mm2b_free.argtypes = None, [vp]
     _lib = L
     return L
 
@@ -361,3 +392,89 @@ class DeviceBatch:
             self.close()
         except Exception:
             pass
+
+
+# ---- the seeding front end (include/mm2seed_b200.h) ---------------------------------------------------------------------
+
+class Index:
+    """The reference's minimizer index on every bound device.  flat: dict(k, w, is_hpc, n_seq, keys, vals, pos) as mm2b_index_flatten
+    (host/idx_flatten.cpp) produces it."""
+
+    def __init__(self, flat):
+        L = load()
+        self.k, self.w = int(flat["k"]), int(flat["w"])
+        keys, vals, pos = (np.ascontiguousarray(flat[k], np.uint64) for k in ("keys", "vals", "pos"))
+        d = IndexDesc(self.k, self.w, int(flat.get("is_hpc", 0)), int(flat.get("n_seq", 1)), len(keys), len(pos), keys.ctypes.data, vals.ctypes.data, pos.ctypes.data)
+        self.h = L.mm2b_index_create(C.byref(d))
+        if not self.h:
+            raise Mm2bError("mm2b_index_create failed: %s" % L.mm2b_last_error().decode())
+
+    def close(self):
+        if self.h:
+            load().mm2b_index_destroy(self.h)
+            self.h = None
+
+    def lookup(self, minimizers):
+        m = np.ascontiguousarray(minimizers, np.uint64)
+        n_occ, val = np.zeros(len(m), np.int32), np.zeros(len(m), np.uint64)
+        _check(load().mm2b_index_lookup(self.h, len(m), _p(m), _p(n_occ), _p(val)), "mm2b_index_lookup")
+        return n_occ, val
+
+
+def _seq_batch(seqs):
+    off = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    return off, b"".join(bytes(s) for s in seqs)
+
+
+def _take(ptr, dtype, n):
+    dt = np.dtype(dtype)
+    if n <= 0 or not ptr:
+        return np.empty(0, dt)
+    return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(ptr), dt, n).copy()
+
+
+def seed_debug(index, seqs, max_occ):
+    """Sketch + seed + sort on the GPU for a small batch; returns the intermediate products (mm2b_seed_debug):
+    dict(mini_off, mini, a_off, a, rep_len, n_mini_pos, mini_pos, n_tie_reads)."""
+    L = load()
+    off, blob = _seq_batch(seqs)
+    sp = SeedParams(max_occ, 0)
+    ptrs = [C.c_void_p() for _ in range(7)]
+    n_tie = C.c_int64(0)
+    _check(L.mm2b_seed_debug(index.h, C.byref(sp), len(seqs), _p(off), blob, *[C.byref(p) for p in ptrs], C.byref(n_tie)), "mm2b_seed_debug")
+    n = len(seqs)
+    mini_off = _take(ptrs[0].value, np.int64, n + 1)
+    a_off = _take(ptrs[2].value, np.int64, n + 1)
+    out = dict(mini_off=mini_off, mini=_take(ptrs[1].value, ANCHOR, int(mini_off[-1])), a_off=a_off, a=_take(ptrs[3].value, ANCHOR, int(a_off[-1])),
+               rep_len=_take(ptrs[4].value, np.int32, n), n_mini_pos=_take(ptrs[5].value, np.int32, n), mini_pos=_take(ptrs[6].value, np.uint32, int(mini_off[-1])),
+               n_tie_reads=n_tie.value)
+    for p in ptrs:
+        L.mm2b_free(p)
+    return out
+
+
+def map_batch(index, seqs, max_occ, par=None, seq_off=None, blob=None):
+    """mm2b_map_batch: read sequences in, chains out.  seqs: list of bytes (or pass seq_off + blob).  Returns a dict of per-read
+    arrays plus lists `u`, `b`, `mini_pos` (one numpy array per read) when `seqs` is small, and the call's totals in `stats`."""
+    L = load()
+    if seq_off is None:
+        seq_off, blob = _seq_batch(seqs)
+    par = par or Params()
+    sp = SeedParams(max_occ, 0)
+    res = C.POINTER(MapResult)()
+    _check(L.mm2b_map_batch(index.h, C.byref(sp), C.byref(par), len(seq_off) - 1, _p(seq_off), blob, C.byref(res)), "mm2b_map_batch")
+    r = res.contents
+    n = int(r.n_reads)
+    out = {k: np.ctypeslib.as_array(getattr(r, k), (n,)).copy() if n else np.empty(0, np.int64) for k in ("status", "n_u", "n_v", "rep_len", "n_mini_pos", "n_mini", "seg", "n_a", "u_off", "b_off", "mp_off")}
+    out["stats"] = {k: getattr(r, k) for k in ("tot_mini", "tot_anchors", "tot_chains", "tot_chained", "n_tie_reads", "h2d_bytes", "d2h_bytes", "sketch_ms", "seed_ms", "sort_ms", "chain_ms", "cells_ref")}
+    out["stats"]["n_segs"] = int(r.n_segs)
+    u, b, mp = [], [], []
+    for i in range(n):
+        s = int(out["seg"][i])
+        u.append(_take((r.seg_u[s] or 0) + 8 * int(out["u_off"][i]), np.uint64, int(out["n_u"][i])))
+        b.append(_take((r.seg_b[s] or 0) + 16 * int(out["b_off"][i]), ANCHOR, int(out["n_v"][i])))
+        mp.append(_take((r.seg_mini_pos[s] or 0) + 4 * int(out["mp_off"][i]), np.uint32, int(out["n_mini_pos"][i])))
+    out["u"], out["b"], out["mini_pos"] = u, b, mp
+    L.mm2b_map_result_release(res)
+    return out

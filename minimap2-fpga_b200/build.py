@@ -1,6 +1,7 @@
 """In-tree build of the native library (explicit nvcc / g++ commands, no JIT cache).
 
-  libmm2chain_b200.so = csrc/chain_kernels.cu + csrc/chain_api.cu (nvcc, sm_100a) + host/chain_backend.cpp (g++)
+  libmm2chain_b200.so = csrc/chain_kernels.cu + csrc/chain_api.cu + csrc/seed_kernels.cu (nvcc, sm_100a)
+                        + host/chain_backend.cpp + host/map_backend.cpp (g++)
   mm2b-replay         = host/replay_main.cpp (g++) linked against the library: the batched caller for anchor dumps
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
@@ -21,9 +22,9 @@ NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 INC = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]
 
-CU_SRCS = ["csrc/chain_kernels.cu", "csrc/chain_api.cu"]
-CXX_SRCS = ["host/chain_backend.cpp"]
-HEADERS = ["csrc/chain_kernels.cuh", "csrc/shim_internal.h", "../include/mm2chain_b200.h"]
+CU_SRCS = ["csrc/chain_kernels.cu", "csrc/chain_api.cu", "csrc/seed_kernels.cu"]
+CXX_SRCS = ["host/chain_backend.cpp", "host/map_backend.cpp"]
+HEADERS = ["csrc/chain_kernels.cuh", "csrc/sort_replay.cuh", "csrc/seed_kernels.cuh", "csrc/shim_internal.h", "../include/mm2chain_b200.h", "../include/mm2seed_b200.h"]
 
 
 def _newer(target, deps):

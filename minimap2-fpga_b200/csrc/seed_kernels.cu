@@ -1,0 +1,614 @@
+// Hand-written sm_100a kernels for minimap2's seeding front end — SURVEY.md 8(f) next-4 (mm_sketch, /root/reference/sketch.c:77-143)
+// and next-1 (collect_matches / collect_seed_hits over mm_idx_get, map.c:90-247, index.c:81-98).  Anchors are born in HBM, sorted
+// there the way the reference's radix_sort_128x leaves them (map.c:245), and go straight into the chaining kernels.
+//
+// Design (B200-first; the reference is a per-read sequential scan with a w-entry ring buffer and a khash probe per minimizer):
+//   * sketch: one thread per base position, one CTA per tile of 512 positions.  The CTA packs the tile's bases to 2 bits with
+//     warp ballots / REDUX.OR, every thread cuts its k-mer and the reverse complement out of two 64-bit words (funnel shift,
+//     BREV), hashes it, and the w + 1 hashes around it in shared memory tell it everything mm_sketch's state machine does at its
+//     position: the ring buffer's minimum is always the NEWEST minimal entry of the last w positions, so "what is pushed at
+//     step t" is a function of X[t-w .. t] and of the distance to the last ambiguous base.  A count pass, an exclusive scan over
+//     the tiles and an emit pass put the minimizers in the reference's order, duplicates of its first-window rule included.
+//   * index: one open-addressing table in HBM (linear probing, load <= 0.5) instead of 2^b khash buckets; one probe thread per
+//     minimizer, all minimizers of a sub-batch at once (the probes are dependent HBM accesses: parallelism is what hides them).
+//   * matches: one warp per read walks its minimizers 32 at a time: occurrence filter, repeat length (a merge of intervals the
+//     reference does sequentially, here a "previous flagged lane" vote), tandem flags, mini_pos and the anchor offsets.
+//   * anchors: expanded by the read's warp, sorted by a warp-level LSD radix sort over the key bytes that differ.  Sorted order is
+//     unique except among equal keys, whose order in the reference is whatever its in-place MSD radix sort leaves; reads that
+//     hold equal keys (a minimizer repeated in the query hitting one reference position) are expanded again and put through an
+//     exact replay of that sort (sort_replay.cuh), so a[] is byte-identical to the reference's in every case.
+// No tensor cores (nothing here is a contraction) and no collective (reads are independent).
+#include "seed_kernels.cuh"
+#include "sort_replay.cuh"
+#include <limits.h>
+
+namespace mm2b {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int HALO = 96;                                    // positions loaded in front of a tile: >= w + k, a multiple of 32
+constexpr int TILE_SPAN = SKETCH_TILE + HALO;               // 608 = 19 warps of positions
+constexpr uint64_t EMPTY = ~0ull;
+constexpr uint64_t SEED_TANDEM = 1ull << 42;                // MM_SEED_TANDEM, mmpriv.h:19
+
+__device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// seq_nt4_table (sketch.c:9-26): A/a 0, C/c 1, G/g 2, T/t/U/u 3, the byte values 0..3 themselves, everything else 4
+__device__ __forceinline__ int nt4(unsigned ch)
+{
+	if (ch < 4) return (int)ch;
+	const unsigned u = ch & 0xdfu;                          // only clears bit 5: 65 comes from 'A' or 'a' alone, and so on
+	return u == 65 ? 0 : u == 67 ? 1 : u == 71 ? 2 : (u == 84 || u == 85) ? 3 : 4;
+}
+
+// hash64 of sketch.c:28-38
+__device__ __forceinline__ uint64_t hash64(uint64_t key, uint64_t mask)
+{
+	key = (~key + (key << 21)) & mask;
+	key = key ^ key >> 24;
+	key = ((key + (key << 3)) + (key << 8)) & mask;
+	key = key ^ key >> 14;
+	key = ((key + (key << 2)) + (key << 4)) & mask;
+	key = key ^ key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+__device__ __forceinline__ uint64_t table_slot(uint64_t minimizer, int log2cap)
+{
+	return (minimizer * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sketch
+// ---------------------------------------------------------------------------------------------------------------
+// mm_sketch's state after processing position t (sketch.c:89-139; non-HPC, odd k so no k-mer equals its reverse complement):
+//   buf      the infos of positions t-w+1 .. t        info = (hash << 8 | k, t << 1 | strand) or "invalid" (all ones)
+//   min      the NEWEST entry of buf with the smallest x — `<=` when a new info arrives (sketch.c:121), `>=` in the rescan
+//            that runs oldest to newest (sketch.c:126-129); an invalid entry is just the largest possible x
+//   l        valid bases since the last ambiguous one (or since the start of the read)
+// so with X[j] the x of position j (invalid before the read and wherever l < k) and m = newest minimal of X[t-w .. t-1], step t
+// pushes, in this order:
+//   S  l == w+k-1 and m valid:  every j in (t-w, t) with X[j] == X[m], j != m                       (sketch.c:115-120, first window)
+//   A  X[t] <= X[m]:            m, if l >= w+k and m valid                                          (sketch.c:121-123)
+//   B  else if m == t-w:        m, if l >= w+k-1 and m valid; then with n = newest minimal of X[t-w+1 .. t], if l >= w+k-1 and
+//                               n valid: every j in (t-w, t] with X[j] == X[n], j != n              (sketch.c:124-137)
+//   E  at the last position:    the minimum after the step, if valid                                (sketch.c:141-142)
+// A position can be pushed more than once (S and B at the same step): the output is a sequence, not a set, and is reproduced as such.
+struct Emit {
+	unsigned long long mask_s, mask_b;      // bit d <-> position t - w + 1 + d
+	int first_m, last_e;                    // position pushed by A / B's first push (or -1); by E (or -1)
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
+{
+	__shared__ uint64_t X[TILE_SPAN];
+	__shared__ uint64_t pk[TILE_SPAN / 32 + 1];             // 2-bit bases, 32 per word, earlier base in the lower bits
+	__shared__ uint32_t badw[TILE_SPAN / 32];               // one bit per position: ambiguous base or outside the read
+	__shared__ uint8_t zs[TILE_SPAN];                       // strand of the position's k-mer
+	__shared__ int warp_sum[SKETCH_TILE / 32];
+	__shared__ int read_of_tile;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) {                                         // which read this tile belongs to: last r with tile_off[r] <= blockIdx.x
+		int lo = 0, hi = (int)s.n_reads - 1;
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			if (s.tile_off[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+		}
+		read_of_tile = lo;
+		pk[TILE_SPAN / 32] = 0;
+	}
+	__syncthreads();
+	const int r = read_of_tile;
+	const int64_t so = s.seq_off[r];
+	const int L = (int)(s.seq_off[r + 1] - so);
+	const int t0 = ((int)blockIdx.x - s.tile_off[r]) * SKETCH_TILE;
+	const int pb = t0 - HALO;                               // position of shared-memory index 0
+	const int k = s.k, w = s.w;
+	const uint64_t mask = (1ull << 2 * k) - 1;
+
+	// 1. bases -> 2-bit words and the bitmap of ambiguous positions (warps 0..18 of positions; the CTA has 16 warps)
+	for (int base = warp * 32; base < TILE_SPAN; base += SKETCH_TILE) {
+		const int pos = pb + base + lane;
+		int c = 4;
+		if (pos >= 0 && pos < L) c = nt4(s.seq[so + pos]);
+		const unsigned bad = __ballot_sync(FULL, c == 4);
+		const unsigned two = (unsigned)(c & 3) << 2 * (lane & 15);
+		const unsigned lo = __reduce_or_sync(FULL, lane < 16 ? two : 0u), hi = __reduce_or_sync(FULL, lane >= 16 ? two : 0u);
+		if (lane == 0) badw[base >> 5] = bad, pk[base >> 5] = (uint64_t)hi << 32 | lo;
+	}
+	__syncthreads();
+
+	// valid bases up to and including shared index i (0 when i itself is ambiguous); 128 when the run reaches past what is loaded —
+	// every threshold below is <= w + k <= 92, and a thread only asks about indices that have that much in front of them
+	auto run_len = [&](int i) -> int {
+		int wi = i >> 5;
+		const int b = i & 31;
+		unsigned m = badw[wi] & (0xffffffffu >> (31 - b));
+		if (m) return b - (31 - __clz(m));
+		int l = b + 1;
+		for (int back = 0; back < 3; ++back) {
+			if (--wi < 0) return 128;
+			m = badw[wi];
+			if (m) return l + __clz(m);
+			l += 32;
+		}
+		return 128;
+	};
+
+	// 2. X for the positions t0 - w .. t0 + TILE - 1
+	for (int i = HALO - w + tid; i < TILE_SPAN; i += SKETCH_TILE) {
+		uint64_t x = EMPTY;
+		int z = 0;
+		if (run_len(i) >= k) {
+			const int p0 = i - k + 1, wi = p0 >> 5, sh = (p0 & 31) * 2;
+			uint64_t f = pk[wi] >> sh;
+			if (sh) f |= pk[wi + 1] << (64 - sh);
+			f &= mask;                                              // oldest base in the lowest bits ...
+			const uint64_t rv = f ^ mask;                           // ... which is how the reverse k-mer is kept (sketch.c:109): complement only
+			uint64_t fw = __brevll(f);                              // forward k-mer: oldest base on top (sketch.c:108) = the 2-bit groups reversed
+			fw = ((fw >> 1) & 0x5555555555555555ull) | ((fw & 0x5555555555555555ull) << 1);
+			fw >>= 64 - 2 * k;
+			z = fw < rv ? 0 : 1;                                    // sketch.c:111 (fw != rv for odd k)
+			x = hash64(z ? rv : fw, mask) << 8 | (uint64_t)k;       // sketch.c:114; kmer_span == k once l >= k
+		}
+		X[i] = x, zs[i] = (uint8_t)z;
+	}
+	__syncthreads();
+
+	// 3. what mm_sketch pushes at this thread's position
+	const int i = HALO + tid, t = t0 + tid;
+	Emit e;
+	e.mask_s = e.mask_b = 0, e.first_m = e.last_e = -1;
+	int cnt = 0;
+	if (t < L) {
+		const int l = run_len(i);
+		uint64_t xm = EMPTY;
+		int jm = i - w;
+		for (int j = i - w; j < i; ++j) if (X[j] <= xm) xm = X[j], jm = j;      // newest minimal of the previous window
+		const uint64_t xt = X[i];
+		int after = jm;                                                     // the minimum after this step (shared index)
+		if (l == w + k - 1 && xm != EMPTY)
+			for (int j = i - w + 1; j < i; ++j) if (X[j] == xm && j != jm) e.mask_s |= 1ull << (j - (i - w + 1));
+		if (xt <= xm) {
+			if (l >= w + k && xm != EMPTY) e.first_m = jm;
+			after = i;
+		} else if (jm == i - w) {
+			if (l >= w + k - 1 && xm != EMPTY) e.first_m = jm;
+			uint64_t xn = EMPTY;
+			int jn = i - w + 1;
+			for (int j = i - w + 1; j <= i; ++j) if (X[j] <= xn) xn = X[j], jn = j;
+			if (l >= w + k - 1 && xn != EMPTY)
+				for (int j = i - w + 1; j <= i; ++j) if (X[j] == xn && j != jn) e.mask_b |= 1ull << (j - (i - w + 1));
+			after = jn;
+		}
+		if (t == L - 1 && X[after] != EMPTY) e.last_e = after;
+		cnt = __popcll(e.mask_s) + (e.first_m >= 0) + __popcll(e.mask_b) + (e.last_e >= 0);
+	}
+	// block-wide exclusive scan of the counts
+	int incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int o = __shfl_up_sync(FULL, incl, d);
+		if (lane >= d) incl += o;
+	}
+	if (lane == 31) warp_sum[warp] = incl;
+	__syncthreads();
+	int before = 0, total = 0;
+	for (int q = 0; q < SKETCH_TILE / 32; ++q) {
+		const int v = warp_sum[q];
+		if (q < warp) before += v;
+		total += v;
+	}
+	if (!WRITE) {
+		if (tid == 0) s.tile_cnt[blockIdx.x] = total;
+		return;
+	}
+	if (cnt == 0) return;
+	ulonglong2 *dst = s.mv + s.tile_mv_off[blockIdx.x] + before + (incl - cnt);
+	auto push = [&](int j) { *dst++ = make_ulonglong2(X[j], (uint64_t)(uint32_t)(pb + j) << 1 | zs[j]); };     // sketch.c:115 (rid 0)
+	const int j0 = i - w + 1;
+	for (unsigned long long m = e.mask_s; m; m &= m - 1) push(j0 + __ffsll((long long)m) - 1);
+	if (e.first_m >= 0) push(e.first_m);
+	for (unsigned long long m = e.mask_b; m; m &= m - 1) push(j0 + __ffsll((long long)m) - 1);
+	if (e.last_e >= 0) push(e.last_e);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small utilities: exclusive prefix sums over a few thousand entries (one CTA), per-read minimizer offsets
+// ---------------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(1024) scan_kernel(const T *in, int64_t *out, int64_t n)
+{
+	__shared__ int64_t warp_sum[32];
+	__shared__ int64_t carry_s;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) carry_s = 0;
+	__syncthreads();
+	for (int64_t base = 0; base < n; base += 1024) {
+		const int64_t i = base + tid;
+		const int64_t v = i < n ? (int64_t)in[i] : 0;
+		int64_t incl = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int64_t o = __shfl_up_sync(FULL, incl, d);
+			if (lane >= d) incl += o;
+		}
+		if (lane == 31) warp_sum[warp] = incl;
+		__syncthreads();
+		int64_t before = carry_s;
+		for (int q = 0; q < warp; ++q) before += warp_sum[q];
+		if (i < n) out[i] = before + incl - v;
+		__syncthreads();
+		if (tid == 1023) carry_s = before + incl;
+		__syncthreads();
+	}
+	if (tid == 0) out[n] = carry_s;
+}
+
+__global__ void read_offsets_kernel(const SeedArgs s)
+{
+	const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r <= s.n_reads) s.mv_off[r] = s.tile_mv_off[r < s.n_reads ? s.tile_off[r] : s.n_tiles];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Index: build and probe (mm_idx_get, index.c:81-98)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void index_insert_kernel(int64_t n_keys, const uint64_t *keys, const uint64_t *vals, uint64_t *tab_keys, uint64_t *tab_vals, int log2cap)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_keys) return;
+	const uint64_t key = keys[i], cap_mask = (1ull << log2cap) - 1;
+	uint64_t h = table_slot(key >> 1, log2cap);
+	for (;;) {
+		const unsigned long long old = atomicCAS((unsigned long long*)&tab_keys[h], (unsigned long long)EMPTY, (unsigned long long)key);
+		if (old == EMPTY) { tab_vals[h] = vals[i]; return; }
+		h = (h + 1) & cap_mask;                                 // (keys are distinct: an occupied slot is somebody else's)
+	}
+}
+
+__device__ __forceinline__ int index_get(const DeviceIndex &ix, uint64_t minimizer, uint64_t &val)
+{
+	const uint64_t cap_mask = (1ull << ix.log2cap) - 1;
+	uint64_t h = table_slot(minimizer, ix.log2cap);
+	for (;;) {
+		const uint64_t key = __ldg(&ix.tab_keys[h]);
+		if (key == EMPTY) { val = 0; return 0; }
+		if (key >> 1 == minimizer) {
+			val = __ldg(&ix.tab_vals[h]);
+			return (key & 1) ? 1 : (int)(uint32_t)val;              // index.c:90-96
+		}
+		h = (h + 1) & cap_mask;
+	}
+}
+
+__global__ void __launch_bounds__(256) index_lookup_kernel(const DeviceIndex ix, int64_t n, const ulonglong2 *mv, const uint64_t *raw, int32_t *occ, uint64_t *hv)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t minimizer = mv ? __ldg(&mv[i].x) >> 8 : raw[i];      // map.c:103
+	uint64_t v;
+	occ[i] = index_get(ix, minimizer, v);
+	hv[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// collect_matches (map.c:90-123), one warp per read
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) matches_kernel(const SeedArgs s)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < s.n_reads; r += n_warps) {
+		const int64_t m0 = s.mv_off[r];
+		const int n = (int)(s.mv_off[r + 1] - m0);
+		const ulonglong2 *mv = s.mv + m0;
+		int rep_len = 0, prev_en = 0, n_mp = 0;
+		long long n_a = 0;
+		for (int base = 0; base < n; base += 32) {
+			const int i = base + lane;
+			const bool in = i < n;
+			uint64_t x = 0, y = 0;
+			int t = 0;
+			if (in) {
+				const ulonglong2 q = __ldg(mv + i);
+				x = q.x, y = q.y;
+				t = s.occ[m0 + i];
+			}
+			__syncwarp();
+			const int q_span = (int)(x & 0xff), q_pos = (int)(uint32_t)y;
+			const bool high = in && t >= s.max_occ, match = in && t < s.max_occ;
+			// repeat length (map.c:104-110, :120): the union of the query intervals [en - q_span, en) of the skipped minimizers, taken in
+			// order of en; each adds en - max(st, en of the previous one)
+			const int en = (q_pos >> 1) + 1, st = en - q_span;
+			const unsigned hm = __ballot_sync(FULL, high);
+			const unsigned below = hm & lanemask_lt(lane);
+			const int src = below ? 31 - __clz(below) : 0;
+			int pe = __shfl_sync(FULL, en, src);
+			if (!below) pe = prev_en;
+			int add = high ? en - (st > pe ? st : pe) : 0;
+#pragma unroll
+			for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(FULL, add, d);
+			rep_len += add;
+			if (hm) prev_en = __shfl_sync(FULL, en, 31 - __clz(hm));
+			// matches: mini_pos (map.c:117) and the first anchor of each (exclusive prefix of the occurrence counts, map.c:116)
+			const unsigned mm = __ballot_sync(FULL, match);
+			if (match) s.mini_pos[m0 + n_mp + __popc(mm & lanemask_lt(lane))] = (uint32_t)(q_pos >> 1);
+			int incl = match ? t : 0;
+			const int mine = incl;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(FULL, incl, d);
+				if (lane >= d) incl += o;
+			}
+			if (in) s.arel[m0 + i] = match ? (int32_t)(n_a + incl - mine) : -1;
+			__syncwarp();
+			n_a += __shfl_sync(FULL, incl, 31);
+			n_mp += __popc(mm);
+		}
+		if (lane == 0) s.rep_len[r] = rep_len, s.n_mini_pos[r] = n_mp, s.n_a[r] = n_a;
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// collect_seed_hits (map.c:215-247): anchors of one read, written by its warp in the reference's order (match by match)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void expand_read(const SeedArgs &s, const DeviceIndex &ix, int64_t r, int lane)
+{
+	const int64_t m0 = s.mv_off[r];
+	const int n = (int)(s.mv_off[r + 1] - m0);
+	const int qlen = (int)(s.seq_off[r + 1] - s.seq_off[r]);
+	ulonglong2 *a = s.a + s.a_off[r];
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + lane;
+		int t = 0, rel = -1;
+		uint64_t x = 0, y = 0, v = 0;
+		bool tandem = false;
+		if (i < n) {
+			rel = s.arel[m0 + i];
+			if (rel >= 0) {
+				const ulonglong2 q = __ldg(s.mv + m0 + i);
+				x = q.x, y = q.y, t = s.occ[m0 + i], v = s.hv[m0 + i];
+				// map.c:113-115: the same minimizer right before or after this one in the read's sketch (whatever its occurrence count)
+				tandem = (i > 0 && __ldg(&s.mv[m0 + i - 1].x) >> 8 == x >> 8) || (i < n - 1 && __ldg(&s.mv[m0 + i + 1].x) >> 8 == x >> 8);
+			}
+		}
+		__syncwarp();
+		const uint32_t q_pos = (uint32_t)y;
+		const uint64_t q_span = x & 0xff;
+		for (int h = 0; h < t; ++h) {
+			const uint64_t rr = t == 1 ? v : __ldg(&ix.pos[(v >> 32) + h]);                 // index.c:90-96
+			const uint32_t rpos = (uint32_t)rr >> 1;
+			uint64_t ax, ay;
+			if ((rr & 1) == (q_pos & 1)) {                                                   // forward strand (map.c:232-234)
+				ax = (rr & 0xffffffff00000000ull) | rpos;
+				ay = q_span << 32 | (q_pos >> 1);
+			} else {                                                                         // reverse strand (map.c:235-238)
+				ax = 1ull << 63 | (rr & 0xffffffff00000000ull) | rpos;
+				ay = q_span << 32 | (uint32_t)(qlen - (int)((q_pos >> 1) + 1 - (uint32_t)q_span) - 1);
+			}
+			ay |= (y >> 32) << 48;                                                           // seg_id (map.c:239): 0 on this path
+			if (tandem) ay |= SEED_TANDEM;
+			a[rel + h] = make_ulonglong2(ax, ay);
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(256) expand_kernel(const SeedArgs s, const DeviceIndex ix)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < s.n_reads; r += n_warps) expand_read(s, ix, r, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// radix_sort_128x (map.c:245).  Stable LSD radix sort by one warp over the bytes of x that differ inside the read; the result is
+// the reference's unless the read holds equal keys, and those reads are listed for the exact replay below.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void warp_sort_by_x(ulonglong2 *keys, ulonglong2 *tmp, int n, int *hist, int lane)
+{
+	uint64_t diff = 0;
+	const uint64_t k0 = keys[0].x;
+	for (int k = lane; k < n; k += 32) diff |= keys[k].x ^ k0;
+	__syncwarp();
+#pragma unroll
+	for (int d = 16; d; d >>= 1) diff |= __shfl_xor_sync(FULL, diff, d);
+	ulonglong2 *src = keys, *dst = tmp;
+	for (int shift = 0; shift < 64; shift += 8) {
+		if (((diff >> shift) & 0xff) == 0) continue;
+		for (int b = lane; b < 256; b += 32) hist[b] = 0;
+		__syncwarp();
+		for (int base = 0; base < n; base += 32) {
+			const int k = base + lane;
+			const int dig = k < n ? (int)(src[k].x >> shift & 0xff) : 256;
+			const unsigned peers = __match_any_sync(FULL, dig);
+			if (k < n && (peers & lanemask_lt(lane)) == 0) hist[dig] += __popc(peers);
+			__syncwarp();
+		}
+		{
+			int loc[8], sum = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) loc[q] = hist[lane * 8 + q], sum += loc[q];
+			int incl = sum;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(FULL, incl, d);
+				if (lane >= d) incl += o;
+			}
+			int run = incl - sum;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = run, run += loc[q];
+		}
+		__syncwarp();
+		for (int base = 0; base < n; base += 32) {
+			const int k = base + lane;
+			const bool act = k < n;
+			ulonglong2 rec = make_ulonglong2(0, 0);
+			if (act) rec = src[k];
+			const int dig = act ? (int)(rec.x >> shift & 0xff) : 256;
+			const unsigned peers = __match_any_sync(FULL, dig);
+			const int rank = __popc(peers & lanemask_lt(lane));
+			int pos = 0;
+			if (act) pos = hist[dig] + rank;
+			__syncwarp();
+			if (act) {
+				dst[pos] = rec;
+				if (rank == 0) hist[dig] += __popc(peers);
+			}
+			__syncwarp();
+		}
+		ulonglong2 *t = src; src = dst; dst = t;
+	}
+	if (src != keys) for (int k = lane; k < n; k += 32) keys[k] = src[k];
+	__syncwarp();
+}
+
+__global__ void __launch_bounds__(128) sort_kernel(const SeedArgs s)
+{
+	__shared__ int hist[4][256];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (;;) {
+		int r = 0;
+		if (lane == 0) r = atomicAdd(&s.tie_count[1], 1);
+		r = __shfl_sync(FULL, r, 0);
+		if (r >= s.n_reads) break;
+		const int64_t o = s.a_off[r], n64 = s.a_off[r + 1] - o;
+		if (n64 < 2) continue;
+		const int n = (int)n64;
+		ulonglong2 *a = s.a + o;
+		if (n <= 32) {                                      // one key per lane: rank by (x, position)
+			const ulonglong2 rec = lane < n ? a[lane] : make_ulonglong2(EMPTY, 0);
+			int rank = 0;
+			bool tie = false;
+			for (int q = 0; q < n; ++q) {
+				const uint64_t xq = __shfl_sync(FULL, rec.x, q);
+				rank += xq < rec.x || (xq == rec.x && q < lane);
+				tie |= q != lane && xq == rec.x;
+			}
+			__syncwarp();
+			if (lane < n) a[rank] = rec;
+			const bool any_tie = __any_sync(FULL, lane < n && tie);
+			if (any_tie && lane == 0) s.tie_list[atomicAdd(&s.tie_count[0], 1)] = r;
+			__syncwarp();
+			continue;
+		}
+		warp_sort_by_x(a, s.a_tmp + o, n, hist[warp], lane);
+		bool tie = false;
+		for (int k = lane; k + 1 < n; k += 32) tie |= a[k].x == a[k + 1].x;
+		__syncwarp();
+		if (__any_sync(FULL, tie) && lane == 0) s.tie_list[atomicAdd(&s.tie_count[0], 1)] = r;
+		__syncwarp();
+	}
+}
+
+// Reads with equal keys: expand again (the sort above was in place) and replay radix_sort_128x itself — insertion sort up to 64
+// elements, else the in-place MSD byte radix permutation (ksort.h:116-151) — on one lane.  Rare for reads against a unique
+// reference (a minimizer has to repeat inside the query); the rule for tandem repeats.
+__global__ void __launch_bounds__(128) tie_replay_kernel(const SeedArgs s, const DeviceIndex ix)
+{
+	__shared__ int sm[4][768];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int n_tie = 0;
+	if (lane == 0) n_tie = s.tie_count[0];
+	n_tie = __shfl_sync(FULL, n_tie, 0);
+	for (;;) {
+		int slot = 0;
+		if (lane == 0) slot = atomicAdd(&s.tie_count[2], 1);
+		slot = __shfl_sync(FULL, slot, 0);
+		if (slot >= n_tie) break;
+		const int r = s.tie_list[slot];
+		expand_read(s, ix, r, lane);
+		__syncwarp();
+		const int64_t o = s.a_off[r];
+		const int n = (int)(s.a_off[r + 1] - o);
+		if (lane == 0) {
+			W16 *w = (W16*)(s.a + o);
+			if (n <= 64) insertion_by_x(w, n);
+			else flag_sort_by_x_lane0(w, n, sm[warp], (int3*)(s.a_tmp + o), (int)((int64_t)n * 16 / (int64_t)sizeof(int3)));
+		}
+		__syncwarp();
+	}
+}
+
+}  // anonymous namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+int launch_index_build(const DeviceIndex &ix, const uint64_t *d_keys, const uint64_t *d_vals, cudaStream_t stream)
+{
+	cudaMemsetAsync(ix.tab_keys, 0xff, sizeof(uint64_t) << ix.log2cap, stream);
+	if (ix.n_keys <= 0) return 0;
+	index_insert_kernel<<<(unsigned)((ix.n_keys + 255) / 256), 256, 0, stream>>>(ix.n_keys, d_keys, d_vals, ix.tab_keys, ix.tab_vals, ix.log2cap);
+	return 1;
+}
+
+int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, const uint64_t *raw, int32_t *occ, uint64_t *hv, cudaStream_t stream)
+{
+	if (n <= 0) return 0;
+	index_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ix, n, mv, raw, occ, hv);
+	return 1;
+}
+
+int launch_sketch(const SeedArgs &s, bool write, cudaStream_t stream)
+{
+	if (s.n_tiles <= 0) return 0;
+	if (write) sketch_kernel<true><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
+	else sketch_kernel<false><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
+	return 1;
+}
+
+int launch_scan_i32(const int32_t *in, int64_t *out, int64_t n, cudaStream_t stream)
+{
+	scan_kernel<int32_t><<<1, 1024, 0, stream>>>(in, out, n);
+	return 1;
+}
+int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream)
+{
+	scan_kernel<int64_t><<<1, 1024, 0, stream>>>(in, out, n);
+	return 1;
+}
+
+int launch_read_offsets(const SeedArgs &s, cudaStream_t stream)
+{
+	read_offsets_kernel<<<(unsigned)((s.n_reads + 1 + 255) / 256), 256, 0, stream>>>(s);
+	return 1;
+}
+
+static int warp_grid(int64_t n_reads, int n_sms, int warps_per_cta)
+{
+	int64_t blocks = (n_reads + warps_per_cta - 1) / warps_per_cta;
+	const int64_t cap = (int64_t)n_sms * 16;
+	return (int)(blocks > cap ? cap : blocks < 1 ? 1 : blocks);
+}
+
+int launch_matches(const SeedArgs &s, int n_sms, cudaStream_t stream)
+{
+	if (s.n_reads <= 0) return 0;
+	matches_kernel<<<warp_grid(s.n_reads, n_sms, 8), 256, 0, stream>>>(s);
+	return 1;
+}
+
+int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream)
+{
+	if (s.n_reads <= 0) return 0;
+	expand_kernel<<<warp_grid(s.n_reads, n_sms, 8), 256, 0, stream>>>(s, ix);
+	return 1;
+}
+
+int launch_sort(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream)
+{
+	if (s.n_reads <= 0) return 0;
+	cudaMemsetAsync(s.tie_count, 0, 4 * sizeof(int), stream);
+	sort_kernel<<<warp_grid(s.n_reads, n_sms, 4), 128, 0, stream>>>(s);
+	tie_replay_kernel<<<n_sms * 4, 128, 0, stream>>>(s, ix);
+	return 2;
+}
+
+}  // namespace mm2b

@@ -44,6 +44,8 @@
 extern "C" void *kmalloc(void *km, size_t size) __attribute__((weak));
 extern "C" void kfree(void *km, void *ptr) __attribute__((weak));
 
+extern "C" void mm2b_map_backend_shutdown(void);     // host/map_backend.cpp: pooled contexts of the seeding front end
+
 namespace {
 
 using mm2b::cuda_ok;
@@ -884,6 +886,7 @@ void batcher_release(Batcher *bt, Flight *f)
 // undo whatever mm2b_init built so far (g.mu held): a failed start-up leaves no device without a worker and no thread behind
 void teardown_locked()
 {
+	mm2b_map_backend_shutdown();
 	for (Device *d : g.devs) {
 		{ std::lock_guard<std::mutex> l2(d->mu); d->stop = true; }
 		d->cv.notify_all();
@@ -1037,6 +1040,9 @@ void mm2b_shutdown(void)
 }
 
 int mm2b_num_devices(void) { return g.up ? (int)g.devs.size() : 0; }
+// (internal, for host/map_backend.cpp) CUDA id of the i-th bound device; the statistics switch
+int mm2b_device_id(int i) { return g.up && i >= 0 && i < (int)g.devs.size() ? g.devs[(size_t)i]->id : -1; }
+int mm2b_counting(void) { return g.count_cells.load(); }
 
 double mm2b_measure_host_copy(int n_threads, size_t bytes_per_thread)
 {

@@ -46,7 +46,7 @@ _ref = None
 def build(force=False):
     """Compile the oracle (and the in-place reference build when /root/reference exists)."""
     if force or not os.path.exists(LIB_ORACLE) or \
-            os.path.getmtime(LIB_ORACLE) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("chain_oracle.c", "replay.c", "chain_oracle.h")):
+            os.path.getmtime(LIB_ORACLE) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("chain_oracle.c", "replay.c", "seed_oracle.c", "chain_oracle.h")):
         subprocess.check_call(["make", "-s", "-C", HERE, "all"])
     if os.path.exists("/root/reference/chain.c"):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref", "-j8"])

@@ -21,8 +21,8 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = bld.build_all()
     assert os.path.exists(lib)
     L = ctypes.CDLL(lib)
-    names = _declared_functions(os.path.join(ROOT, "include", "mm2chain_b200.h"))
-    assert "mm_chain_dp" in names and "mm2b_chain_batch" in names and len(names) >= 23
+    names = sorted(set(_declared_functions(os.path.join(ROOT, "include", "mm2chain_b200.h")) + _declared_functions(os.path.join(ROOT, "include", "mm2seed_b200.h"))))
+    assert "mm_chain_dp" in names and "mm2b_chain_batch" in names and "mm2b_map_batch" in names and len(names) >= 31
     for n in names:
         assert hasattr(L, n), "C ABI symbol missing from the library: " + n
     binding = pkg("binding")
