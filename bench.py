@@ -254,7 +254,7 @@ def e2e_variants(torch, binding, w, steps, warmup, sync, which, keep_res=True):
         h_b, h_bi = pin(n_anchors, binding.ANCHOR), pin(n_anchors, np.int32)
         modes = {"default": ("default", 0, True, False), "index": ("index", 0, False, True),
                  "host_gather": ("b", binding.F_HOST_GATHER, True, False),
-                 "round1_format": ("b", binding.F_RAW_INPUT | binding.F_DEVICE_GATHER, True, False)}
+                 "packed_b": ("b", binding.F_DEVICE_GATHER, True, False)}
         for name in which:
             mode, flags, want_b, want_bi = modes[name]
             o = dict(bufs)
@@ -276,6 +276,62 @@ def e2e_variants(torch, binding, w, steps, warmup, sync, which, keep_res=True):
         for p in pins:
             p.free()
     return out
+
+
+def _read_fingerprints(n_a, n_u, n_v, u_flat):
+    n_u64 = np.asarray(n_u).astype(np.int64)
+    h = np.zeros(len(n_u64), np.uint64)
+    if len(u_flat):
+        starts = np.cumsum(n_u64) - n_u64
+        k = np.arange(len(u_flat), dtype=np.uint64) - np.repeat(starts, n_u64).astype(np.uint64)
+        v = np.asarray(u_flat, np.uint64) * np.uint64(0x9E3779B97F4A7C15) + (k + np.uint64(1)) * np.uint64(0xD6E8FEB86659FD93)
+        nz = np.flatnonzero(n_u64)
+        h[nz] = np.add.reduceat(v, starts[nz])
+    return h ^ (np.asarray(n_a).astype(np.uint64) << np.uint64(40)) ^ (n_u64.astype(np.uint64) << np.uint64(20)) ^ np.asarray(n_v).astype(np.uint64)
+
+
+def frontend_e2e(torch, binding, name, n_reads, seed, w, steps, warmup, cells):
+    """SURVEY 8(f) next-4 / next-1 in front of the chaining path: mm2b_map_batch — pinned ASCII read sequences in; sketch, seed hits, sort and
+    chaining on the GPU; chains (u[], b[]), rep_len and mini_pos out.  Same reads as the anchor workload, so its chains are checked against
+    the reference CLI's recorded outputs and its GCUPS counts the same reference cells."""
+    fi = BW.front_inputs(name, n_reads, seed)
+    if fi is None:
+        return None
+    t0 = time.perf_counter()
+    idx = binding.Index(fi["index"])
+    t_index = time.perf_counter() - t0
+    pin = binding.PinnedArray(max(len(fi["seq"]), 1), np.uint8)
+    try:
+        pin.array[:len(fi["seq"])] = fi["seq"]
+        par = binding.Params(**w["par"])
+        res = None
+        for _ in range(warmup):
+            res = binding.map_batch(idx, None, fi["mid_occ"], par, seq_off=fi["seq_off"], blob=pin.array, collect="u")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = binding.map_batch(idx, None, fi["mid_occ"], par, seq_off=fi["seq_off"], blob=pin.array, collect=False)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        chk = binding.map_batch(idx, None, fi["mid_occ"], par, seq_off=fi["seq_off"], blob=pin.array, collect="u")
+        ref = w["ref"]
+        # the workload recorded the reference's calls in the order its threads made them, not in read order: compare the multisets of
+        # per-read fingerprints (anchors seeded, n_u, n_v, a position-dependent hash of u[])
+        fp_gpu = _read_fingerprints(chk["n_a"], chk["n_u"], chk["n_v"], chk["u_flat"])
+        fp_ref = _read_fingerprints(np.diff(w["off"]), ref["ref_n_u"], ref["ref_n_v"], ref["ref_u"])
+        bad = int(len(fp_gpu) != len(fp_ref)) or int(np.count_nonzero(np.sort(fp_gpu) != np.sort(fp_ref)))
+        st = res["stats"]
+        return {"api": "mm2b_map_batch (include/mm2seed_b200.h): pinned ASCII read sequences in; mm_sketch, seed hits, anchor sort and chaining on the GPU; u[], b[] (16 B), rep_len and "
+                       "mini_pos out; host<->device copies inside the timed region",
+                "value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms, "reads_per_s": n_reads / (ms * 1e-3), "bases_per_s": float(len(fi["seq"])) / (ms * 1e-3),
+                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
+                "stage_ms_sum_over_subbatches": {"sketch": st["sketch_ms"], "seed": st["seed_ms"], "sort": st["sort_ms"], "chain": st["chain_ms"]},
+                "minimizers": int(st["tot_mini"]), "anchors": int(st["tot_anchors"]), "reads_with_equal_keys": int(st["n_tie_reads"]), "segments": int(st["n_segs"]),
+                "index": {"minimizers": int(len(fi["index"]["keys"])), "positions": int(len(fi["index"]["pos"])), "upload_and_build_s": t_index, "mid_occ": int(fi["mid_occ"])},
+                "parity_check": {"reads": int(n_reads), "mismatching_reads_or_entries": bad,
+                                 "checked": "multiset over reads of (anchors seeded, n_u, n_v, hash of u[]) against the reference CLI's own seeding + chaining recorded with the workload"}}
+    finally:
+        pin.free()
+        idx.close()
 
 
 def copy_ceiling(torch, devices, mbytes=512):
@@ -319,6 +375,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the asm20 / ultralong / tandem lines (N=1 only)")
+    ap.add_argument("--no-frontend", action="store_true", help="skip the seeding front end line (N=1 only)")
     ap.add_argument("--strong-reads", type=int, default=0, help="additionally chain this many reads in ONE in-process call over all --gpus devices (BASELINE configs[4]: 1000000)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -404,7 +461,7 @@ def main():
     value = tot_cells / (ms_value * 1e-3) / 1e9
 
     # ---- e2e: pinned host buffers through the host-buffer batch call, one process per GPU ------------------------
-    ev = e2e_variants(torch, binding, w, args.steps, args.warmup, barrier, ["default", "index", "host_gather", "round1_format"] if world == 1 else ["default", "index"])
+    ev = e2e_variants(torch, binding, w, args.steps, args.warmup, barrier, ["default", "index", "host_gather", "packed_b"] if world == 1 else ["default", "index"])
     ms_e2e = {k: max_over_ranks(v["ms"]) for k, v in ev.items()}
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (value and e2e)
     est = ev["default"]["stats"]
@@ -417,11 +474,11 @@ def main():
                 "stage_ms_sum_over_subbatches_rank0": {"h2d": s.h2d_ms, "kernels": s.kernel_ms, "d2h": s.d2h_ms, "host_pack": s.pack_ms, "host_gather": s.gather_ms},
                 "subbatches_rank0": {"packed": int(s.n_packed_subs), "raw": int(s.n_raw_subs)}}
 
-    apis = {"default": "mm2b_chain_batch: pinned mm128_t anchors in, u[] and b[] (mm128_t) out; inside the call the library packs the input to 8 B/anchor on its helper threads, "
-                       "receives 4-byte indices and gathers b[] on the host",
-            "index": "mm2b_chain_batch_ex with bi[]: same input path, the chained anchors come back as int32 indices into the caller's a[] (no b[] gather)",
+    apis = {"default": "mm2b_chain_batch: pinned mm128_t anchors in (16 B/anchor over PCIe), u[] and b[] (mm128_t, gathered on the device) out",
+            "index": "mm2b_chain_batch_ex with bi[] (what the product's own callers use: mm_chain_dp's batcher and the phase-split caller hold a[]): input packed to 8 B/anchor by the "
+                     "library's helper threads, chained anchors back as int32 indices",
             "host_gather": "mm2b_chain_batch_ex(MM2B_F_HOST_GATHER): packed input, int32 indices over PCIe, b[] gathered from the caller's a[] by the library's helper threads",
-            "round1_format": "mm2b_chain_batch_ex(MM2B_F_RAW_INPUT | MM2B_F_DEVICE_GATHER): 16 B/anchor in, 16 B/chained anchor out (round 1's transfer format)"}
+            "packed_b": "mm2b_chain_batch_ex(MM2B_F_DEVICE_GATHER): packed input, b[] as 16-byte anchors from the device"}
     e2e = e2e_obj("default", apis["default"])
     e2e["variants"] = {k: e2e_obj(k, apis[k]) for k in ev if k != "default"}
     e2e["host_threads"] = "helper pool of the library (MM2B_HOST_THREADS, default min(cores-2, 16)) + 1 worker per device"
@@ -460,6 +517,14 @@ def main():
         cpu = {"value": r["value"], "unit": "GCUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "reads_per_s": r["reads_per_s"]}
         if r["reads"] == n_reads:
             assert r["cells"] == cells, "GPU cell tally %d != oracle %d" % (cells, r["cells"])
+
+    # ---- the seeding front end in front of the same reads (N=1 only) ------------------------------------------------------
+    front = None
+    if rank == 0 and world == 1 and args.workload == "map-ont" and w["ref"] is not None and not args.no_frontend:
+        try:
+            front = frontend_e2e(torch, binding, args.workload, args.reads, 1000, w, min(args.steps, 5), 2, cells)
+        except Exception as e:      # noqa: BLE001
+            front = {"error": repr(e)[:300]}
 
     # ---- the other configurations of BASELINE.json, inside the same line (N=1 only) -------------------------------
     others = None
@@ -525,7 +590,7 @@ def main():
                                                 "integer operations (profiles/int32_peak_sass.txt); achieved = 30 algorithmic ops x reference cells / kernel time",
                                    "ncu_capture": None if not cap else {k: cap[k] for k in ("issue_slots_busy_pct", "alu_pipe_pct", "fma_pipe_pct", "warp_instr_per_anchor", "file") if k in cap},
                                    "peak_source": "measured live: mm2b_measure_int32_peak"},
-                "cpu_baseline": cpu, "other_workloads": others, "e2e_per_process": None, "strong_scaling": strong, "workload_gen_s": w["gen_s"], "host_affinity_rank0": affinity}
+                "cpu_baseline": cpu, "frontend": front, "other_workloads": others, "e2e_per_process": None, "strong_scaling": strong, "workload_gen_s": w["gen_s"], "host_affinity_rank0": affinity}
         if multi is not None:        # N > 1: the headline e2e is the library's own multi-device call; the one-process-per-GPU number stays beside it
             line["e2e_per_process"] = e2e
             m = multi["default"]

@@ -208,7 +208,9 @@ def real_seed_batch(name, n_reads, seed, threads=None, verbose=False):
                 np.save(os.path.join(d, k + ".npy"), w[k])
             meta = dict(preset=name, reads_requested=n_reads, calls_recorded=len(w["off"]) - 1, anchors=int(w["off"][-1]), seed=seed, par=list(w["par"]),
                         cli=" ".join(["minimap2-sw"] + PRESETS[name][2]), paf_md5=paf_md5, paf_lines=paf_lines, simulate_s=round(t_sim, 1), seed_and_chain_s=round(t_map, 1))
-            os.remove(dump), os.remove(q)
+            os.remove(dump)
+            if name != "map-ont":           # map-ont keeps its reads: the seeding front end's bench line maps the sequences themselves
+                os.remove(q)
             json.dump(meta, open(os.path.join(d, "meta.json"), "w"))
     meta = json.load(open(os.path.join(d, "meta.json")))
     out = {k: np.load(os.path.join(d, k + ".npy")) for k in ("off", "a", "ref_n_u", "ref_n_v", "ref_u", "ref_b_hash")}
@@ -217,6 +219,41 @@ def real_seed_batch(name, n_reads, seed, threads=None, verbose=False):
     if verbose:
         print("[bench_workloads] %s: %s" % (key, meta), file=sys.stderr, flush=True)
     return out
+
+
+SEED_TOOL = os.path.join(ROOT, "oracle", "_ref", "mm2-seed-ref")
+
+
+def front_inputs(name, n_reads, seed, threads=None):
+    """Inputs of the seeding front end for the same reads real_seed_batch(name, n_reads, seed) recorded: dict(seq_off, seq (uint8), index
+    (flat arrays as the product's mm2b_index_flatten writes them, via oracle/_ref/mm2-seed-ref), mid_occ) — or None when the reads were
+    not kept or the tool is missing."""
+    threads = threads or os.cpu_count() or 1
+    d = os.path.join(CACHE, "%s_r%d_s%d" % (name, n_reads, seed))
+    q = os.path.join(d, "reads.fa")
+    if not (os.path.exists(q) and os.path.exists(SEED_TOOL)):
+        return None
+    seqsim = load_package("seqsim")
+    fa, mmi = _reference_files(name, seqsim, threads)
+    flat = mmi + ".flat"
+    with _Lock(mmi + ".flat.lock"):
+        if not os.path.exists(flat):
+            empty = os.path.join(CACHE, "empty.fa")
+            open(empty, "w").close()
+            subprocess.run([SEED_TOOL, PRESETS[name][2][1], mmi, empty, flat + ".seeds", flat + ".tmp"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            os.replace(flat + ".tmp", flat)
+    from oracle import seed_py
+    idx = seed_py.read_index(flat)
+    buf = np.fromfile(q, dtype=np.uint8)
+    nl = np.flatnonzero(buf == 10)                    # two lines per read: >name, sequence
+    starts, ends = nl[0::2] + 1, nl[1::2]
+    lens = (ends - starts).astype(np.int64)
+    seq_off = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=seq_off[1:])
+    seq = np.empty(int(seq_off[-1]), np.uint8)
+    for i in range(len(lens)):                        # (slice copies: the name lines and newlines stay behind)
+        seq[seq_off[i]:seq_off[i + 1]] = buf[starts[i]:ends[i]]
+    return dict(seq_off=seq_off, seq=seq, index=idx, mid_occ=idx["mid_occ"])
 
 
 if __name__ == "__main__":

@@ -85,7 +85,13 @@ int mm2b_abi_version(void);
 
 /* Pinned host memory for batch inputs/outputs (H2D/D2H run at PCIe speed only from pinned pages). */
 void *mm2b_host_alloc(size_t bytes);
-void mm2b_host_free(void *p);
+void mm2b_host_free(void *p);               /* the block goes back to the library's pool (released by mm2b_shutdown) */
+/* Fill that pool ahead of time with n_blocks blocks of `bytes` (pinning memory is slow: ~0.5 ms per MB); mm2b_host_pool_trim empties it. */
+void mm2b_host_reserve(size_t bytes, int n_blocks);
+void mm2b_host_pool_trim(void);
+/* After the devices are up (mm2b_init_async), reserve on the same background thread the pinned staging that mapping mini-batches of
+ * about `seq_bytes` of read sequence will ask for (mm2seed_b200.h), so that the first mini-batch does not pay for it. */
+void mm2b_reserve_for_mapping(size_t seq_bytes);
 
 /* ---- batch chaining, host buffers (the end-to-end path) ------------------------------------------------------- */
 
@@ -116,8 +122,9 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
  *           MM2B_F_DEVICE_GATHER  b[] comes back from the device as 16-byte anchors (the default when only b is asked for).
  *           MM2B_F_HOST_GATHER    b[] is gathered on the host's helper threads from 4-byte indices (pays off only where host
  *                                 memory bandwidth is plentiful compared with the PCIe link).
- * Environment overrides of the defaults of mm2b_chain_batch (tuning): MM2B_PACK=0|1, MM2B_PACK_INFLIGHT=n, MM2B_GATHER=host|device,
- * MM2B_HOST_THREADS=n. */
+ * mm2b_chain_batch itself (b[] out as anchors) sends the input raw and gathers on the device: with 16 B per chained anchor coming back the
+ * host's memory system is busy enough, and packing next to it measured slower.  Environment overrides (tuning): MM2B_PACK=1 (pack there
+ * too), MM2B_PACK_INFLIGHT=n, MM2B_GATHER=host|device, MM2B_HOST_THREADS=n. */
 enum { MM2B_F_RAW_INPUT = 1, MM2B_F_DEVICE_GATHER = 2, MM2B_F_HOST_GATHER = 4 };
 int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
                         int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,

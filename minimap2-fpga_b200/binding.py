@@ -18,7 +18,7 @@ ANCHOR = np.dtype([("x", "<u8"), ("y", "<u8")])
 READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 
 EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version", "mm2b_ws_set_longest_read",
-           "mm2b_host_alloc", "mm2b_host_free", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
+           "mm2b_host_alloc", "mm2b_host_free", "mm2b_host_reserve", "mm2b_host_pool_trim", "mm2b_reserve_for_mapping", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
            "mm2b_chain_batch_device", "mm2b_chain_batch_device_idx", "mm2b_chain_batch_ex", "mm2b_unpack_anchors_device", "mm2b_pack_anchors", "mm2b_measure_host_copy", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",
            "mm_chain_dp",
@@ -454,21 +454,41 @@ def seed_debug(index, seqs, max_occ):
     return out
 
 
-def map_batch(index, seqs, max_occ, par=None, seq_off=None, blob=None):
-    """mm2b_map_batch: read sequences in, chains out.  seqs: list of bytes (or pass seq_off + blob).  Returns a dict of per-read
-    arrays plus lists `u`, `b`, `mini_pos` (one numpy array per read) when `seqs` is small, and the call's totals in `stats`."""
+def map_batch(index, seqs, max_occ, par=None, seq_off=None, blob=None, collect=True):
+    """mm2b_map_batch: read sequences in, chains out.  seqs: list of bytes (or pass seq_off + blob, a bytes object or a uint8 array).
+    Returns a dict of per-read arrays, the call's totals in `stats` and — with collect=True — lists `u`, `b`, `mini_pos` (one numpy
+    array per read; for small batches) or — with collect="u" — all u[] entries in read order as one array."""
     L = load()
     if seq_off is None:
         seq_off, blob = _seq_batch(seqs)
     par = par or Params()
     sp = SeedParams(max_occ, 0)
     res = C.POINTER(MapResult)()
-    _check(L.mm2b_map_batch(index.h, C.byref(sp), C.byref(par), len(seq_off) - 1, _p(seq_off), blob, C.byref(res)), "mm2b_map_batch")
+    blob_p = blob if isinstance(blob, (bytes, bytearray)) or blob is None else blob.ctypes.data_as(C.c_void_p)
+    _check(L.mm2b_map_batch(index.h, C.byref(sp), C.byref(par), len(seq_off) - 1, _p(seq_off), blob_p, C.byref(res)), "mm2b_map_batch")
     r = res.contents
     n = int(r.n_reads)
     out = {k: np.ctypeslib.as_array(getattr(r, k), (n,)).copy() if n else np.empty(0, np.int64) for k in ("status", "n_u", "n_v", "rep_len", "n_mini_pos", "n_mini", "seg", "n_a", "u_off", "b_off", "mp_off")}
     out["stats"] = {k: getattr(r, k) for k in ("tot_mini", "tot_anchors", "tot_chains", "tot_chained", "n_tie_reads", "h2d_bytes", "d2h_bytes", "sketch_ms", "seed_ms", "sort_ms", "chain_ms", "cells_ref")}
     out["stats"]["n_segs"] = int(r.n_segs)
+    if collect == "u":                                  # every u[] entry in read order (segment by segment, vectorised)
+        parts = []
+        n_u, seg, u_off = out["n_u"].astype(np.int64), out["seg"], out["u_off"]
+        for sg in range(int(r.n_segs)):
+            sel = np.flatnonzero(seg == sg)
+            cnt = n_u[sel]
+            tot = int(cnt.sum())
+            if not tot:
+                continue
+            hi = int((u_off[sel] + cnt).max())
+            arr = _take(r.seg_u[sg], np.uint64, hi)
+            idx = np.repeat(u_off[sel] - (np.cumsum(cnt) - cnt), cnt) + np.arange(tot)
+            parts.append(arr[idx])
+        out["u_flat"] = np.concatenate(parts) if parts else np.empty(0, np.uint64)
+        collect = False
+    if not collect:
+        L.mm2b_map_result_release(res)
+        return out
     u, b, mp = [], [], []
     for i in range(n):
         s = int(out["seg"][i])

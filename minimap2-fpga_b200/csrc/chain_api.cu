@@ -3,6 +3,10 @@
 #include "chain_kernels.cuh"
 #include "shim_internal.h"
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
+#include <vector>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -11,6 +15,10 @@ namespace mm2b {
 
 static thread_local char g_err[512];
 static std::atomic<int64_t> g_launches{0};
+static std::mutex g_pin_mu;
+static std::vector<std::pair<size_t, void*>> g_pin_free;        // pooled pinned blocks: (bytes, pointer)
+static std::unordered_map<void*, size_t> g_pin_size;            // every live block handed out by mm2b_host_alloc
+static size_t g_pin_pooled = 0, g_pin_pool_max = (size_t)16 << 30;
 
 void set_error(const char *fmt, const char *a, const char *b)
 {
@@ -62,13 +70,66 @@ int mm2b_cuda_device_count(void)
 	return n;
 }
 
+// Pinned host memory comes from a small pool: cudaHostAlloc costs about half a millisecond per megabyte on the hosts measured, which
+// is more than the whole GPU side of a mini-batch, so blocks are kept when they are freed and handed out again (best fit, at most
+// twice the size asked for), and mm2b_host_reserve can fill the pool ahead of time on a background thread.
 void *mm2b_host_alloc(size_t bytes)
 {
+	if (bytes == 0) bytes = 1;
+	{
+		std::lock_guard<std::mutex> lk(g_pin_mu);
+		size_t best = (size_t)-1;
+		for (size_t i = 0; i < g_pin_free.size(); ++i)
+			if (g_pin_free[i].first >= bytes && g_pin_free[i].first <= 2 * bytes + (1u << 20) && (best == (size_t)-1 || g_pin_free[i].first < g_pin_free[best].first)) best = i;
+		if (best != (size_t)-1) {
+			void *p = g_pin_free[best].second;
+			g_pin_pooled -= g_pin_free[best].first;
+			g_pin_free.erase(g_pin_free.begin() + (long)best);
+			return p;
+		}
+	}
 	void *p = 0;
-	if (!cuda_ok(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable), "cudaHostAlloc")) return 0;
+	if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocPortable), "cudaHostAlloc")) return 0;
+	std::lock_guard<std::mutex> lk(g_pin_mu);
+	g_pin_size[p] = bytes;
 	return p;
 }
-void mm2b_host_free(void *p) { if (p) cudaFreeHost(p); }
+void mm2b_host_free(void *p)
+{
+	if (!p) return;
+	{
+		std::lock_guard<std::mutex> lk(g_pin_mu);
+		auto it = g_pin_size.find(p);
+		if (it != g_pin_size.end() && g_pin_pooled + it->second <= g_pin_pool_max) {
+			g_pin_free.push_back(std::make_pair(it->second, p));
+			g_pin_pooled += it->second;
+			return;
+		}
+		if (it != g_pin_size.end()) g_pin_size.erase(it);
+	}
+	cudaFreeHost(p);
+}
+void mm2b_host_reserve(size_t bytes, int n_blocks)
+{
+	std::vector<void*> got;
+	for (int i = 0; i < n_blocks; ++i) {
+		void *p = 0;
+		if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) break;
+		{ std::lock_guard<std::mutex> lk(g_pin_mu); g_pin_size[p] = bytes ? bytes : 1; }
+		got.push_back(p);
+	}
+	for (void *p : got) mm2b_host_free(p);
+}
+void mm2b_host_pool_trim(void)
+{
+	std::vector<void*> blocks;
+	{
+		std::lock_guard<std::mutex> lk(g_pin_mu);
+		for (auto &b : g_pin_free) blocks.push_back(b.second), g_pin_size.erase(b.second);
+		g_pin_free.clear(), g_pin_pooled = 0;
+	}
+	for (void *p : blocks) cudaFreeHost(p);
+}
 
 mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_reads)
 {

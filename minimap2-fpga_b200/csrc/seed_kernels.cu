@@ -89,20 +89,10 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 	__shared__ uint32_t badw[TILE_SPAN / 32];               // one bit per position: ambiguous base or outside the read
 	__shared__ uint8_t zs[TILE_SPAN];                       // strand of the position's k-mer
 	__shared__ int warp_sum[SKETCH_TILE / 32];
-	__shared__ int read_of_tile;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) {                                         // which read this tile belongs to: last r with tile_off[r] <= blockIdx.x
-		int lo = 0, hi = (int)s.n_reads - 1;
-		while (lo < hi) {
-			const int mid = (lo + hi + 1) >> 1;
-			if (s.tile_off[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-		}
-		read_of_tile = lo;
-		pk[TILE_SPAN / 32] = 0;
-	}
-	__syncthreads();
-	const int r = read_of_tile;
+	if (tid == 0) pk[TILE_SPAN / 32] = 0;
+	const int r = s.tile_read[blockIdx.x];                  // which read this tile belongs to (filled by the host with the offsets)
 	const int64_t so = s.seq_off[r];
 	const int L = (int)(s.seq_off[r + 1] - so);
 	const int t0 = ((int)blockIdx.x - s.tile_off[r]) * SKETCH_TILE;
@@ -358,12 +348,12 @@ __global__ void __launch_bounds__(256) matches_kernel(const SeedArgs s)
 // ---------------------------------------------------------------------------------------------------------------
 // collect_seed_hits (map.c:215-247): anchors of one read, written by its warp in the reference's order (match by match)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void expand_read(const SeedArgs &s, const DeviceIndex &ix, int64_t r, int lane)
+__device__ void expand_read(const SeedArgs &s, const DeviceIndex &ix, int64_t r, int lane, ulonglong2 *dst)
 {
 	const int64_t m0 = s.mv_off[r];
 	const int n = (int)(s.mv_off[r + 1] - m0);
 	const int qlen = (int)(s.seq_off[r + 1] - s.seq_off[r]);
-	ulonglong2 *a = s.a + s.a_off[r];
+	ulonglong2 *a = dst + s.a_off[r];
 	for (int base = 0; base < n; base += 32) {
 		const int i = base + lane;
 		int t = 0, rel = -1;
@@ -404,7 +394,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const SeedArgs s, const Dev
 {
 	const int lane = threadIdx.x & 31;
 	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-	for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < s.n_reads; r += n_warps) expand_read(s, ix, r, lane);
+	for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < s.n_reads; r += n_warps) expand_read(s, ix, r, lane, s.a_tmp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -469,21 +459,32 @@ __device__ void warp_sort_by_x(ulonglong2 *keys, ulonglong2 *tmp, int n, int *hi
 	__syncwarp();
 }
 
-__global__ void __launch_bounds__(128) sort_kernel(const SeedArgs s)
+// The expansion leaves a read's anchors in a_tmp; the sorted read is written to a.  Reads of up to SORT_SMEM anchors — all but the
+// longest — are sorted inside shared memory: the keys are loaded once, a 16-bit index per anchor is what the radix passes move, and
+// the 16-byte records are gathered once at the end.  Longer reads take the global-memory sort above.
+constexpr int SORT_SMEM = 1024;
+constexpr int SORT_WARPS = 2;
+
+__global__ void __launch_bounds__(SORT_WARPS * 32) sort_kernel(const SeedArgs s)
 {
-	__shared__ int hist[4][256];
+	__shared__ uint64_t xs_all[SORT_WARPS][SORT_SMEM];
+	__shared__ uint16_t idx_all[SORT_WARPS][2][SORT_SMEM];
+	__shared__ int hist_all[SORT_WARPS][256];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint64_t *xs = xs_all[warp];
+	int *hist = hist_all[warp];
 	for (;;) {
 		int r = 0;
 		if (lane == 0) r = atomicAdd(&s.tie_count[1], 1);
 		r = __shfl_sync(FULL, r, 0);
 		if (r >= s.n_reads) break;
 		const int64_t o = s.a_off[r], n64 = s.a_off[r + 1] - o;
-		if (n64 < 2) continue;
+		if (n64 <= 0) continue;
 		const int n = (int)n64;
+		const ulonglong2 *src = s.a_tmp + o;
 		ulonglong2 *a = s.a + o;
 		if (n <= 32) {                                      // one key per lane: rank by (x, position)
-			const ulonglong2 rec = lane < n ? a[lane] : make_ulonglong2(EMPTY, 0);
+			const ulonglong2 rec = lane < n ? src[lane] : make_ulonglong2(EMPTY, 0);
 			int rank = 0;
 			bool tie = false;
 			for (int q = 0; q < n; ++q) {
@@ -491,29 +492,185 @@ __global__ void __launch_bounds__(128) sort_kernel(const SeedArgs s)
 				rank += xq < rec.x || (xq == rec.x && q < lane);
 				tie |= q != lane && xq == rec.x;
 			}
-			__syncwarp();
 			if (lane < n) a[rank] = rec;
 			const bool any_tie = __any_sync(FULL, lane < n && tie);
 			if (any_tie && lane == 0) s.tie_list[atomicAdd(&s.tie_count[0], 1)] = r;
 			__syncwarp();
 			continue;
 		}
-		warp_sort_by_x(a, s.a_tmp + o, n, hist[warp], lane);
 		bool tie = false;
-		for (int k = lane; k + 1 < n; k += 32) tie |= a[k].x == a[k + 1].x;
+		if (n <= SORT_SMEM) {
+			uint16_t *ia = idx_all[warp][0], *ib = idx_all[warp][1];
+			uint64_t diff = 0;
+			const uint64_t k0 = src[0].x;
+			for (int k = lane; k < n; k += 32) {
+				const uint64_t x = src[k].x;
+				xs[k] = x, ia[k] = (uint16_t)k, diff |= x ^ k0;
+			}
+#pragma unroll
+			for (int d = 16; d; d >>= 1) diff |= __shfl_xor_sync(FULL, diff, d);
+			__syncwarp();
+			for (int shift = 0; shift < 64; shift += 8) {
+				if (((diff >> shift) & 0xff) == 0) continue;
+				for (int b = lane; b < 256; b += 32) hist[b] = 0;
+				__syncwarp();
+				for (int base = 0; base < n; base += 32) {
+					const int k = base + lane;
+					const int dig = k < n ? (int)(xs[ia[k]] >> shift & 0xff) : 256;
+					const unsigned peers = __match_any_sync(FULL, dig);
+					if (k < n && (peers & lanemask_lt(lane)) == 0) hist[dig] += __popc(peers);
+					__syncwarp();
+				}
+				{
+					int loc[8], sum = 0;
+#pragma unroll
+					for (int q = 0; q < 8; ++q) loc[q] = hist[lane * 8 + q], sum += loc[q];
+					int incl = sum;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const int v = __shfl_up_sync(FULL, incl, d);
+						if (lane >= d) incl += v;
+					}
+					int run = incl - sum;
+#pragma unroll
+					for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = run, run += loc[q];
+				}
+				__syncwarp();
+				for (int base = 0; base < n; base += 32) {
+					const int k = base + lane;
+					const bool act = k < n;
+					const uint16_t id = act ? ia[k] : 0;
+					const int dig = act ? (int)(xs[id] >> shift & 0xff) : 256;
+					const unsigned peers = __match_any_sync(FULL, dig);
+					const int rank = __popc(peers & lanemask_lt(lane));
+					int pos = 0;
+					if (act) pos = hist[dig] + rank;
+					__syncwarp();
+					if (act) {
+						ib[pos] = id;
+						if (rank == 0) hist[dig] += __popc(peers);
+					}
+					__syncwarp();
+				}
+				uint16_t *t = ia; ia = ib; ib = t;
+			}
+			for (int k = lane; k < n; k += 32) {
+				const int id = ia[k];
+				a[k] = src[id];
+				if (k + 1 < n) tie |= xs[id] == xs[ia[k + 1]];
+			}
+		} else {
+			for (int k = lane; k < n; k += 32) a[k] = src[k];
+			__syncwarp();
+			warp_sort_by_x(a, s.a_tmp + o, n, hist, lane);
+			for (int k = lane; k + 1 < n; k += 32) tie |= a[k].x == a[k + 1].x;
+		}
 		__syncwarp();
 		if (__any_sync(FULL, tie) && lane == 0) s.tie_list[atomicAdd(&s.tie_count[0], 1)] = r;
 		__syncwarp();
 	}
 }
 
-// Reads with equal keys: expand again (the sort above was in place) and replay radix_sort_128x itself — insertion sort up to 64
-// elements, else the in-place MSD byte radix permutation (ksort.h:116-151) — on one lane.  Rare for reads against a unique
-// reference (a minimizer has to repeat inside the query); the rule for tandem repeats.
-__global__ void __launch_bounds__(128) tie_replay_kernel(const SeedArgs s, const DeviceIndex ix)
+// Reads with equal keys: expand again, this time straight into a[], and replay radix_sort_128x itself — insertion sort up to 64
+// elements, else the in-place MSD byte radix permutation (ksort.h:116-151).  Rare for reads against a unique reference (a minimizer
+// has to repeat inside the query); the rule for tandem repeats.  The permutation of one level is a chain of dependent swaps and
+// stays on one lane, but everything around it is done by the warp: the digit counts (match-any histogram), the bucket offsets,
+// the insertion sorts of the small buckets (every lane takes the buckets of its 8 digits: the ranges are disjoint), and levels on
+// which every key has the same digit are skipped outright (nothing would move).  Reads of up to REPLAY_SMEM anchors are replayed
+// in shared memory, where a dependent access costs tens of cycles instead of hundreds.
+constexpr int REPLAY_SMEM = 2048;
+constexpr int REPLAY_WORK = 64;                 // pending ranges of a read held in shared memory (a range has > 64 elements)
+
+__device__ void warp_replay_sort(W16 *w, int n, int *sm /* 768 ints */, int3 *work, int work_cap, int lane)
 {
-	__shared__ int sm[4][768];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int *head = sm, *tail = sm + 256, *cnt = sm + 512;
+	if (n <= 64) {
+		if (lane == 0) insertion_by_x(w, n);
+		__syncwarp();
+		return;
+	}
+	int n_work = 1;
+	if (lane == 0) work[0] = make_int3(0, n, 56);
+	__syncwarp();
+	while (n_work > 0) {
+		const int3 job = work[--n_work];
+		__syncwarp();
+		W16 *a = w + job.x;
+		const int m = job.y, shift = job.z;
+		for (int b = lane; b < 256; b += 32) cnt[b] = 0;
+		__syncwarp();
+		for (int base = 0; base < m; base += 32) {
+			const int k = base + lane;
+			const int dig = k < m ? (int)(a[k].x >> shift & 0xff) : 256;
+			const unsigned peers = __match_any_sync(FULL, dig);
+			if (k < m && (peers & lanemask_lt(lane)) == 0) cnt[dig] += __popc(peers);
+			__syncwarp();
+		}
+		int loc[8], sum = 0;
+		bool one = false;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) loc[q] = cnt[lane * 8 + q], sum += loc[q], one |= loc[q] == m;
+		int incl = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int v = __shfl_up_sync(FULL, incl, d);
+			if (lane >= d) incl += v;
+		}
+		int run = incl - sum;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) head[lane * 8 + q] = run, run += loc[q], tail[lane * 8 + q] = run;
+		const bool one_bucket = __any_sync(FULL, one);
+		__syncwarp();
+		if (!one_bucket && lane == 0) {                   // ksort.h:131-143, verbatim in effect
+			for (int k = 0; k < 256;) {
+				if (head[k] == tail[k]) { ++k; continue; }
+				int l = (int)(a[head[k]].x >> shift & 0xff);
+				if (l == k) { ++head[k]; continue; }
+				W16 carry = a[head[k]];
+				do {
+					const W16 out = a[head[l]];
+					a[head[l]++] = carry;
+					carry = out;
+					l = (int)(carry.x >> shift & 0xff);
+				} while (l != k);
+				a[head[k]++] = carry;
+			}
+		}
+		__syncwarp();
+		if (shift) {                                      // ksort.h:145-150: recurse into buckets > 64, insertion-sort the others
+			const int next = shift > 8 ? shift - 8 : 0;
+			int big = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) big += loc[q] > 64;
+			int bincl = big;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int v = __shfl_up_sync(FULL, bincl, d);
+				if (lane >= d) bincl += v;
+			}
+			int slot = n_work + bincl - big;
+			const int n_big = __shfl_sync(FULL, bincl, 31);
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				const int c = loc[q], beg = tail[lane * 8 + q] - c;
+				if (c > 64) {
+					if (slot < work_cap) work[slot] = make_int3(job.x + beg, c, next);
+					else insertion_by_x(a + beg, c);          // unreachable: work_cap >= n / 65 + 1 pending ranges always fit
+					++slot;
+				} else if (c > 1) insertion_by_x(a + beg, c);
+			}
+			n_work += n_big < work_cap - n_work ? n_big : work_cap - n_work;
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(32) tie_replay_kernel(const SeedArgs s, const DeviceIndex ix)
+{
+	__shared__ __align__(16) W16 buf[REPLAY_SMEM];
+	__shared__ int sm[768];
+	__shared__ int3 work_s[REPLAY_WORK];
+	const int lane = threadIdx.x & 31;
 	int n_tie = 0;
 	if (lane == 0) n_tie = s.tie_count[0];
 	n_tie = __shfl_sync(FULL, n_tie, 0);
@@ -523,15 +680,17 @@ __global__ void __launch_bounds__(128) tie_replay_kernel(const SeedArgs s, const
 		slot = __shfl_sync(FULL, slot, 0);
 		if (slot >= n_tie) break;
 		const int r = s.tie_list[slot];
-		expand_read(s, ix, r, lane);
+		expand_read(s, ix, r, lane, s.a);
 		__syncwarp();
 		const int64_t o = s.a_off[r];
 		const int n = (int)(s.a_off[r + 1] - o);
-		if (lane == 0) {
-			W16 *w = (W16*)(s.a + o);
-			if (n <= 64) insertion_by_x(w, n);
-			else flag_sort_by_x_lane0(w, n, sm[warp], (int3*)(s.a_tmp + o), (int)((int64_t)n * 16 / (int64_t)sizeof(int3)));
-		}
+		W16 *w = (W16*)(s.a + o);
+		if (n <= REPLAY_SMEM) {
+			for (int k = lane; k < n; k += 32) buf[k] = w[k];
+			__syncwarp();
+			warp_replay_sort(buf, n, sm, work_s, REPLAY_WORK, lane);
+			for (int k = lane; k < n; k += 32) w[k] = buf[k];
+		} else warp_replay_sort(w, n, sm, (int3*)(s.a_tmp + o), (int)((int64_t)n * 16 / (int64_t)sizeof(int3)), lane);
 		__syncwarp();
 	}
 }
@@ -606,8 +765,8 @@ int launch_sort(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_
 {
 	if (s.n_reads <= 0) return 0;
 	cudaMemsetAsync(s.tie_count, 0, 4 * sizeof(int), stream);
-	sort_kernel<<<warp_grid(s.n_reads, n_sms, 4), 128, 0, stream>>>(s);
-	tie_replay_kernel<<<n_sms * 4, 128, 0, stream>>>(s, ix);
+	sort_kernel<<<warp_grid(s.n_reads, n_sms, SORT_WARPS), SORT_WARPS * 32, 0, stream>>>(s);
+	tie_replay_kernel<<<n_sms * 4, 32, 0, stream>>>(s, ix);
 	return 2;
 }
 

@@ -27,6 +27,7 @@ struct SeedArgs {
 	const uint8_t *seq;         // concatenated ASCII bases
 	const int64_t *seq_off;     // [n_reads + 1]
 	const int32_t *tile_off;    // [n_reads + 1] first sketch tile of every read
+	const int32_t *tile_read;   // [n_tiles] the read every tile belongs to
 	int32_t n_tiles;
 	int k, w, max_occ;
 	// sketch

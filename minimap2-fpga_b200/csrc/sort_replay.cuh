@@ -37,8 +37,9 @@ __device__ void flag_sort_by_x_lane0(W16 *w, int n, int *sm /* >= 768 ints */, i
 		const int m = job.y, shift = job.z;
 		for (int k = 0; k < 256; ++k) cnt[k] = 0;
 		for (int i = 0; i < m; ++i) ++cnt[(int)(a[i].x >> shift & 0xff)];
-		for (int k = 0, acc = 0; k < 256; ++k) head[k] = acc, acc += cnt[k], tail[k] = acc;
-		for (int k = 0; k < 256;) {
+		bool one_bucket = false;                        // every key shares this byte: the permutation below would move nothing
+		for (int k = 0, acc = 0; k < 256; ++k) head[k] = acc, acc += cnt[k], tail[k] = acc, one_bucket |= cnt[k] == m;
+		for (int k = one_bucket ? 256 : 0; k < 256;) {
 			if (head[k] == tail[k]) { ++k; continue; }
 			int l = (int)(a[head[k]].x >> shift & 0xff);
 			if (l == k) { ++head[k]; continue; }

@@ -911,6 +911,7 @@ void teardown_locked()
 	g_batchers.clear();
 	g.pool.shutdown();
 	for (auto &e : g.trace_ev0) if (e) { cudaEventDestroy(e); e = nullptr; }
+	mm2b_host_pool_trim();
 	g.up = false;
 }
 
@@ -1001,6 +1002,17 @@ int mm2b_init(int n_devices, const int *devices)
 static std::thread &g_init_thread = *new std::thread();
 static std::mutex g_init_mu;
 static int g_init_rc = MM2B_OK;
+static std::atomic<size_t> g_reserve_seq_bytes{0};
+
+static void reserve_for_mapping_now(size_t seq_bytes)
+{
+	if (seq_bytes == 0) return;
+	// what host/map_batch.cpp and host/map_backend.cpp will ask for: one block for the staged sequences, and per sub-batch of
+	// sequence (MM2B_MAP_SUB_BYTES, 96 MB) the chained anchors (~0.6 B per base) and mini_pos (~0.75 B per base) coming back
+	const size_t sub = (size_t)96 << 20;
+	mm2b_host_reserve(seq_bytes + seq_bytes / 8 + 4096, 1);
+	mm2b_host_reserve(sub, 2 * (int)((seq_bytes + sub - 1) / sub) + 2);
+}
 
 int mm2b_init_async(int n_devices, const int *devices)
 {
@@ -1013,8 +1025,18 @@ int mm2b_init_async(int n_devices, const int *devices)
 	}
 	std::vector<int> ids;
 	if (n_devices > 0 && devices) ids.assign(devices, devices + n_devices);
-	g_init_thread = std::thread([n_devices, ids] { g_init_rc = mm2b_init(n_devices, ids.empty() ? nullptr : ids.data()); });
+	g_init_thread = std::thread([n_devices, ids] {
+		g_init_rc = mm2b_init(n_devices, ids.empty() ? nullptr : ids.data());
+		if (g_init_rc == MM2B_OK) reserve_for_mapping_now(g_reserve_seq_bytes.exchange(0));
+	});
 	return MM2B_OK;
+}
+
+void mm2b_reserve_for_mapping(size_t seq_bytes)
+{
+	std::lock_guard<std::mutex> lk(g_init_mu);
+	if (g_init_thread.joinable()) { g_reserve_seq_bytes.store(seq_bytes); return; }     // picked up when the devices are up
+	if (g.up) reserve_for_mapping_now(seq_bytes);
 }
 
 static int ensure_up(void)
@@ -1145,7 +1167,13 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
                      int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,
                      uint64_t *u, int64_t u_cap, mm2b_anchor_t *b, int64_t b_cap, mm2b_stats_t *stats)
 {
-	const unsigned flags = (g.default_pack ? 0u : (unsigned)MM2B_F_RAW_INPUT) | (g.default_device_gather ? (unsigned)MM2B_F_DEVICE_GATHER : (unsigned)MM2B_F_HOST_GATHER);
+	// b[] wanted as 16-byte anchors: the copy back (16 B per chained anchor) already loads the host's memory system, and packing the
+	// input next to it made the call slower and erratic on the hosts measured (20-33 ms per 100k reads packed against 23-24 ms raw,
+	// profiles/r2b_e2e_sweep.txt, profiles/r2e_bench.json), so this entry point sends mm128_t as it is unless MM2B_PACK=1 asks otherwise.
+	// Callers that take indices (mm2b_chain_batch_ex with bi) get the packed input: there it wins (15-21 ms against 19 ms).
+	const char *pe = getenv("MM2B_PACK");
+	const bool pack_b = pe && atoi(pe) > 0;
+	const unsigned flags = (pack_b && g.default_pack ? 0u : (unsigned)MM2B_F_RAW_INPUT) | (g.default_device_gather ? (unsigned)MM2B_F_DEVICE_GATHER : (unsigned)MM2B_F_HOST_GATHER);
 	if (!b && n_reads > 0 && off && off[n_reads] > 0) { set_error("%s%s", "mm2b_chain_batch: NULL buffer", ""); return MM2B_ERR_ARG; }
 	return mm2b_chain_batch_ex(par, n_reads, off, a, n_u, n_v, status, u_off, b_off, u, u_cap, b, nullptr, b_cap, flags, stats);
 }

@@ -31,15 +31,17 @@
 #define PBCCS_C_SW 0.0f
 
 #define XCLBIN_FILE ((char*)"")    /* no bitstream: kernels are compiled into the library */
-#define BUFFER_N 0                 /* no fixed device buffer: workspaces grow with the largest read seen */
+#define BUFFER_N (500L << 20)      /* not a device buffer any more (workspaces grow with the batches seen): the bytes of read sequence per
+                                      mini-batch (-K, 500M by default, options.c:53) whose pinned staging is reserved while the index loads */
 
 static inline bool hardware_init(long buf_size, char *binary_name)
 {
-	(void)buf_size; (void)binary_name;
+	(void)binary_name;
 	if (mm2b_init_async(0, 0) != MM2B_OK) {      /* devices come up while main() loads the index (main.c:371) */
 		fprintf(stderr, "[ERROR] B200 chaining backend: %s\n", mm2b_last_error());
 		return false;
 	}
+	if (buf_size > 0 && !(getenv("MM2B_RESERVE") && atoi(getenv("MM2B_RESERVE")) == 0)) mm2b_reserve_for_mapping((size_t)buf_size);
 	return true;
 }
 static inline void cleanup(void) { mm2b_shutdown(); }

@@ -54,13 +54,14 @@ struct PinBuf {                             // pinned host buffer that only grow
 	bool ensure(size_t bytes)
 	{
 		if (bytes <= cap) return true;
-		cudaFreeHost(p), p = nullptr, cap = 0;
+		mm2b_host_free(p), p = nullptr, cap = 0;
 		const size_t want = bytes + bytes / 4 + 4096;
-		if (!cuda_ok(cudaHostAlloc(&p, want, cudaHostAllocPortable), "cudaHostAlloc")) return false;
+		p = mm2b_host_alloc(want);                  // from the library's pinned pool when it has a block of about this size
+		if (!p) return false;
 		cap = want;
 		return true;
 	}
-	void release() { cudaFreeHost(p), p = nullptr, cap = 0; }
+	void release() { mm2b_host_free(p), p = nullptr, cap = 0; }
 };
 
 // One pipeline context: a stream and everything a sub-batch needs on its device
@@ -70,14 +71,14 @@ struct Ctx {
 	cudaEvent_t ev[6] = {};
 	DevBuf<uint8_t> seq;
 	DevBuf<int64_t> seq_off, tile_mv_off, mv_off, n_a, a_off, u_off, b_off;
-	DevBuf<int32_t> tile_off, tile_cnt, occ, arel, rep_len, n_mini_pos, tie_list, n_u, n_v, status;
+	DevBuf<int32_t> tile_off, tile_read, tile_cnt, occ, arel, rep_len, n_mini_pos, tie_list, n_u, n_v, status;
 	DevBuf<uint32_t> mini_pos;
 	DevBuf<uint64_t> hv, u;
 	DevBuf<ulonglong2> mv, a, a_tmp, b;
 	DevBuf<int> small;
 	mm2b_workspace_t *ws = nullptr;
 	int64_t ws_anchors = 0, ws_reads = 0;
-	PinBuf h_small, h_read;         // offsets in / totals out; per-read results
+	PinBuf h_small, h_read, h_tiles;    // offsets in / totals out; per-read results; tile -> read map
 	bool create(int dev)
 	{
 		device = dev;
@@ -93,10 +94,10 @@ struct Ctx {
 		cudaSetDevice(device);
 		if (stream) cudaStreamSynchronize(stream);
 		seq.release(), seq_off.release(), tile_mv_off.release(), mv_off.release(), n_a.release(), a_off.release(), u_off.release(), b_off.release();
-		tile_off.release(), tile_cnt.release(), occ.release(), arel.release(), rep_len.release(), n_mini_pos.release(), tie_list.release();
+		tile_off.release(), tile_read.release(), tile_cnt.release(), occ.release(), arel.release(), rep_len.release(), n_mini_pos.release(), tie_list.release();
 		n_u.release(), n_v.release(), status.release(), mini_pos.release(), hv.release(), u.release(), mv.release(), a.release(), a_tmp.release(), b.release(), small.release();
 		mm2b_ws_destroy(ws), ws = nullptr;
-		h_small.release(), h_read.release();
+		h_small.release(), h_read.release(), h_tiles.release();
 		for (auto &e : ev) if (e) cudaEventDestroy(e);
 		if (stream) cudaStreamDestroy(stream);
 		device = -1;
@@ -186,19 +187,24 @@ bool run_sub(Call &call, Ctx &c, int si)
 	CK(cudaSetDevice(c.device), "cudaSetDevice");
 
 	// ---- offsets and tiles (host), sequences to the device
-	if (!c.h_small.ensure((size_t)(R + 1) * 12 + 64)) return false;
+	const int64_t max_tiles = S / SKETCH_TILE + R + 1;
+	if (max_tiles >= (1ll << 31) || S >= (1ll << 40)) { set_error("%s%s", "mm2b_map_batch: sub-batch too large", ""); return false; }
+	if (!c.h_small.ensure((size_t)(R + 1) * 12 + 64) || !c.h_tiles.ensure((size_t)max_tiles * 4)) return false;
 	int64_t *h_seq_off = (int64_t*)c.h_small.p;
-	int32_t *h_tile_off = (int32_t*)(h_seq_off + R + 1);
+	int32_t *h_tile_off = (int32_t*)(h_seq_off + R + 1), *h_tile_read = (int32_t*)c.h_tiles.p;
 	int64_t n_tiles64 = 0;
 	for (int64_t r = 0; r <= R; ++r) {
 		h_seq_off[r] = call.seq_off[sb.r0 + r] - s0;
 		h_tile_off[r] = (int32_t)n_tiles64;
-		if (r < R) n_tiles64 += (call.seq_off[sb.r0 + r + 1] - call.seq_off[sb.r0 + r] + SKETCH_TILE - 1) / SKETCH_TILE;
+		if (r < R) {
+			const int64_t nt = (call.seq_off[sb.r0 + r + 1] - call.seq_off[sb.r0 + r] + SKETCH_TILE - 1) / SKETCH_TILE;
+			for (int64_t q = 0; q < nt; ++q) h_tile_read[n_tiles64 + q] = (int32_t)r;
+			n_tiles64 += nt;
+		}
 	}
-	if (n_tiles64 >= (1ll << 31) || S >= (1ll << 40)) { set_error("%s%s", "mm2b_map_batch: sub-batch too large", ""); return false; }
 	const int32_t n_tiles = (int32_t)n_tiles64;
 	if (!c.seq.ensure(S + 8, "cudaMalloc(seq)") || !c.seq_off.ensure(R + 1, "cudaMalloc") || !c.tile_off.ensure(R + 1, "cudaMalloc") ||
-	    !c.tile_cnt.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_mv_off.ensure(n_tiles + 2, "cudaMalloc") || !c.mv_off.ensure(R + 2, "cudaMalloc") ||
+	    !c.tile_read.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_cnt.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_mv_off.ensure(n_tiles + 2, "cudaMalloc") || !c.mv_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.rep_len.ensure(R + 1, "cudaMalloc") || !c.n_mini_pos.ensure(R + 1, "cudaMalloc") || !c.n_a.ensure(R + 1, "cudaMalloc") || !c.a_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.tie_list.ensure(R + 1, "cudaMalloc") || !c.n_u.ensure(R + 1, "cudaMalloc") || !c.n_v.ensure(R + 1, "cudaMalloc") || !c.status.ensure(R + 1, "cudaMalloc") ||
 	    !c.u_off.ensure(R + 2, "cudaMalloc") || !c.b_off.ensure(R + 2, "cudaMalloc")) return false;
@@ -206,10 +212,11 @@ bool run_sub(Call &call, Ctx &c, int si)
 	if (S > 0) CK(cudaMemcpyAsync(c.seq.p, call.seq + s0, (size_t)S, cudaMemcpyHostToDevice, st), "H2D sequences");
 	CK(cudaMemcpyAsync(c.seq_off.p, h_seq_off, (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, st), "H2D seq_off");
 	CK(cudaMemcpyAsync(c.tile_off.p, h_tile_off, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st), "H2D tile_off");
+	if (n_tiles) CK(cudaMemcpyAsync(c.tile_read.p, h_tile_read, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st), "H2D tile_read");
 
 	SeedArgs a;
 	memset(&a, 0, sizeof(a));
-	a.n_reads = R, a.seq = c.seq.p, a.seq_off = c.seq_off.p, a.tile_off = c.tile_off.p, a.n_tiles = n_tiles;
+	a.n_reads = R, a.seq = c.seq.p, a.seq_off = c.seq_off.p, a.tile_off = c.tile_off.p, a.tile_read = c.tile_read.p, a.n_tiles = n_tiles;
 	a.k = ix->k, a.w = ix->w, a.max_occ = call.seed.max_occ;
 	a.tile_cnt = c.tile_cnt.p, a.tile_mv_off = c.tile_mv_off.p, a.mv_off = c.mv_off.p;
 	a.rep_len = c.rep_len.p, a.n_mini_pos = c.n_mini_pos.p, a.n_a = c.n_a.p, a.a_off = c.a_off.p, a.tie_list = c.tie_list.p, a.tie_count = c.small.p;
@@ -357,7 +364,7 @@ int64_t env_ll(const char *name, int64_t dflt)
 
 void cut_subs(Call &call, int64_t n_reads)
 {
-	const int64_t sub_bytes = env_ll("MM2B_MAP_SUB_BYTES", 32ll << 20), sub_reads = 1 << 16;
+	const int64_t sub_bytes = env_ll("MM2B_MAP_SUB_BYTES", 96ll << 20), sub_reads = 1 << 18;     // (kernels over a few thousand reads do not fill the GPU)
 	for (int64_t r0 = 0; r0 < n_reads;) {
 		const int64_t lim = call.seq_off[r0] + sub_bytes;
 		int64_t r1 = std::upper_bound(call.seq_off + r0 + 1, call.seq_off + n_reads + 1, lim) - call.seq_off - 1;

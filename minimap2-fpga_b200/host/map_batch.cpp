@@ -18,6 +18,13 @@
 // would make the same edit by hand: replace `kt_for(p->n_threads, worker_for, in, n_frag)` at map.c:561 by
 // `mm2b_map_frags(p->n_threads, worker_for, in, n_frag)` and append this file's code to map.c.
 //
+// With the seeding front end (include/mm2seed_b200.h) phase A shrinks to copying the read sequences into
+// one staging buffer and phase B becomes ONE mm2b_map_batch call: sketch, seed hits, sort and chaining all run on the GPU, and
+// phase C receives, per read, exactly what the first half of mm_map_frag would have left it: the chains (u[], b[]), rep_len and
+// mini_pos.  That path is taken when the configuration is one the device reproduces (mm2b_map_supported: one segment per read,
+// no HPC, odd k, no SDUST, none of the seed-skipping flags) and the chaining arguments do not depend on the read; otherwise the
+// anchors are seeded on the host as described above.  MM2B_FRONT=0 switches it off.
+//
 // The kalloc discipline of the reference is kept: nothing allocated from a thread's arena (mm_tbuf_t::km) outlives the phase
 // that allocated it, so the leak check of map.c:386 holds at the end of BOTH halves (it is restated in each).
 // What is not batched falls back to the reference's own per-read worker (and from there to the per-read mm_chain_dp drop-in):
@@ -32,8 +39,12 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <time.h>
 #define MM2B_HOST_DECLARES_MM_CHAIN_DP          /* mmpriv.h:65 already declares it (with mm128_t) */
-#include "mm2chain_b200.h"
+#include "mm2seed_b200.h"
+
+extern "C" int mm2b_index_flatten_mt(const mm_idx_t *mi, mm2b_index_desc_t *out, int n_threads);      // host/idx_flatten.cpp (index.c + the bucket walk)
+extern "C" void mm2b_index_flat_free(mm2b_index_desc_t *d);
 
 extern "C" void kt_for(int n_threads, void (*func)(void*, long, int), void *data, long n);      // kthread.c:54
 
@@ -70,11 +81,22 @@ struct Frag {                                       // what the first half of mm
 	int rep_len = 0, n_mini_pos = 0, qlen_sum = 0, gap_ref = 0, gap_qry = 0;
 	uint32_t hash = 0;
 	uint64_t *mini_pos = nullptr;                   // malloc'd copy (the arena copy dies with phase A)
+	// seeding front end: the read's row in the mm2b_map_batch result (-1: not on that path)
+	int64_t front = -1;
 };
 
 constexpr int MAX_BLOCKS = 4096;
 
 struct Stage {
+	// seeding front end: the device copy of the index this process is mapping against, the sequence staging buffer, the result
+	const mm_idx_t *front_mi = nullptr;
+	const void *front_mi_S = nullptr;
+	int front_mi_part = -1;
+	mm2b_index_t *front_idx = nullptr;
+	char *seq = nullptr;
+	int64_t seq_cap = 0;
+	std::vector<int64_t> seq_off;
+	mm2b_map_result_t *front_res = nullptr;
 	std::mutex mu;
 	Block *blocks[MAX_BLOCKS];                      // blocks of the current mini-batch: appended under `mu`, read without it
 	std::atomic<int> n_blocks{0};
@@ -221,13 +243,34 @@ void finish_worker(void *data, long i, int tid)
 	const int off = s->seg_off[i], n_segs = frag_segments(s, i, qlens, qseqs, false), pe_ori = opt->pe_ori;
 	const char *qname = s->seq[off].name;
 	const int is_sr = !!(opt->flag & MM_F_SR), is_splice = !!(opt->flag & MM_F_SPLICE), qlen_sum = f.qlen_sum;
-	if (f.block >= 0) {
-		// what mm_chain_dp would have returned (chain.c:396-422): u[] copied, b[] gathered from the staged anchors by index
-		Block &blk = *st.blocks[f.block];
+	if (f.block >= 0 || f.front >= 0) {
 		int n_regs0 = 0, rep_len = f.rep_len, n_mini_pos = f.n_mini_pos, j;
 		uint64_t *u = 0, *mini_pos = f.mini_pos;
 		mm128_t *a = 0;
 		bool mini_pos_in_km = false;
+		if (f.front >= 0) {
+			// seeding front end: the chains, rep_len and mini_pos of this read came back from the GPU (mm2b_map_batch)
+			const mm2b_map_result_t *res = st.front_res;
+			const int64_t r = f.front;
+			const int sg = res->seg[r];
+			rep_len = res->rep_len[r], n_mini_pos = res->n_mini_pos[r];
+			if (n_mini_pos > 0) {                                             // map.c:117: q_span << 32 | position; q_span == k on this path
+				const uint32_t *mp = res->seg_mini_pos[sg] + res->mp_off[r];
+				const uint64_t span = (uint64_t)mi->k << 32;
+				mini_pos = (uint64_t*)malloc((size_t)n_mini_pos * 8);
+				for (int32_t k = 0; k < n_mini_pos; ++k) mini_pos[k] = span | mp[k];
+			}
+			if (res->status[r] == MM2B_READ_OK) {
+				const int32_t nu = res->n_u[r], nv = res->n_v[r];
+				u = (uint64_t*)kmalloc(b->km, (size_t)(nu > 0 ? nu : 1) * 8);
+				a = (mm128_t*)kmalloc(b->km, (size_t)nv * sizeof(mm128_t));
+				if (nu > 0) memcpy(u, res->seg_u[sg] + res->u_off[r], (size_t)nu * 8);
+				if (nv > 0) memcpy(a, res->seg_b[sg] + res->b_off[r], (size_t)nv * sizeof(mm128_t));
+				n_regs0 = nu;
+			}
+		} else {
+		// what mm_chain_dp would have returned (chain.c:396-422): u[] copied, b[] gathered from the staged anchors by index
+		Block &blk = *st.blocks[f.block];
 		if (blk.status[f.slot] == MM2B_READ_OK) {
 			const int32_t nu = blk.n_u[f.slot], nv = blk.n_v[f.slot];
 			const mm128_t *src = (const mm128_t*)blk.a + f.pos;
@@ -237,6 +280,7 @@ void finish_worker(void *data, long i, int tid)
 			if (nu > 0) memcpy(u, blk.u + blk.u_off[f.slot], (size_t)nu * 8);
 			for (int32_t k = 0; k < nv; ++k) a[k] = src[ix[k]];
 			n_regs0 = nu;
+		}
 		}
 		if (opt->max_occ > opt->mid_occ && rep_len > 0) {                 // map.c:318-340, verbatim in effect: rare, done per read
 			int rechain = 0;
@@ -315,6 +359,114 @@ void finish_worker(void *data, long i, int tid)
 		}
 }
 
+// ---- seeding front end: phase A is a copy of the sequences, phase B one mm2b_map_batch call ------------------------------------
+void stage_seq_worker(void *data, long i, int tid)
+{
+	(void)tid;
+	Stage &st = *(Stage*)data;
+	step_t *s = st.step;
+	const mm_mapopt_t *opt = s->p->opt;
+	Frag &f = st.frags[i];
+	const int off = s->seg_off[i];
+	const mm_bseq1_t *q = &s->seq[off];
+	s->n_reg[off] = 0, s->reg[off] = 0;
+	f.qlen_sum = q->l_seq;
+	if (st.seq_off[i + 1] == st.seq_off[i]) return;                       // empty or over-long query (map.c:284-285): nothing to map
+	f.front = i;
+	f.hash = q->name ? __ac_X31_hash_string(q->name) : 0;                 // map.c:287-289
+	f.hash ^= __ac_Wang_hash(f.qlen_sum) + __ac_Wang_hash(opt->seed);
+	f.hash = __ac_Wang_hash(f.hash);
+	chain_gaps(opt, f.qlen_sum, f.gap_ref, f.gap_qry);
+	memcpy(st.seq + st.seq_off[i], q->seq, (size_t)q->l_seq);
+}
+
+double wall_s()
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
+// the device copy of the index being mapped against (one per process at a time: the CLI maps against one index part at a time)
+mm2b_index_t *front_index(Stage &st, const mm_idx_t *mi, int n_threads)
+{
+	if (st.front_idx && st.front_mi == mi && st.front_mi_S == (const void*)mi->S && st.front_mi_part == mi->index) return st.front_idx;
+	mm2b_index_destroy(st.front_idx), st.front_idx = nullptr;
+	mm2b_index_desc_t d;
+	const double t0 = wall_s();
+	if (mm2b_index_flatten_mt(mi, &d, n_threads) != 0) return nullptr;
+	const double t1 = wall_s();
+	st.front_idx = mm2b_index_create(&d);
+	if (getenv("MM2B_TRACE") && atoi(getenv("MM2B_TRACE")) > 0)
+		fprintf(stderr, "[mm2b trace] front end: index flattened in %.3f s (%lld minimizers, %lld positions), on the device in %.3f s\n", t1 - t0, (long long)d.n_keys, (long long)d.n_pos, wall_s() - t1);
+	mm2b_index_flat_free(&d);
+	if (!st.front_idx) { fprintf(stderr, "[mm2b] fatal: index upload: %s\n", mm2b_last_error()); exit(EXIT_FAILURE); }
+	st.front_mi = mi, st.front_mi_S = (const void*)mi->S, st.front_mi_part = mi->index;
+	return st.front_idx;
+}
+
+bool front_applies(const step_t *s, long n)
+{
+	static const bool off = getenv("MM2B_FRONT") && atoi(getenv("MM2B_FRONT")) == 0;
+	const mm_mapopt_t *opt = s->p->opt;
+	const mm_idx_t *mi = s->p->mi;
+	if (off || !mm2b_map_supported(mi->k, mi->w, mi->flag & MM_I_HPC, 1, opt->flag, opt->sdust_thres)) return false;
+	if ((opt->flag & MM_F_SR) || (opt->max_gap_ref <= 0 && opt->max_frag_len > 0)) return false;      // chaining gaps depend on the read (map.c:305-314)
+	for (long i = 0; i < n; ++i) if (s->n_seg[i] != 1) return false;
+	return true;
+}
+
+bool map_frags_front(Stage &st, int n_threads, long n)
+{
+	step_t *s = st.step;
+	const mm_mapopt_t *opt = s->p->opt;
+	static const bool trace = getenv("MM2B_TRACE") && atoi(getenv("MM2B_TRACE")) > 0;
+	double t0 = wall_s(), t1;
+	auto lap = [&](const char *what) {
+		if (!trace) return;
+		t1 = wall_s();
+		fprintf(stderr, "[mm2b trace] front end: %-22s %.3f s\n", what, t1 - t0);
+		t0 = t1;
+	};
+	mm2b_index_t *idx = front_index(st, s->p->mi, n_threads);
+	lap("index on the device");
+	if (!idx) return false;                                                 // (an index the flat format cannot hold: seed on the host)
+	st.seq_off.assign((size_t)n + 1, 0);
+	for (long i = 0; i < n; ++i) {
+		const int len = s->seq[s->seg_off[i]].l_seq;
+		const bool skip = len <= 0 || (opt->max_qlen > 0 && len > opt->max_qlen);
+		st.seq_off[(size_t)i + 1] = st.seq_off[(size_t)i] + (skip ? 0 : len);
+	}
+	if (st.seq_off[(size_t)n] > st.seq_cap) {
+		mm2b_host_free(st.seq);
+		st.seq_cap = st.seq_off[(size_t)n] + st.seq_off[(size_t)n] / 8 + 4096;
+		st.seq = (char*)mm2b_host_alloc((size_t)st.seq_cap);
+		if (!st.seq) { fprintf(stderr, "[mm2b] pinned staging for the sequences: %s\n", mm2b_last_error()); exit(1); }
+	}
+	lap("staging buffer");
+	kt_for(n_threads, stage_seq_worker, &st, n);                             // A
+	lap("A: sequences staged");
+	int gap_ref = 0, gap_qry = 0;
+	chain_gaps(opt, 0, gap_ref, gap_qry);
+	const mm2b_params_t par = chain_params(opt, gap_ref, gap_qry, 1);
+	const mm2b_seed_params_t sp = {opt->mid_occ, 0};
+	if (mm2b_map_batch(idx, &sp, &par, n, st.seq_off.data(), st.seq, &st.front_res) != MM2B_OK) {      // B
+		fprintf(stderr, "[mm2b] fatal: mapping a mini-batch: %s\n", mm2b_last_error());                  // same behaviour as checkError (chain_hardware.cpp:208)
+		exit(EXIT_FAILURE);
+	}
+	lap("B: mm2b_map_batch");
+	if (trace) {
+		const mm2b_map_result_t *r = st.front_res;
+		fprintf(stderr, "[mm2b trace] front end: %ld reads, %lld bases -> %lld minimizers, %lld anchors (%lld reads with equal keys), %lld chains; sketch %.2f seed %.2f sort %.2f chain %.2f ms, %d segments\n",
+		        n, (long long)st.seq_off[(size_t)n], (long long)r->tot_mini, (long long)r->tot_anchors, (long long)r->n_tie_reads, (long long)r->tot_chains,
+		        r->sketch_ms, r->seed_ms, r->sort_ms, r->chain_ms, r->n_segs);
+	}
+	kt_for(n_threads, finish_worker, &st, n);                                // C
+	lap("C: reads finished");
+	mm2b_map_result_release(st.front_res), st.front_res = nullptr;
+	return true;
+}
+
 // ---- phase B: every staging block in one batch call, all blocks at once -------------------------------------------------------
 void chain_block(Stage &st, int bi)
 {
@@ -353,6 +505,7 @@ extern "C" void mm2b_map_frags(int n_threads, void (*func)(void*, long, int), vo
 	Stage &st = the_stage();
 	st.step = s;
 	st.frags.assign((size_t)n, Frag());
+	if (front_applies(s, n) && map_frags_front(st, n_threads, n)) return;
 	kt_for(n_threads, seed_worker, &st, n);                                  // A
 	const int nb = st.n_blocks.load();
 	for (int k = 0; k < nb; ++k) st.blocks[k]->off.clear(), st.blocks[k]->frag.clear();

@@ -106,10 +106,13 @@ def test_bounded_packing_mixes_packed_and_raw_subbatches(binding, pkg, oracle):
         b.init(1)
         off, a = pkg("workload").synth_anchor_batch(1200, seed=9)
         ref = oracle.replay(oracle.Params(), off, a, n_threads=8)
-        res = b.chain_batch(b.Params(), off, a)
+        res = b.chain_batch(b.Params(), off, a, mode="both")
         _check_against(res, ref, off)
         st = res["stats"]
         assert st.n_packed_subs + st.n_raw_subs >= 10 and st.n_packed_subs >= 1
+        res = b.chain_batch(b.Params(), off, a)          # mm2b_chain_batch itself sends the input as it is
+        _check_against(res, ref, off)
+        assert res["stats"].n_packed_subs == 0
     finally:
         b.shutdown()
         os.environ.pop("MM2B_PACK_INFLIGHT", None)
@@ -130,7 +133,7 @@ def test_high_words_too_varied_fall_back_to_raw_per_subbatch(binding, oracle):
     a = np.concatenate(reads)
     par = dict(n_segs=2, max_iter=200)
     ref = oracle.replay(oracle.Params(**par), off, a, n_threads=8)
-    res = binding.chain_batch(binding.Params(**par), off, a)
+    res = binding.chain_batch(binding.Params(**par), off, a, mode="both")
     assert res["stats"].n_raw_subs >= 2 and res["stats"].n_packed_subs == 0
     _check_against(res, ref, off)
 

@@ -70,6 +70,32 @@ def test_phase_split_switched_off_is_the_reference_worker(cases):
     _check(SW, cases, 2, only=("syn_ont", "sr_paired"), env={"MM2B_PHASE_SPLIT": "0"})
 
 
+def _front_end_lines(exe, args):
+    out = subprocess.run([exe, "-t", "3"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MM2B_TRACE="1"))
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    return [l for l in out.stderr.decode().splitlines() if "front end:" in l]
+
+
+def test_seeding_front_end_is_taken_where_it_applies_and_only_there(cases):
+    """map-ont / asm20 go through mm2b_map_batch (sequences in, chains out); paired short reads, splice-free presets with per-read
+    chaining gaps and all-vs-all overlap (seed-skipping flags) keep the host seeding.  MM2B_FRONT=0 switches it off: same PAF."""
+    if not os.path.exists(SW):
+        pytest.skip("oracle/_ref/minimap2-batch-sw was not built (needs /root/reference at build time)")
+    by_name = dict(cases)
+    assert _front_end_lines(SW, by_name["syn_ont"]) and _front_end_lines(SW, by_name["syn_ccs"]) and _front_end_lines(SW, by_name["tandem_iter64"])
+    assert not _front_end_lines(SW, by_name["sr_paired"]) and not _front_end_lines(SW, by_name["ava"])
+    _check(SW, cases, 4, only=("syn_ont", "syn_ccs", "inv_map-ont", "tandem_iter64"), env={"MM2B_FRONT": "0"})
+
+
+@pytest.mark.gpu
+def test_seeding_front_end_on_the_b200(cases):
+    if not os.path.exists(B200):
+        pytest.skip("oracle/_ref/minimap2-b200-batch was not built (needs /root/reference at build time)")
+    by_name = dict(cases)
+    assert _front_end_lines(B200, by_name["syn_ont"]) and _front_end_lines(B200, by_name["tandem_iter64"])
+    _check(B200, cases, 8, only=("syn_ont", "syn_ccs"), env={"MM2B_FRONT": "0"})
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("threads", [1, 8])
 def test_phase_split_with_the_b200_backend(cases, threads):

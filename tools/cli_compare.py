@@ -18,10 +18,11 @@ def run(exe, t, env=None):
     p = subprocess.run([R + exe] + BW.PRESETS[preset][2] + ["-t", str(t), mmi, q], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **(env or {})))
     dt = time.time() - t0
     err = p.stderr.decode().splitlines()
-    tr = [l for l in err if "batcher" in l][-1:] + [l for l in err if "mapped" in l or "loaded/built" in l or "Real time" in l]
+    tr = [l for l in err if "batcher" in l][-1:] + [l for l in err if "front end:" in l or "init:" in l] + [l for l in err if "mapped" in l or "loaded/built" in l or "Real time" in l]
     return dt, hashlib.md5(p.stdout).hexdigest(), p.stdout.count(b"\n"), tr
-runs = [("minimap2-sw", threads, None), ("minimap2-b200-batch", threads, None), ("minimap2-b200-batch", threads, {"MM2B_TRACE": "1"}), ("minimap2-b200", 256, {"MM2B_TRACE": "1"}), ("minimap2-sw", threads, None)]
+runs = [("minimap2-sw", threads, None), ("minimap2-b200-batch", threads, None), ("minimap2-b200-batch", threads, {"MM2B_TRACE": "1"}), ("minimap2-b200-batch", threads, {"MM2B_FRONT": "0"}),
+        ("minimap2-b200", 256, None), ("minimap2-sw", threads, None)]
 for exe, t, env in runs:
     dt, md5, lines, tr = run(exe, t, env)
-    print("%-20s -t %-3d wall %.2f s  %d PAF lines  md5 %s" % (exe, t, dt, lines, md5[:8]), flush=True)
+    print("%-20s -t %-3d %-18s wall %.2f s  %d PAF lines  md5 %s" % (exe, t, env or "", dt, lines, md5[:8]), flush=True)
     for l in tr: print("      " + l)
