@@ -7,8 +7,9 @@
 //     warp ballots / REDUX.OR, every thread cuts its k-mer and the reverse complement out of two 64-bit words (funnel shift,
 //     BREV), hashes it, and the w + 1 hashes around it in shared memory tell it everything mm_sketch's state machine does at its
 //     position: the ring buffer's minimum is always the NEWEST minimal entry of the last w positions, so "what is pushed at
-//     step t" is a function of X[t-w .. t] and of the distance to the last ambiguous base.  A count pass, an exclusive scan over
-//     the tiles and an emit pass put the minimizers in the reference's order, duplicates of its first-window rule included.
+//     step t" is a function of X[t-w .. t] and of the distance to the last ambiguous base.  One pass: a tile counts what it pushes,
+//     gets its place in the output from a decoupled look-back over the tiles in front of it, and writes the minimizers in the
+//     reference's order, duplicates of its first-window rule included.
 //   * index: one open-addressing table in HBM (linear probing, load <= 0.5) instead of 2^b khash buckets; one probe thread per
 //     minimizer, all minimizers of a sub-batch at once (the probes are dependent HBM accesses: parallelism is what hides them).
 //   * matches: one warp per read walks its minimizers 32 at a time: occurrence filter, repeat length (a merge of intervals the
@@ -81,21 +82,47 @@ struct Emit {
 	int first_m, last_e;                    // position pushed by A / B's first push (or -1); by E (or -1)
 };
 
-template <bool WRITE>
+// hash64 on 32-bit words, for 2k <= 32: every step of sketch.c:28-38 ends in `& mask`, so carrying only the low 32 bits is exact
+__device__ __forceinline__ uint32_t hash32(uint32_t key, uint32_t mask)
+{
+	key = (~key + (key << 21)) & mask;
+	key = key ^ key >> 24;
+	key = ((key + (key << 3)) + (key << 8)) & mask;
+	key = key ^ key >> 14;
+	key = ((key + (key << 2)) + (key << 4)) & mask;
+	key = key ^ key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+// One pass: a tile counts what it pushes, learns how many minimizers the tiles before it pushed from a decoupled look-back over
+// their published counts (tiles are handed out by an atomic ticket so that every predecessor is already running), and writes.
+// tile_state[t] = flag << 62 | count: flag 1 = the tile's own count, 2 = the inclusive prefix up to and including it.
+// If mv is too small for the batch the writes are dropped but the counting goes on: the host sees the total and runs again.
+template <bool K32>
 __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 {
 	__shared__ uint64_t X[TILE_SPAN];
 	__shared__ uint64_t pk[TILE_SPAN / 32 + 1];             // 2-bit bases, 32 per word, earlier base in the lower bits
 	__shared__ uint32_t badw[TILE_SPAN / 32];               // one bit per position: ambiguous base or outside the read
 	__shared__ uint8_t zs[TILE_SPAN];                       // strand of the position's k-mer
+	__shared__ int16_t jm_s[SKETCH_TILE];                   // per position: newest minimal entry of the window in front of it ...
+	__shared__ uint8_t ties_s[SKETCH_TILE];                 // ... and whether its hash occurs more than once in that window
 	__shared__ int warp_sum[SKETCH_TILE / 32];
+	__shared__ int tile_s;
+	__shared__ long long excl_s;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) pk[TILE_SPAN / 32] = 0;
-	const int r = s.tile_read[blockIdx.x];                  // which read this tile belongs to (filled by the host with the offsets)
+	if (tid == 0) {
+		pk[TILE_SPAN / 32] = 0;
+		tile_s = atomicAdd(s.tile_ticket, 1);
+	}
+	__syncthreads();
+	const int tile = tile_s;
+	const int r = s.tile_read[tile];                        // which read this tile belongs to (filled by the host with the offsets)
 	const int64_t so = s.seq_off[r];
 	const int L = (int)(s.seq_off[r + 1] - so);
-	const int t0 = ((int)blockIdx.x - s.tile_off[r]) * SKETCH_TILE;
+	const int t0 = (tile - s.tile_off[r]) * SKETCH_TILE;
 	const int pb = t0 - HALO;                               // position of shared-memory index 0
 	const int k = s.k, w = s.w;
 	const uint64_t mask = (1ull << 2 * k) - 1;
@@ -143,35 +170,55 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 			fw = ((fw >> 1) & 0x5555555555555555ull) | ((fw & 0x5555555555555555ull) << 1);
 			fw >>= 64 - 2 * k;
 			z = fw < rv ? 0 : 1;                                    // sketch.c:111 (fw != rv for odd k)
-			x = hash64(z ? rv : fw, mask) << 8 | (uint64_t)k;       // sketch.c:114; kmer_span == k once l >= k
+			const uint64_t km = z ? rv : fw;
+			const uint64_t h = K32 ? (uint64_t)hash32((uint32_t)km, (uint32_t)mask) : hash64(km, mask);
+			x = h << 8 | (uint64_t)k;                               // sketch.c:114; kmer_span == k once l >= k
 		}
 		X[i] = x, zs[i] = (uint8_t)z;
 	}
 	__syncthreads();
 
-	// 3. what mm_sketch pushes at this thread's position
+	// 3. the window in front of this thread's position: its newest minimal entry, and whether that hash is there more than once.
+	//    The window AFTER the step (what the reference rescans when the minimum leaves, sketch.c:126-129) is the next thread's.
 	const int i = HALO + tid, t = t0 + tid;
+	uint64_t xm = EMPTY;
+	int jm = i - w;
+	bool ties = false;
+	for (int j = i - w; j < i; ++j) {
+		const uint64_t xj = X[j];
+		if (xj <= xm) ties = xj == xm, xm = xj, jm = j;
+	}
+	jm_s[tid] = (int16_t)jm, ties_s[tid] = ties;
+	__syncthreads();
+
+	// 4. what mm_sketch pushes at this position
 	Emit e;
 	e.mask_s = e.mask_b = 0, e.first_m = e.last_e = -1;
 	int cnt = 0;
 	if (t < L) {
 		const int l = run_len(i);
-		uint64_t xm = EMPTY;
-		int jm = i - w;
-		for (int j = i - w; j < i; ++j) if (X[j] <= xm) xm = X[j], jm = j;      // newest minimal of the previous window
 		const uint64_t xt = X[i];
 		int after = jm;                                                     // the minimum after this step (shared index)
-		if (l == w + k - 1 && xm != EMPTY)
+		if (l == w + k - 1 && xm != EMPTY && ties)
 			for (int j = i - w + 1; j < i; ++j) if (X[j] == xm && j != jm) e.mask_s |= 1ull << (j - (i - w + 1));
 		if (xt <= xm) {
 			if (l >= w + k && xm != EMPTY) e.first_m = jm;
 			after = i;
 		} else if (jm == i - w) {
 			if (l >= w + k - 1 && xm != EMPTY) e.first_m = jm;
-			uint64_t xn = EMPTY;
-			int jn = i - w + 1;
-			for (int j = i - w + 1; j <= i; ++j) if (X[j] <= xn) xn = X[j], jn = j;
-			if (l >= w + k - 1 && xn != EMPTY)
+			int jn;
+			bool tn;
+			if (tid + 1 < SKETCH_TILE) jn = jm_s[tid + 1], tn = ties_s[tid + 1];
+			else {                                                          // the last position of the tile has no neighbour to ask
+				uint64_t xn = EMPTY;
+				jn = i - w + 1, tn = false;
+				for (int j = i - w + 1; j <= i; ++j) {
+					const uint64_t xj = X[j];
+					if (xj <= xn) tn = xj == xn, xn = xj, jn = j;
+				}
+			}
+			const uint64_t xn = X[jn];
+			if (l >= w + k - 1 && xn != EMPTY && tn)
 				for (int j = i - w + 1; j <= i; ++j) if (X[j] == xn && j != jn) e.mask_b |= 1ull << (j - (i - w + 1));
 			after = jn;
 		}
@@ -193,12 +240,39 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 		if (q < warp) before += v;
 		total += v;
 	}
-	if (!WRITE) {
-		if (tid == 0) s.tile_cnt[blockIdx.x] = total;
-		return;
+	// decoupled look-back: how many minimizers the tiles before this one pushed.  Warp 0 looks at 32 predecessors at a time.
+	if (warp == 0) {
+		volatile unsigned long long *state = s.tile_state;
+		const unsigned long long F1 = 1ull << 62, F2 = 2ull << 62, VAL = F1 - 1;
+		long long excl = 0;
+		if (tile > 0) {
+			if (lane == 0) state[tile] = F1 | (unsigned long long)total;
+			__syncwarp();
+			for (int top = tile - 1; top >= 0; top -= 32) {
+				const int p = top - lane;
+				unsigned long long v = F2;                              // lanes in front of tile 0 count as a finished prefix of 0
+				if (p >= 0) while (((v = state[p]) >> 62) == 0) { }
+				const unsigned done = __ballot_sync(FULL, v >> 62 == 2);
+				const int stop = done ? __ffs((int)done) - 1 : 32;          // nearest predecessor with an inclusive prefix
+				long long part = lane <= stop ? (long long)(v & VAL) : 0;
+#pragma unroll
+				for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+				excl += part;
+				if (done) break;
+			}
+		}
+		if (lane == 0) {
+			state[tile] = F2 | (unsigned long long)(excl + total);
+			s.tile_excl[tile] = excl;
+			if (tile == s.n_tiles - 1) s.tile_excl[s.n_tiles] = excl + total;
+			excl_s = excl;
+		}
 	}
+	__syncthreads();
 	if (cnt == 0) return;
-	ulonglong2 *dst = s.mv + s.tile_mv_off[blockIdx.x] + before + (incl - cnt);
+	const long long at = excl_s + before + (incl - cnt);
+	if (at + cnt > s.mv_cap) return;                        // (the host sees the total and comes back with a larger buffer)
+	ulonglong2 *dst = s.mv + at;
 	auto push = [&](int j) { *dst++ = make_ulonglong2(X[j], (uint64_t)(uint32_t)(pb + j) << 1 | zs[j]); };     // sketch.c:115 (rid 0)
 	const int j0 = i - w + 1;
 	for (unsigned long long m = e.mask_s; m; m &= m - 1) push(j0 + __ffsll((long long)m) - 1);
@@ -242,7 +316,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const T *in, int64_t *out, i
 __global__ void read_offsets_kernel(const SeedArgs s)
 {
 	const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r <= s.n_reads) s.mv_off[r] = s.tile_mv_off[r < s.n_reads ? s.tile_off[r] : s.n_tiles];
+	if (r <= s.n_reads) s.mv_off[r] = s.n_tiles > 0 ? s.tile_excl[r < s.n_reads ? s.tile_off[r] : s.n_tiles] : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -578,8 +652,8 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) sort_kernel(const SeedArgs s)
 // the insertion sorts of the small buckets (every lane takes the buckets of its 8 digits: the ranges are disjoint), and levels on
 // which every key has the same digit are skipped outright (nothing would move).  Reads of up to REPLAY_SMEM anchors are replayed
 // in shared memory, where a dependent access costs tens of cycles instead of hundreds.
-constexpr int REPLAY_SMEM = 2048;
-constexpr int REPLAY_WORK = 64;                 // pending ranges of a read held in shared memory (a range has > 64 elements)
+constexpr int REPLAY_SMEM = 8192;                // 128 KB of shared memory: one replaying warp per SM is plenty, such reads are few
+constexpr int REPLAY_WORK = 160;                // pending ranges of a read held in shared memory (a range has > 64 elements)
 
 __device__ void warp_replay_sort(W16 *w, int n, int *sm /* 768 ints */, int3 *work, int work_cap, int lane)
 {
@@ -667,9 +741,10 @@ __device__ void warp_replay_sort(W16 *w, int n, int *sm /* 768 ints */, int3 *wo
 
 __global__ void __launch_bounds__(32) tie_replay_kernel(const SeedArgs s, const DeviceIndex ix)
 {
-	__shared__ __align__(16) W16 buf[REPLAY_SMEM];
-	__shared__ int sm[768];
-	__shared__ int3 work_s[REPLAY_WORK];
+	extern __shared__ __align__(16) unsigned char replay_smem[];
+	W16 *buf = (W16*)replay_smem;
+	int *sm = (int*)(buf + REPLAY_SMEM);
+	int3 *work_s = (int3*)(sm + 768);
 	const int lane = threadIdx.x & 31;
 	int n_tie = 0;
 	if (lane == 0) n_tie = s.tie_count[0];
@@ -715,10 +790,12 @@ int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, 
 	return 1;
 }
 
-int launch_sketch(const SeedArgs &s, bool write, cudaStream_t stream)
+int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 {
 	if (s.n_tiles <= 0) return 0;
-	if (write) sketch_kernel<true><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
+	cudaMemsetAsync(s.tile_state, 0, (size_t)s.n_tiles * 8, stream);
+	cudaMemsetAsync(s.tile_ticket, 0, sizeof(int), stream);
+	if (2 * s.k <= 32) sketch_kernel<true><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
 	else sketch_kernel<false><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
 	return 1;
 }
@@ -766,7 +843,15 @@ int launch_sort(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_
 	if (s.n_reads <= 0) return 0;
 	cudaMemsetAsync(s.tie_count, 0, 4 * sizeof(int), stream);
 	sort_kernel<<<warp_grid(s.n_reads, n_sms, SORT_WARPS), SORT_WARPS * 32, 0, stream>>>(s);
-	tie_replay_kernel<<<n_sms * 4, 32, 0, stream>>>(s, ix);
+	constexpr int replay_bytes = REPLAY_SMEM * 16 + 768 * 4 + REPLAY_WORK * 12;
+	static bool attr_set[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 64 && !attr_set[dev]) {
+		cudaFuncSetAttribute(tie_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, replay_bytes);
+		attr_set[dev] = true;
+	}
+	tie_replay_kernel<<<n_sms, 32, replay_bytes, stream>>>(s, ix);
 	return 2;
 }
 

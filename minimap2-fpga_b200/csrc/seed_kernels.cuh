@@ -31,9 +31,11 @@ struct SeedArgs {
 	int32_t n_tiles;
 	int k, w, max_occ;
 	// sketch
-	int32_t *tile_cnt;          // [n_tiles] minimizers emitted per tile (count pass)
-	const int64_t *tile_mv_off; // [n_tiles + 1] their exclusive prefix (emit pass)
+	unsigned long long *tile_state; // [n_tiles] look-back words: flag << 62 | count
+	int *tile_ticket;           // tiles are taken in ticket order
+	int64_t *tile_excl;         // [n_tiles + 1] minimizers pushed by the tiles before each tile; entry n_tiles = the total
 	ulonglong2 *mv;             // minimizers: x = hash << 8 | span, y = pos << 1 | strand
+	int64_t mv_cap;             // capacity of mv: beyond it the kernel only counts
 	int64_t *mv_off;            // [n_reads + 1]
 	// lookup + matches
 	int32_t *occ;               // per minimizer: occurrences in the index (mm_idx_get's *n)
@@ -50,10 +52,10 @@ struct SeedArgs {
 
 int launch_index_build(const DeviceIndex &ix, const uint64_t *d_keys, const uint64_t *d_vals, cudaStream_t stream);
 int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, const uint64_t *raw_minimizers, int32_t *occ, uint64_t *hv, cudaStream_t stream);
-int launch_sketch(const SeedArgs &s, bool write, cudaStream_t stream);
+int launch_sketch(const SeedArgs &s, cudaStream_t stream);
 int launch_scan_i32(const int32_t *in, int64_t *out, int64_t n, cudaStream_t stream);      // out[0..n]: exclusive prefix, out[n] = total
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream);
-int launch_read_offsets(const SeedArgs &s, cudaStream_t stream);                            // mv_off[r] = tile_mv_off[tile_off[r]]
+int launch_read_offsets(const SeedArgs &s, cudaStream_t stream);                            // mv_off[r] = tile_excl[tile_off[r]]
 int launch_matches(const SeedArgs &s, int n_sms, cudaStream_t stream);                      // collect_matches per read
 int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream);
 int launch_sort(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream);  // stable sort + exact replay of the reads with equal keys

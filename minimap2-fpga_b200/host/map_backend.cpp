@@ -70,8 +70,9 @@ struct Ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[6] = {};
 	DevBuf<uint8_t> seq;
-	DevBuf<int64_t> seq_off, tile_mv_off, mv_off, n_a, a_off, u_off, b_off;
-	DevBuf<int32_t> tile_off, tile_read, tile_cnt, occ, arel, rep_len, n_mini_pos, tie_list, n_u, n_v, status;
+	DevBuf<int64_t> seq_off, tile_excl, mv_off, n_a, a_off, u_off, b_off;
+	DevBuf<unsigned long long> tile_state;
+	DevBuf<int32_t> tile_off, tile_read, occ, arel, rep_len, n_mini_pos, tie_list, n_u, n_v, status;
 	DevBuf<uint32_t> mini_pos;
 	DevBuf<uint64_t> hv, u;
 	DevBuf<ulonglong2> mv, a, a_tmp, b;
@@ -93,8 +94,8 @@ struct Ctx {
 		if (device < 0) return;
 		cudaSetDevice(device);
 		if (stream) cudaStreamSynchronize(stream);
-		seq.release(), seq_off.release(), tile_mv_off.release(), mv_off.release(), n_a.release(), a_off.release(), u_off.release(), b_off.release();
-		tile_off.release(), tile_read.release(), tile_cnt.release(), occ.release(), arel.release(), rep_len.release(), n_mini_pos.release(), tie_list.release();
+		seq.release(), seq_off.release(), tile_excl.release(), tile_state.release(), mv_off.release(), n_a.release(), a_off.release(), u_off.release(), b_off.release();
+		tile_off.release(), tile_read.release(), occ.release(), arel.release(), rep_len.release(), n_mini_pos.release(), tie_list.release();
 		n_u.release(), n_v.release(), status.release(), mini_pos.release(), hv.release(), u.release(), mv.release(), a.release(), a_tmp.release(), b.release(), small.release();
 		mm2b_ws_destroy(ws), ws = nullptr;
 		h_small.release(), h_read.release(), h_tiles.release();
@@ -204,7 +205,7 @@ bool run_sub(Call &call, Ctx &c, int si)
 	}
 	const int32_t n_tiles = (int32_t)n_tiles64;
 	if (!c.seq.ensure(S + 8, "cudaMalloc(seq)") || !c.seq_off.ensure(R + 1, "cudaMalloc") || !c.tile_off.ensure(R + 1, "cudaMalloc") ||
-	    !c.tile_read.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_cnt.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_mv_off.ensure(n_tiles + 2, "cudaMalloc") || !c.mv_off.ensure(R + 2, "cudaMalloc") ||
+	    !c.tile_read.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_state.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_excl.ensure(n_tiles + 2, "cudaMalloc") || !c.mv_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.rep_len.ensure(R + 1, "cudaMalloc") || !c.n_mini_pos.ensure(R + 1, "cudaMalloc") || !c.n_a.ensure(R + 1, "cudaMalloc") || !c.a_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.tie_list.ensure(R + 1, "cudaMalloc") || !c.n_u.ensure(R + 1, "cudaMalloc") || !c.n_v.ensure(R + 1, "cudaMalloc") || !c.status.ensure(R + 1, "cudaMalloc") ||
 	    !c.u_off.ensure(R + 2, "cudaMalloc") || !c.b_off.ensure(R + 2, "cudaMalloc")) return false;
@@ -218,21 +219,31 @@ bool run_sub(Call &call, Ctx &c, int si)
 	memset(&a, 0, sizeof(a));
 	a.n_reads = R, a.seq = c.seq.p, a.seq_off = c.seq_off.p, a.tile_off = c.tile_off.p, a.tile_read = c.tile_read.p, a.n_tiles = n_tiles;
 	a.k = ix->k, a.w = ix->w, a.max_occ = call.seed.max_occ;
-	a.tile_cnt = c.tile_cnt.p, a.tile_mv_off = c.tile_mv_off.p, a.mv_off = c.mv_off.p;
+	a.tile_state = c.tile_state.p, a.tile_ticket = c.small.p + 8, a.tile_excl = c.tile_excl.p, a.mv_off = c.mv_off.p;
 	a.rep_len = c.rep_len.p, a.n_mini_pos = c.n_mini_pos.p, a.n_a = c.n_a.p, a.a_off = c.a_off.p, a.tie_list = c.tie_list.p, a.tie_count = c.small.p;
 
-	// ---- sketch: count, scan, (sync: how many minimizers), emit
-	int launches = launch_sketch(a, false, st);
-	launches += launch_scan_i32(c.tile_cnt.p, c.tile_mv_off.p, n_tiles, st);
+	// ---- sketch: one pass into a buffer sized for the usual density of minimizers (2 / (w + 1) per base, and half as much again);
+	//      (sync: how many there are) and once more into a larger buffer in the rare case that was not enough
+	int launches = 0;
 	int64_t *h_tot = (int64_t*)((char*)c.h_small.p + (size_t)(R + 1) * 12);       // 8-byte aligned: (R+1)*12 is a multiple of 4 only ...
 	h_tot = (int64_t*)(((uintptr_t)h_tot + 7) & ~(uintptr_t)7);                   // ... so round up (64 spare bytes were reserved)
-	CK(cudaMemcpyAsync(h_tot, c.tile_mv_off.p + n_tiles, 8, cudaMemcpyDeviceToHost, st), "D2H minimizer total");
-	CK(cudaStreamSynchronize(st), "sketch count");
-	const int64_t n_mv = h_tot[0];
-	if (!c.mv.ensure(n_mv + 1, "cudaMalloc(mv)") || !c.occ.ensure(n_mv + 1, "cudaMalloc") || !c.hv.ensure(n_mv + 1, "cudaMalloc") ||
-	    !c.arel.ensure(n_mv + 1, "cudaMalloc") || !c.mini_pos.ensure(n_mv + 1, "cudaMalloc")) return false;
-	a.mv = c.mv.p, a.occ = c.occ.p, a.hv = c.hv.p, a.arel = c.arel.p, a.mini_pos = c.mini_pos.p;
-	launches += launch_sketch(a, true, st);
+	int64_t n_mv = 0;
+	if (!c.mv.ensure(std::max<int64_t>(c.mv.cap, 3 * S / (ix->w + 1) + 1024), "cudaMalloc(mv)")) return false;
+	static const bool tiny_first = getenv("MM2B_TEST_SMALL_MV") && atoi(getenv("MM2B_TEST_SMALL_MV")) > 0;     // test hook: force the second attempt
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		a.mv = c.mv.p, a.mv_cap = tiny_first && attempt == 0 ? std::min<int64_t>(c.mv.cap, 1000) : c.mv.cap;
+		h_tot[0] = 0;
+		if (n_tiles > 0) {
+			launches += launch_sketch(a, st);
+			CK(cudaMemcpyAsync(h_tot, c.tile_excl.p + n_tiles, 8, cudaMemcpyDeviceToHost, st), "D2H minimizer total");
+		}
+		CK(cudaStreamSynchronize(st), "sketch");
+		n_mv = h_tot[0];
+		if (n_mv <= a.mv_cap) break;
+		if (attempt == 1 || !c.mv.ensure(n_mv + 1, "cudaMalloc(mv)")) { if (attempt == 1) set_error("%s%s", "mm2b_map_batch: minimizer buffer", ""); return false; }
+	}
+	if (!c.occ.ensure(n_mv + 1, "cudaMalloc") || !c.hv.ensure(n_mv + 1, "cudaMalloc") || !c.arel.ensure(n_mv + 1, "cudaMalloc") || !c.mini_pos.ensure(n_mv + 1, "cudaMalloc")) return false;
+	a.occ = c.occ.p, a.hv = c.hv.p, a.arel = c.arel.p, a.mini_pos = c.mini_pos.p;
 	launches += launch_read_offsets(a, st);
 	CK(cudaEventRecord(c.ev[1], st), "cudaEventRecord");
 

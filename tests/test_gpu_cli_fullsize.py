@@ -5,7 +5,9 @@ with its own software chaining (oracle/_ref/minimap2-sw) for
   * 50,000 synthetic CCS-like reads (15 kb, ~1 % error), -x asm20      (configs[2]: "bit-exact PAF check")
   * 20,000 synthetic ONT reads (10 kb, ~10 % error), -x map-ont        (configs[1] shape)
 
-against the 100 Mbp random reference.  Both binaries are built in place from /root/reference by oracle/Makefile and travel with
+against the 100 Mbp random reference — both through the per-read drop-in (minimap2-b200: mm_chain_dp on the GPU behind the cross-thread
+batcher) and through the phase-split caller with the seeding front end (minimap2-b200-batch: sketch, seed hits, sort and chaining of a
+whole mini-batch on the GPU, include/mm2seed_b200.h).  The binaries are built in place from /root/reference by oracle/Makefile and travel with
 the repository; the inputs are simulated here (bench_workloads.py), nothing reads /root/reference at run time.
 MM2B_TEST_CCS_READS / MM2B_TEST_ONT_READS shrink the cases for quick runs.
 """
@@ -21,6 +23,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 SW = os.path.join(ROOT, "oracle", "_ref", "minimap2-sw")
 B200 = os.path.join(ROOT, "oracle", "_ref", "minimap2-b200")
+BATCH = os.path.join(ROOT, "oracle", "_ref", "minimap2-b200-batch")
 
 
 def _run(exe, args, threads, env=None):
@@ -46,3 +49,8 @@ def test_cli_paf_identical_at_size(pkg, tmp_path, name, n_reads_env, default_rea
     # an oversubscribed -t keeps hundreds of reads in flight at the per-read boundary (the cross-thread batcher aggregates them)
     md5_gpu, lines_gpu = _run(B200, args, 256)
     assert (md5_gpu, lines_gpu) == (md5_sw, lines_sw), "%s: PAF of the B200 drop-in differs from the reference's software chaining" % name
+    if os.path.exists(BATCH):
+        md5_b, lines_b = _run(BATCH, args, threads)
+        assert (md5_b, lines_b) == (md5_sw, lines_sw), "%s: PAF of the phase-split caller with the GPU seeding front end differs from the reference's" % name
+        md5_b, lines_b = _run(BATCH, args, threads, env={"MM2B_FRONT": "0"})
+        assert (md5_b, lines_b) == (md5_sw, lines_sw), "%s: PAF of the phase-split caller (host seeding, GPU chaining) differs from the reference's" % name

@@ -145,6 +145,27 @@ def test_map_batch_chains_equal_chaining_the_reference_anchors(binding, oracle, 
         gi.close()
 
 
+def test_minimizer_buffer_too_small_is_run_again(pkg, seed_oracle, golden):
+    """The sketch writes into a buffer sized for the usual minimizer density; when a batch has more (low-complexity sequence can push
+    a minimizer at every position) the kernel only counts and the host runs it again with the size it learned.  MM2B_TEST_SMALL_MV=1
+    forces that path (read once per process: run in a child)."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from __graft_entry__ import load_package; b = load_package('binding'); b.init(1)\n"
+            "g = np.load(%r); flat = dict(k=int(g['k']), w=int(g['w']), keys=g['keys'], vals=g['vals'], pos=g['pos'])\n"
+            "blob, off = bytes(g['seq']), g['seq_off']; seqs = [blob[off[i]:off[i + 1]] for i in range(len(off) - 1)]\n"
+            "gi = b.Index(flat); d = b.seed_debug(gi, seqs, int(g['mid_occ']))\n"
+            "import hashlib; print(' '.join(hashlib.sha1(d['mini'][int(d['mini_off'][i]):int(d['mini_off'][i + 1])].tobytes()).hexdigest() for i in range(len(seqs))))\n"
+            "print(' '.join(hashlib.sha1(d['a'][int(d['a_off'][i]):int(d['a_off'][i + 1])].tobytes()).hexdigest() for i in range(len(seqs))))\n"
+            "gi.close(); b.shutdown()\n"
+            % (os.path.dirname(GOLDEN.rstrip('/')).rsplit('/tests', 1)[0], os.path.join(GOLDEN, 'seed_golden.npz')))
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, MM2B_TEST_SMALL_MV="1"), timeout=300)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    lines = out.stdout.decode().strip().splitlines()
+    g = np.load(os.path.join(GOLDEN, "seed_golden.npz"))
+    assert lines[-2].split() == [str(x) for x in g["mv_sha"]] and lines[-1].split() == [str(x) for x in g["a_sha"]]
+
+
 def test_unsupported_configurations_are_refused(binding, golden):
     L = binding.load()
     assert L.mm2b_map_supported(15, 10, 0, 1, 0, 0) == 1
