@@ -99,3 +99,48 @@ def test_batcher_aggregates_many_mm_chain_dp_callers(binding, oracle, pkg):
     for t in th:
         t.join()
     assert not errs, errs[:3]
+
+
+def test_map_batch_over_all_devices(binding, oracle):
+    """The seeding front end shards sub-batches of reads over every bound device (an index replica on each) and concurrent callers
+    share the devices: results equal chaining the seeding oracle's anchors, whatever device a read landed on."""
+    import threading
+    import seedgen
+    from oracle import seed_py
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "seed_golden.npz"))
+    flat = dict(k=int(g["k"]), w=int(g["w"]), keys=g["keys"], vals=g["vals"], pos=g["pos"])
+    blob, off = bytes(g["seq"]), g["seq_off"]
+    seqs = [blob[off[i]:off[i + 1]] for i in range(len(off) - 1)] * 3
+    oi = seed_py.Index(flat)
+    par = oracle.Params()
+    ref = []
+    for q in seqs[:len(seqs) // 3]:
+        mv = seed_py.sketch(q, flat["w"], flat["k"])
+        a, rep, mp = oi.seed(mv, len(q), int(g["mid_occ"]))
+        ref.append((oracle.chain(par, a), rep, len(a)))
+    ref = ref * 3
+    gi = binding.Index(flat)
+    os.environ["MM2B_MAP_SUB_BYTES"] = "20000"
+    errs = []
+
+    def caller():
+        try:
+            res = binding.map_batch(gi, seqs, int(g["mid_occ"]), binding.Params(**par.as_dict()))
+            assert res["stats"]["n_segs"] >= 8
+            for i, (rc, rep, n_a) in enumerate(ref):
+                assert int(res["n_a"][i]) == n_a and int(res["rep_len"][i]) == rep and int(res["status"][i]) == rc["status"], i
+                assert np.array_equal(res["u"][i], rc["u"]) and np.array_equal(res["b"][i], rc["b"]), i
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e)[:300])
+
+    try:
+        th = [threading.Thread(target=caller) for _ in range(3)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    finally:
+        os.environ.pop("MM2B_MAP_SUB_BYTES", None)
+        gi.close()
+    assert not errs, errs
