@@ -3,8 +3,8 @@
 synth_anchor_batch() draws, per read, one collinear cluster (the read's true locus, minimizers every ~5.5 bp of which
 ~1/5 survive 10 % error, with indel drift between reference and query coordinates) plus uniformly scattered random
 seed hits, and packs them exactly as collect_seed_hits does (map.c:232-241): x = rev<<63 | rid<<32 | ref_pos,
-y = q_span<<32 | q_pos, sorted by x.  It is used by __graft_entry__.smoke() and by quick tests; bench.py's headline
-workload comes from workload_seeds (real minimizer sketching + index lookup of simulated reads, in C++).
+y = q_span<<32 | q_pos, sorted by x.  It is used by __graft_entry__.smoke() and by quick tests; bench.py's workloads are the
+anchors the reference's own CLI seeds for simulated reads (bench_workloads.py), this model only with `--source model`.
 """
 import numpy as np
 
