@@ -22,6 +22,7 @@
 #include "seed_kernels.cuh"
 #include "sort_replay.cuh"
 #include <limits.h>
+#include <type_traits>
 
 namespace mm2b {
 
@@ -99,12 +100,17 @@ __device__ __forceinline__ uint32_t hash32(uint32_t key, uint32_t mask)
 // their published counts (tiles are handed out by an atomic ticket so that every predecessor is already running), and writes.
 // tile_state[t] = flag << 62 | count: flag 1 = the tile's own count, 2 = the inclusive prefix up to and including it.
 // If mv is too small for the batch the writes are dropped but the counting goes on: the host sees the total and runs again.
-template <bool K32>
+// K32: 2k < 32, the hash fits 32 bits with room for "invalid" (all ones): the window scans compare 32-bit words.  W: the window size
+// when it is one of the presets' (the scan is unrolled), 0 for any other w.
+template <bool K32, int W>
 __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 {
+	typedef typename std::conditional<K32, uint32_t, uint64_t>::type key_t;
+	constexpr key_t NOKEY = (key_t)~(key_t)0;
 	__shared__ uint64_t X[TILE_SPAN];
+	__shared__ uint32_t H32[K32 ? TILE_SPAN : 1];           // K32: the hashes alone, all ones where X is invalid
 	__shared__ uint64_t pk[TILE_SPAN / 32 + 1];             // 2-bit bases, 32 per word, earlier base in the lower bits
-	__shared__ uint32_t badw[TILE_SPAN / 32];               // one bit per position: ambiguous base or outside the read
+	__shared__ uint32_t badw[TILE_SPAN / 32 + 1];           // one bit per position: ambiguous base or outside the read
 	__shared__ uint8_t zs[TILE_SPAN];                       // strand of the position's k-mer
 	__shared__ int16_t jm_s[SKETCH_TILE];                   // per position: newest minimal entry of the window in front of it ...
 	__shared__ uint8_t ties_s[SKETCH_TILE];                 // ... and whether its hash occurs more than once in that window
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) {
-		pk[TILE_SPAN / 32] = 0;
+		pk[TILE_SPAN / 32] = 0, badw[TILE_SPAN / 32] = 0;
 		tile_s = atomicAdd(s.tile_ticket, 1);
 	}
 	__syncthreads();
@@ -124,8 +130,9 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 	const int L = (int)(s.seq_off[r + 1] - so);
 	const int t0 = (tile - s.tile_off[r]) * SKETCH_TILE;
 	const int pb = t0 - HALO;                               // position of shared-memory index 0
-	const int k = s.k, w = s.w;
+	const int k = s.k, w = W ? W : s.w;
 	const uint64_t mask = (1ull << 2 * k) - 1;
+	const key_t *K = K32 ? (const key_t*)H32 : (const key_t*)X;         // what the window scans compare
 
 	// 1. bases -> 2-bit words and the bitmap of ambiguous positions (warps 0..18 of positions; the CTA has 16 warps)
 	for (int base = warp * 32; base < TILE_SPAN; base += SKETCH_TILE) {
@@ -159,9 +166,12 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 	// 2. X for the positions t0 - w .. t0 + TILE - 1
 	for (int i = HALO - w + tid; i < TILE_SPAN; i += SKETCH_TILE) {
 		uint64_t x = EMPTY;
+		uint32_t h32 = ~0u;
 		int z = 0;
-		if (run_len(i) >= k) {
-			const int p0 = i - k + 1, wi = p0 >> 5, sh = (p0 & 31) * 2;
+		const int p0 = i - k + 1;
+		const uint64_t bad_bits = ((uint64_t)badw[(p0 >> 5) + 1] << 32 | badw[p0 >> 5]) >> (p0 & 31);     // positions p0 .. p0 + 31
+		if ((bad_bits & ((1ull << k) - 1)) == 0) {                          // k valid bases end here: l >= k (sketch.c:113)
+			const int wi = p0 >> 5, sh = (p0 & 31) * 2;
 			uint64_t f = pk[wi] >> sh;
 			if (sh) f |= pk[wi + 1] << (64 - sh);
 			f &= mask;                                              // oldest base in the lowest bits ...
@@ -173,19 +183,22 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 			const uint64_t km = z ? rv : fw;
 			const uint64_t h = K32 ? (uint64_t)hash32((uint32_t)km, (uint32_t)mask) : hash64(km, mask);
 			x = h << 8 | (uint64_t)k;                               // sketch.c:114; kmer_span == k once l >= k
+			h32 = (uint32_t)h;
 		}
 		X[i] = x, zs[i] = (uint8_t)z;
+		if (K32) H32[i] = h32;
 	}
 	__syncthreads();
 
 	// 3. the window in front of this thread's position: its newest minimal entry, and whether that hash is there more than once.
 	//    The window AFTER the step (what the reference rescans when the minimum leaves, sketch.c:126-129) is the next thread's.
 	const int i = HALO + tid, t = t0 + tid;
-	uint64_t xm = EMPTY;
+	key_t xm = NOKEY;
 	int jm = i - w;
 	bool ties = false;
+#pragma unroll
 	for (int j = i - w; j < i; ++j) {
-		const uint64_t xj = X[j];
+		const key_t xj = K[j];
 		if (xj <= xm) ties = xj == xm, xm = xj, jm = j;
 	}
 	jm_s[tid] = (int16_t)jm, ties_s[tid] = ties;
@@ -197,32 +210,32 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 	int cnt = 0;
 	if (t < L) {
 		const int l = run_len(i);
-		const uint64_t xt = X[i];
+		const key_t xt = K[i];
 		int after = jm;                                                     // the minimum after this step (shared index)
-		if (l == w + k - 1 && xm != EMPTY && ties)
-			for (int j = i - w + 1; j < i; ++j) if (X[j] == xm && j != jm) e.mask_s |= 1ull << (j - (i - w + 1));
+		if (l == w + k - 1 && xm != NOKEY && ties)
+			for (int j = i - w + 1; j < i; ++j) if (K[j] == xm && j != jm) e.mask_s |= 1ull << (j - (i - w + 1));
 		if (xt <= xm) {
-			if (l >= w + k && xm != EMPTY) e.first_m = jm;
+			if (l >= w + k && xm != NOKEY) e.first_m = jm;
 			after = i;
 		} else if (jm == i - w) {
-			if (l >= w + k - 1 && xm != EMPTY) e.first_m = jm;
+			if (l >= w + k - 1 && xm != NOKEY) e.first_m = jm;
 			int jn;
 			bool tn;
 			if (tid + 1 < SKETCH_TILE) jn = jm_s[tid + 1], tn = ties_s[tid + 1];
 			else {                                                          // the last position of the tile has no neighbour to ask
-				uint64_t xn = EMPTY;
+				key_t xq = NOKEY;
 				jn = i - w + 1, tn = false;
 				for (int j = i - w + 1; j <= i; ++j) {
-					const uint64_t xj = X[j];
-					if (xj <= xn) tn = xj == xn, xn = xj, jn = j;
+					const key_t xj = K[j];
+					if (xj <= xq) tn = xj == xq, xq = xj, jn = j;
 				}
 			}
-			const uint64_t xn = X[jn];
-			if (l >= w + k - 1 && xn != EMPTY && tn)
-				for (int j = i - w + 1; j <= i; ++j) if (X[j] == xn && j != jn) e.mask_b |= 1ull << (j - (i - w + 1));
+			const key_t xn = K[jn];
+			if (l >= w + k - 1 && xn != NOKEY && tn)
+				for (int j = i - w + 1; j <= i; ++j) if (K[j] == xn && j != jn) e.mask_b |= 1ull << (j - (i - w + 1));
 			after = jn;
 		}
-		if (t == L - 1 && X[after] != EMPTY) e.last_e = after;
+		if (t == L - 1 && K[after] != NOKEY) e.last_e = after;
 		cnt = __popcll(e.mask_s) + (e.first_m >= 0) + __popcll(e.mask_b) + (e.last_e >= 0);
 	}
 	// block-wide exclusive scan of the counts
@@ -234,11 +247,16 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 	}
 	if (lane == 31) warp_sum[warp] = incl;
 	__syncthreads();
-	int before = 0, total = 0;
-	for (int q = 0; q < SKETCH_TILE / 32; ++q) {
-		const int v = warp_sum[q];
-		if (q < warp) before += v;
-		total += v;
+	int before, total;
+	{	// every warp scans the 16 warp totals for itself (one shared-memory read and four shuffles, no second barrier)
+		int v = warp_sum[lane & (SKETCH_TILE / 32 - 1)], sc = v;
+#pragma unroll
+		for (int d = 1; d < SKETCH_TILE / 32; d <<= 1) {
+			const int o = __shfl_up_sync(FULL, sc, d);
+			if ((lane & (SKETCH_TILE / 32 - 1)) >= d) sc += o;
+		}
+		before = __shfl_sync(FULL, sc - v, warp);
+		total = __shfl_sync(FULL, sc, SKETCH_TILE / 32 - 1);
 	}
 	// decoupled look-back: how many minimizers the tiles before this one pushed.  Warp 0 looks at 32 predecessors at a time.
 	if (warp == 0) {
@@ -795,8 +813,16 @@ int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 	if (s.n_tiles <= 0) return 0;
 	cudaMemsetAsync(s.tile_state, 0, (size_t)s.n_tiles * 8, stream);
 	cudaMemsetAsync(s.tile_ticket, 0, sizeof(int), stream);
-	if (2 * s.k <= 32) sketch_kernel<true><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
-	else sketch_kernel<false><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s);
+	const bool k32 = 2 * s.k < 32;
+#define MM2B_SKETCH(W_) do { if (k32) sketch_kernel<true, W_><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s); else sketch_kernel<false, W_><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s); } while (0)
+	switch (s.w) {                          // the presets' window sizes get an unrolled scan (options.c:82-150: 5, 10, 11, 19)
+	case 5: MM2B_SKETCH(5); break;
+	case 10: MM2B_SKETCH(10); break;
+	case 11: MM2B_SKETCH(11); break;
+	case 19: MM2B_SKETCH(19); break;
+	default: MM2B_SKETCH(0); break;
+	}
+#undef MM2B_SKETCH
 	return 1;
 }
 

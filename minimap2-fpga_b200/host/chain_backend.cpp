@@ -284,7 +284,11 @@ struct Backend {
 	std::atomic<int> count_cells{0};
 	Pool pool;
 	cudaEvent_t trace_ev0[64] = {};
-} g;
+};
+// heap-allocated and never destroyed: a host that exits without mm2b_shutdown() (main.c returns early on several error paths; a
+// script that forgets) must not run the destructors of joinable std::threads at exit (std::terminate -> abort -> a core dump of a
+// process with a CUDA context mapped)
+Backend &g = *new Backend();
 
 void job_fail(Job *job)
 {

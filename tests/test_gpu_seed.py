@@ -179,3 +179,33 @@ def test_unsupported_configurations_are_refused(binding, golden):
             binding.map_batch(gi, seqs[:2], mid_occ)
     finally:
         gi.close()
+
+
+def test_empty_and_unseedable_reads(binding, golden):
+    """Reads without a single minimizer (empty, shorter than k, all N) in a batch of their own and mixed with real ones."""
+    flat, seqs, mid_occ = golden
+    gi = binding.Index(flat)
+    try:
+        res = binding.map_batch(gi, [b"", b"NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN", b"ACGTACG", b""], mid_occ)
+        assert res["n_a"].tolist() == [0, 0, 0, 0] and res["n_u"].tolist() == [0, 0, 0, 0] and res["status"].tolist() == [0, 0, 0, 0]
+        mixed = [b"", seqs[0], b"NNNN", seqs[1], b""]
+        res = binding.map_batch(gi, mixed, mid_occ)
+        alone = binding.map_batch(gi, [seqs[0], seqs[1]], mid_occ)
+        for i, j in ((1, 0), (3, 1)):
+            assert int(res["n_a"][i]) == int(alone["n_a"][j]) and np.array_equal(res["u"][i], alone["u"][j]) and np.array_equal(res["b"][i], alone["b"][j])
+            assert np.array_equal(res["mini_pos"][i], alone["mini_pos"][j])
+        assert res["n_a"][[0, 2, 4]].tolist() == [0, 0, 0]
+    finally:
+        gi.close()
+
+
+def test_exit_without_shutdown_does_not_hang(golden):
+    """A host that exits without mm2b_shutdown (main.c returns early on several error paths) must still exit promptly."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys; sys.path.insert(0, %r); from __graft_entry__ import load_package; b = load_package('binding'); b.init(1)\n"
+            "import numpy as np; off = np.array([0, 3], np.int64); a = np.zeros(3, b.ANCHOR); a['x'] = [10, 20, 30]; a['y'] = [(15 << 32) | 10, (15 << 32) | 20, (15 << 32) | 30]\n"
+            "r = b.chain_batch(b.Params(), off, a); print('ok', int(r['n_u'][0]))\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert b"ok" in out.stdout, out.stderr.decode()[-1500:]
