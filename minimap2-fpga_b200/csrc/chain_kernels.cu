@@ -380,9 +380,9 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 // A read in tandem repeats has windows at the max_iter clamp (thousands of anchors) and scans dozens of chunks per anchor; on
 // one warp that is a serial chain of ~100 instructions per chunk.  The heavy-read kernel gives such a read a CTA of HEAVY_WARPS
 // warps and a ring that holds the whole window.  Warp 0 runs the read exactly like the warp-per-read kernel; for a long scan
-// it posts the anchor in a mailbox and all warps take the window's chunks round-robin, HEAVY_WARPS chunks per round:
-//   A  every warp scores its chunk and writes ALL its stamps (chain.c:233) to the ring                           -> barrier
-//   B  every warp reads its cells' stamps and reduces the chunk to a summary that does not depend on the scan's state:
+// it posts the anchor in a mailbox and all warps take the window's chunks round-robin, two per warp and round (32 chunks):
+//   A  every warp scores its chunks and writes ALL their stamps (chain.c:233) to the ring                        -> barrier
+//   B  every warp reads its cells' stamps and reduces each chunk to a summary that does not depend on the scan's state:
 //      the chunk's maximum score and its number of stamped valid cells (a stamp only comes from a nearer cell, and the
 //      nearer chunks stamped in A of this round or earlier)                                                        -> barrier
 //   C  every warp folds the round's summaries in chunk order with the same replicated state (max_f, max_j, n_skip): a chunk
@@ -393,7 +393,10 @@ __device__ __forceinline__ void scan_predecessors(const DpConst &c, const ReadCt
 constexpr int HEAVY_RING = 8192;           // covers max_iter = 5000 entirely: no look-back below the ring in this kernel
 constexpr int HEAVY_WARPS = 16;
 constexpr int COOP_MIN_CELLS = 128;        // windows longer than this are scanned cooperatively
-constexpr int COOP_WORDS = 128;            // mailbox: [0,8) job, [16,48) chunk summaries, [48,112) detailed results
+constexpr int COOP_CPW = 2;                // chunks per warp and round of a cooperative scan
+constexpr int COOP_ROUND = HEAVY_WARPS * COOP_CPW;     // = 32: one summary per lane in the fold
+static_assert(COOP_ROUND == 32 && COOP_CPW == 2, "the fold keeps chunk k's summary in lane k");
+constexpr int COOP_WORDS = 224;            // mailbox: [0,8) job, [16,80) chunk summaries, [80,208) detailed results
 enum { JOB_SCAN = 1, JOB_EXIT = 2 };
 enum { BAR_JOB = 1, BAR_STAMPS = 2, BAR_SUMM = 3, BAR_DETAIL = 4 };
 
@@ -453,59 +456,74 @@ __device__ __forceinline__ bool resolve_records(int32_t sc, unsigned hitv, int l
 }
 
 // The scan of anchor i over [st, i) by all warps of the CTA (same-segment, non-cDNA cost only); w = this warp's index.
+// A round covers COOP_ROUND = 32 chunks (1,024 cells), two per warp: the scans this kernel exists for visit ~900 cells before the
+// max_skip break, so they finish in one round — one barrier per phase instead of two rounds' worth — and lane k of every warp
+// holds chunk k's summary in the fold.
 template <int RING>
 __device__ void coop_scan(const DpConst &c, const Ring &ring, int lane, int w, int i, int st, int32_t xi, int32_t qi, int32_t q_span,
                           int32_t &max_f_out, int32_t &max_j_out)
 {
-	int32_t *summ = ring.coop + 16, *detail = ring.coop + 16 + 2 * HEAVY_WARPS;
+	int32_t *summ = ring.coop + 16, *detail = ring.coop + 16 + 2 * COOP_ROUND;
 	int32_t max_f = q_span, max_j = -1;
 	int n_skip = 0;
 	const int n_chunks = (i - st + 31) >> 5;
 	bool broke = false;
-	for (int g0 = 0; g0 < n_chunks && !broke; g0 += HEAVY_WARPS) {
-		// A: this warp's chunk of the round
-		const int jt = i - 1 - 32 * (g0 + w);
-		const int left = jt - st + 1;                             // <= 0 for a warp without a chunk in the last round
-		const bool act = lane < left;
-		const int j = jt - lane;
-		const int s = j & (RING - 1);
-		const int4 q = ring.a[s];
-		const int32_t pj = q.w;
-		const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)q.x);
-		const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)q.y);
-		const int32_t diff = dr - dq;
-		const int32_t dd = diff < 0 ? -diff : diff;
-		const bool valid = act && dr != 0 && (uint32_t)(dq - 1) < (uint32_t)c.max_dq_same && dd <= c.bw;    // chain.c:202-205
-		const int32_t md = dq < dr ? dq : dr;
-		int32_t sc = md < q_span ? md : q_span;
-		const float fdd = __int2float_rn(dd);
-		const int c_lin = __float2int_rz(__fmul_rn(fdd, c.avg));
-		int lg = (__float_as_int(fdd) >> 23) - 127;
-		lg = lg < 0 ? 0 : lg;
-		sc = valid ? sc - (c_lin + (lg >> 1)) + q.z : INT_MIN;
-		MM2B_CHK(!valid || (j >= st && j < i && pj < j), 0x100);
-		if (valid && pj >= st) ring.b[pj & (RING - 1)].y = i;
-		__syncwarp();
+	for (int g0 = 0; g0 < n_chunks && !broke; g0 += COOP_ROUND) {
+		// A: this warp's chunks of the round (chunk w and chunk w + HEAVY_WARPS)
+		int32_t sc[COOP_CPW];
+		bool valid[COOP_CPW];
+		int jt[COOP_CPW], sl[COOP_CPW];
+#pragma unroll
+		for (int q = 0; q < COOP_CPW; ++q) {
+			jt[q] = i - 1 - 32 * (g0 + w + q * HEAVY_WARPS);
+			const int left = jt[q] - st + 1;                          // <= 0 for a warp without a chunk in the last round
+			const bool act = lane < left;
+			const int j = jt[q] - lane;
+			sl[q] = j & (RING - 1);
+			sc[q] = INT_MIN, valid[q] = false;
+			if (left > 0) {                                           // (warp-uniform)
+				const int4 r = ring.a[sl[q]];
+				const int32_t pj = r.w;
+				const int32_t dr = (int32_t)((uint32_t)xi - (uint32_t)r.x);
+				const int32_t dq = (int32_t)((uint32_t)qi - (uint32_t)r.y);
+				const int32_t diff = dr - dq;
+				const int32_t dd = diff < 0 ? -diff : diff;
+				valid[q] = act && dr != 0 && (uint32_t)(dq - 1) < (uint32_t)c.max_dq_same && dd <= c.bw;    // chain.c:202-205
+				const int32_t md = dq < dr ? dq : dr;
+				int32_t v = md < q_span ? md : q_span;
+				const float fdd = __int2float_rn(dd);
+				const int c_lin = __float2int_rz(__fmul_rn(fdd, c.avg));
+				int lg = (__float_as_int(fdd) >> 23) - 127;
+				lg = lg < 0 ? 0 : lg;
+				sc[q] = valid[q] ? v - (c_lin + (lg >> 1)) + r.z : INT_MIN;
+				MM2B_CHK(!valid[q] || (j >= st && j < i && pj < j), 0x100);
+				if (valid[q] && pj >= st) ring.b[pj & (RING - 1)].y = i;
+			}
+			__syncwarp();
+		}
 		cta_bar(BAR_STAMPS);
-		// B: state-independent summary
-		const int32_t tj = ring.b[s].y;
-		const unsigned hitv = __ballot_sync(FULL, valid && tj == i);
-		const int32_t best = __reduce_max_sync(FULL, sc);
-		if (lane == 0) summ[2 * w] = best, summ[2 * w + 1] = __popc(hitv);
+		// B: state-independent summaries
+		unsigned hitv[COOP_CPW];
+#pragma unroll
+		for (int q = 0; q < COOP_CPW; ++q) {
+			const int32_t tj = ring.b[sl[q]].y;
+			hitv[q] = __ballot_sync(FULL, valid[q] && tj == i);
+			const int32_t best = __reduce_max_sync(FULL, sc[q]);
+			if (lane == 0) summ[2 * (w + q * HEAVY_WARPS)] = best, summ[2 * (w + q * HEAVY_WARPS) + 1] = __popc(hitv[q]);
+		}
 		__syncwarp();
 		cta_bar(BAR_SUMM);
 		// C: fold in chunk order (every warp, same values).  Lane k holds chunk k's summary; votes find the first chunk with a
 		// record and, from a prefix sum of the hit counts, the first chunk in which the counter passes max_skip.
-		int2 mine = make_int2(INT_MIN, 0);
-		if (lane < HEAVY_WARPS) mine = *(const int2*)&summ[2 * lane];
+		const int2 mine = *(const int2*)&summ[2 * lane];
 		__syncwarp();
-		const int in_round = n_chunks - g0 < HEAVY_WARPS ? n_chunks - g0 : HEAVY_WARPS;
+		const int in_round = n_chunks - g0 < COOP_ROUND ? n_chunks - g0 : COOP_ROUND;
 		for (int k0 = 0; k0 < in_round;) {                        // chunks [k0, in_round) are still to be folded
 			const bool todo = lane >= k0 && lane < in_round;
 			const unsigned recs = __ballot_sync(FULL, todo && mine.x > max_f);
 			int h = todo ? mine.y : 0;                            // inclusive prefix sum of the hits over the chunks still to fold
 #pragma unroll
-			for (int d = 1; d < HEAVY_WARPS; d <<= 1) {
+			for (int d = 1; d < COOP_ROUND; d <<= 1) {
 				const int o = __shfl_up_sync(FULL, h, d);
 				if (lane >= d) h += o;
 			}
@@ -514,10 +532,11 @@ __device__ void coop_scan(const DpConst &c, const Ring &ring, int lane, int w, i
 			if (kb < kr) { broke = true; break; }                 // the counter passes max_skip before any record (chain.c:229-231)
 			if (kr == 32) { n_skip += __shfl_sync(FULL, h, in_round - 1); break; }
 			if (kr > k0) n_skip += __shfl_sync(FULL, h, kr - 1);  // up to the chunk with a record; its owner resolves that one in detail
-			if (w == kr) {
+			if (w == (kr & (HEAVY_WARPS - 1))) {
+				const int q = kr / HEAVY_WARPS;
 				int32_t f2 = max_f, j2 = max_j;
 				int s2 = n_skip;
-				const bool b2 = resolve_records(sc, hitv, lane, jt, c.max_skip, f2, j2, s2);
+				const bool b2 = resolve_records(q ? sc[COOP_CPW - 1] : sc[0], q ? hitv[COOP_CPW - 1] : hitv[0], lane, q ? jt[COOP_CPW - 1] : jt[0], c.max_skip, f2, j2, s2);
 				if (lane == 0) *(int4*)&detail[4 * kr] = make_int4(f2, j2, s2, b2 ? 1 : 0);
 				__syncwarp();
 			}

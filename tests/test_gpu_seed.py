@@ -209,3 +209,27 @@ def test_exit_without_shutdown_does_not_hang(golden):
             "r = b.chain_batch(b.Params(), off, a); print('ok', int(r['n_u'][0]))\n" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert b"ok" in out.stdout, out.stderr.decode()[-1500:]
+
+
+def test_pinned_pool_hands_blocks_back(binding):
+    """mm2b_host_alloc / _free go through a pool (pinning costs ~0.5 ms per MB): a freed block is handed out again for a request of
+    about its size, mm2b_host_reserve fills the pool ahead of time, mm2b_host_pool_trim empties it."""
+    import ctypes as C
+    L = binding.load()
+    L.mm2b_host_reserve.restype, L.mm2b_host_reserve.argtypes = None, [C.c_size_t, C.c_int]
+    L.mm2b_host_pool_trim.restype, L.mm2b_host_pool_trim.argtypes = None, []
+    L.mm2b_host_pool_trim()
+    p = L.mm2b_host_alloc(8 << 20)
+    assert p
+    L.mm2b_host_free(p)
+    q = L.mm2b_host_alloc(6 << 20)                   # fits the pooled 8 MB block (at most twice the size asked for)
+    assert q == p
+    r = L.mm2b_host_alloc(1 << 20)                   # too small a request for an 8 MB block, and the pool is empty anyway
+    assert r and r != p
+    L.mm2b_host_free(q), L.mm2b_host_free(r)
+    L.mm2b_host_reserve(4 << 20, 3)
+    got = [L.mm2b_host_alloc(4 << 20) for _ in range(3)]
+    assert len(set(got)) == 3 and all(got)
+    for g in got:
+        L.mm2b_host_free(g)
+    L.mm2b_host_pool_trim()
