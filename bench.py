@@ -254,7 +254,8 @@ def e2e_variants(torch, binding, w, steps, warmup, sync, which, keep_res=True):
         h_b, h_bi = pin(n_anchors, binding.ANCHOR), pin(n_anchors, np.int32)
         modes = {"default": ("default", 0, True, False), "index": ("index", 0, False, True),
                  "host_gather": ("b", binding.F_HOST_GATHER, True, False),
-                 "packed_b": ("b", binding.F_DEVICE_GATHER, True, False)}
+                 "packed_b": ("b", binding.F_DEVICE_GATHER, True, False),
+                 "raw_index": ("index", binding.F_RAW_INPUT, False, True)}
         for name in which:
             mode, flags, want_b, want_bi = modes[name]
             o = dict(bufs)
@@ -461,7 +462,7 @@ def main():
     value = tot_cells / (ms_value * 1e-3) / 1e9
 
     # ---- e2e: pinned host buffers through the host-buffer batch call, one process per GPU ------------------------
-    ev = e2e_variants(torch, binding, w, args.steps, args.warmup, barrier, ["default", "index", "host_gather", "packed_b"] if world == 1 else ["default", "index"])
+    ev = e2e_variants(torch, binding, w, args.steps, args.warmup, barrier, ["default", "index", "raw_index", "host_gather", "packed_b"] if world == 1 else ["default", "index", "raw_index"])
     ms_e2e = {k: max_over_ranks(v["ms"]) for k, v in ev.items()}
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (value and e2e)
     est = ev["default"]["stats"]
@@ -478,7 +479,8 @@ def main():
             "index": "mm2b_chain_batch_ex with bi[] (what the product's own callers use: mm_chain_dp's batcher and the phase-split caller hold a[]): input packed to 8 B/anchor by the "
                      "library's helper threads, chained anchors back as int32 indices",
             "host_gather": "mm2b_chain_batch_ex(MM2B_F_HOST_GATHER): packed input, int32 indices over PCIe, b[] gathered from the caller's a[] by the library's helper threads",
-            "packed_b": "mm2b_chain_batch_ex(MM2B_F_DEVICE_GATHER): packed input, b[] as 16-byte anchors from the device"}
+            "packed_b": "mm2b_chain_batch_ex(MM2B_F_DEVICE_GATHER): packed input, b[] as 16-byte anchors from the device",
+            "raw_index": "mm2b_chain_batch_ex(MM2B_F_RAW_INPUT) with bi[]: 16 B/anchor in as it is (no host pass at all), int32 indices out: the least host memory traffic per anchor"}
     e2e = e2e_obj("default", apis["default"])
     e2e["variants"] = {k: e2e_obj(k, apis[k]) for k in ev if k != "default"}
     e2e["host_threads"] = "helper pool of the library (MM2B_HOST_THREADS, default min(cores-2, 16)) + 1 worker per device"
@@ -498,7 +500,7 @@ def main():
             ws = None
             binding.init(list(range(world)))
             ceiling = copy_ceiling(torch, list(range(world)))
-            mv = e2e_variants(torch, binding, big, args.steps, args.warmup, lambda: None, ["default", "index"], keep_res=False)
+            mv = e2e_variants(torch, binding, big, args.steps, args.warmup, lambda: None, ["default", "index", "raw_index"], keep_res=False)
             binding.shutdown()
             cells_all = tot_cells
             multi = {k: {"value": cells_all / (v["ms"] * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": v["ms"], "reads_per_s": (len(big_off) - 1) / (v["ms"] * 1e-3),
@@ -608,7 +610,7 @@ def main():
             m = multi["default"]
             line["e2e"] = {"value": m["value"], "unit": "GCUPS", "ms_per_step": m["ms_per_step"], "reads_per_s": m["reads_per_s"], "h2d_bytes_per_step": m["h2d_bytes_per_step"],
                            "d2h_bytes_per_step": m["d2h_bytes_per_step"], "api": "ONE mm2b_chain_batch call from rank 0 over all %d devices (per-device worker threads inside the library) on %d reads"
-                           % (world, int(tot_reads)), "stage_ms_sum_over_subbatches": m["stage_ms_sum_over_subbatches"], "variants": {"index": multi["index"]},
+                           % (world, int(tot_reads)), "stage_ms_sum_over_subbatches": m["stage_ms_sum_over_subbatches"], "variants": {k: multi[k] for k in ("index", "raw_index") if k in multi},
                            "copy_ceiling_GBps": multi["copy_ceiling"]}
         print(json.dumps(line), flush=True)
     binding.shutdown()

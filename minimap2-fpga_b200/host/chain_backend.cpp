@@ -1012,8 +1012,8 @@ static void reserve_for_mapping_now(size_t seq_bytes)
 {
 	if (seq_bytes == 0) return;
 	// what host/map_batch.cpp and host/map_backend.cpp will ask for: one block for the staged sequences, and per sub-batch of
-	// sequence (MM2B_MAP_SUB_BYTES, 96 MB) the chained anchors (~0.6 B per base) and mini_pos (~0.75 B per base) coming back
-	const size_t sub = (size_t)96 << 20;
+	// sequence (MM2B_MAP_SUB_BYTES, 64 MB) the chained anchors (~0.6 B per base) and mini_pos (~0.75 B per base) coming back
+	const size_t sub = (size_t)64 << 20;
 	mm2b_host_reserve(seq_bytes + seq_bytes / 8 + 4096, 1);
 	mm2b_host_reserve(sub, 2 * (int)((seq_bytes + sub - 1) / sub) + 2);
 }

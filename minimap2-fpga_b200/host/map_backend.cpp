@@ -2,7 +2,7 @@
 // sequences through sketch -> seed -> sort -> chain on the GPU.  It replaces, for a whole mini-batch at once, the first half of the
 // reference's mm_map_frag (/root/reference/map.c:287-316): collect_minimizers, collect_seed_hits and the mm_chain_dp call.
 //
-// Reads are cut into sub-batches by sequence bytes; per device a few contexts (stream + device buffers that only ever grow) take
+// Reads are cut into sub-batches by sequence bytes; per device six contexts (stream + device buffers that only ever grow) take
 // sub-batches from a shared counter, so H2D, kernels and D2H of neighbouring sub-batches overlap.  How much the later stages need
 // (minimizers, anchors, chained anchors) is only known on the device, so a sub-batch has three short host round trips: the
 // minimizer total after the count pass of the sketch, the anchor total after the matches, the output totals after chaining.
@@ -375,7 +375,7 @@ int64_t env_ll(const char *name, int64_t dflt)
 
 void cut_subs(Call &call, int64_t n_reads)
 {
-	const int64_t sub_bytes = env_ll("MM2B_MAP_SUB_BYTES", 96ll << 20), sub_reads = 1 << 18;     // (kernels over a few thousand reads do not fill the GPU)
+	const int64_t sub_bytes = env_ll("MM2B_MAP_SUB_BYTES", 64ll << 20), sub_reads = 1 << 18;     // (kernels over a few thousand reads do not fill the GPU)
 	for (int64_t r0 = 0; r0 < n_reads;) {
 		const int64_t lim = call.seq_off[r0] + sub_bytes;
 		int64_t r1 = std::upper_bound(call.seq_off + r0 + 1, call.seq_off + n_reads + 1, lim) - call.seq_off - 1;
@@ -389,7 +389,7 @@ void cut_subs(Call &call, int64_t n_reads)
 void run_call(Call &call)
 {
 	const int n_dev = (int)call.idx->dev.size();
-	const int per_dev = (int)env_ll("MM2B_MAP_CTX", 3);
+	const int per_dev = (int)env_ll("MM2B_MAP_CTX", 6);      // measured: 2 / 3 / 4 / 6 contexts -> 1.09 / 1.19 / 1.27 / 1.37 M reads/s (profiles/r2r_front_sweep.txt)
 	const int n_workers = (int)std::min<int64_t>((int64_t)n_dev * per_dev, (int64_t)call.subs.size());
 	std::vector<std::thread> th;
 	for (int i = 1; i < n_workers; ++i) th.emplace_back(worker, &call, call.idx->dev[(size_t)(i % n_dev)].device);
