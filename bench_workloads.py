@@ -209,7 +209,7 @@ def real_seed_batch(name, n_reads, seed, threads=None, verbose=False):
             meta = dict(preset=name, reads_requested=n_reads, calls_recorded=len(w["off"]) - 1, anchors=int(w["off"][-1]), seed=seed, par=list(w["par"]),
                         cli=" ".join(["minimap2-sw"] + PRESETS[name][2]), paf_md5=paf_md5, paf_lines=paf_lines, simulate_s=round(t_sim, 1), seed_and_chain_s=round(t_map, 1))
             os.remove(dump)
-            if name != "map-ont":           # map-ont keeps its reads: the seeding front end's bench line maps the sequences themselves
+            if name not in ("map-ont", "asm20"):    # these keep their reads: the seeding front end maps the sequences themselves
                 os.remove(q)
             json.dump(meta, open(os.path.join(d, "meta.json"), "w"))
     meta = json.load(open(os.path.join(d, "meta.json")))
