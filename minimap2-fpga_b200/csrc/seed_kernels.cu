@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small utilities: exclusive prefix sums over a few thousand entries (one CTA), per-read minimizer offsets
+// Small utilities: exclusive prefix sum over the reads of a sub-batch (one CTA), per-read minimizer offsets
 // ---------------------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(1024) scan_kernel(const T *in, int64_t *out, int64_t n)
@@ -826,11 +826,6 @@ int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 	return 1;
 }
 
-int launch_scan_i32(const int32_t *in, int64_t *out, int64_t n, cudaStream_t stream)
-{
-	scan_kernel<int32_t><<<1, 1024, 0, stream>>>(in, out, n);
-	return 1;
-}
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream)
 {
 	scan_kernel<int64_t><<<1, 1024, 0, stream>>>(in, out, n);

@@ -53,8 +53,7 @@ struct SeedArgs {
 int launch_index_build(const DeviceIndex &ix, const uint64_t *d_keys, const uint64_t *d_vals, cudaStream_t stream);
 int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, const uint64_t *raw_minimizers, int32_t *occ, uint64_t *hv, cudaStream_t stream);
 int launch_sketch(const SeedArgs &s, cudaStream_t stream);
-int launch_scan_i32(const int32_t *in, int64_t *out, int64_t n, cudaStream_t stream);      // out[0..n]: exclusive prefix, out[n] = total
-int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream);
+int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream);      // out[0..n]: exclusive prefix, out[n] = total
 int launch_read_offsets(const SeedArgs &s, cudaStream_t stream);                            // mv_off[r] = tile_excl[tile_off[r]]
 int launch_matches(const SeedArgs &s, int n_sms, cudaStream_t stream);                      // collect_matches per read
 int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream);

@@ -97,6 +97,15 @@ def test_seeding_front_end_on_the_b200(cases):
 
 
 @pytest.mark.gpu
+def test_front_end_many_small_mini_batches_on_the_b200(cases):
+    """-K 1k / -K 20k: hundreds of tiny mm2b_map_batch calls, so contexts, pinned segments and the staging buffer are recycled."""
+    if not os.path.exists(B200):
+        pytest.skip("oracle/_ref/minimap2-b200-batch was not built (needs /root/reference at build time)")
+    _check(B200, cases, 4, only=("syn_ont", "syn_ccs", "inv_map-ont", "tandem"), extra=("-K", "1k"))
+    _check(B200, cases, 4, only=("syn_ont", "splice"), extra=("-K", "20k"))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("threads", [1, 8])
 def test_phase_split_with_the_b200_backend(cases, threads):
     if not os.path.exists(B200):
