@@ -229,8 +229,9 @@ def device_value(torch, binding, w, local_rank, steps, warmup, barrier=None):
         db.run()
         k1.append(db.chain_kernel_ms())
     res = db.results()
+    st_timed = db.stats()
     db.close()
-    return dict(ms=ms, k1_ms=sum(k1) / len(k1), cells=int(st.cells_ref), stats=st, launches=launches, res=res)
+    return dict(ms=ms, k1_ms=sum(k1) / len(k1), cells=int(st.cells_ref), stats=st, stats_timed=st_timed, launches=launches, res=res)
 
 
 def e2e_variants(torch, binding, w, steps, warmup, sync, which, keep_res=True):
@@ -559,6 +560,43 @@ def main():
                                               "cells_per_step": d5["cells"], "value": d5["cells"] / (d5["ms"] * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": d5["ms"],
                                               "kernel_ms": d5["k1_ms"], "reads_per_s": (len(off5) - 1) / (d5["ms"] * 1e-3)}
                     w5 = d5 = None
+                    # long-read segmenting: eight recorded reads at a time merged into one chimeric read (their anchors together, sorted by x,
+                    # the query coordinates of each shifted behind the previous one's): the loci are x-gap cut points (chain.c:192), the library
+                    # cuts such reads into pieces filled by warps of their own.  Checked against the oracle; timed with and without cutting.
+                    grp = 8
+                    parts, offs = [], [0]
+                    for g0 in range(0, len(n) - grp + 1, grp):
+                        qshift, chunk = 0, []
+                        for r in range(g0, g0 + grp):
+                            ar = wo["a"][wo["off"][r]:wo["off"][r + 1]].copy()
+                            ar["y"] += np.uint64(qshift)
+                            qshift += 1 << 20
+                            chunk.append(ar)
+                        ch = np.concatenate(chunk)
+                        parts.append(ch[np.argsort(ch["x"], kind="stable")])
+                        offs.append(offs[-1] + len(ch))
+                    wc = dict(off=np.asarray(offs, np.int64), a=np.concatenate(parts), par=wo["par"], ref=None)
+                    dc = device_value(torch, binding, wc, local_rank, steps=min(args.steps, 5), warmup=3)
+                    os.environ["MM2B_SEG"] = "0"
+                    try:
+                        dn = device_value(torch, binding, wc, local_rank, steps=min(args.steps, 5), warmup=3)
+                    finally:
+                        os.environ.pop("MM2B_SEG", None)
+                    from oracle import oracle_py as O
+                    oref = O.replay(O.Params(**wc["par"]), wc["off"], wc["a"], n_threads=os.cpu_count() or 1)
+                    rc_ = dc["res"]
+                    bad = int(np.count_nonzero(rc_["n_u"] != oref["n_u"]) + np.count_nonzero(rc_["n_v"].astype(np.int64) != oref["n_v"].astype(np.int64)))
+                    if bad == 0:
+                        for r in range(len(offs) - 1):
+                            o_, nu_ = int(offs[r]), int(oref["n_u"][r])
+                            bad += int(not np.array_equal(rc_["u"][int(rc_["u_off"][r]):int(rc_["u_off"][r]) + nu_], oref["u"][o_:o_ + nu_]))
+                    others["ultralong_chimeric"] = {"workload": "the ultra-long reads merged eight at a time into chimeric reads: %d reads, %d anchors (mean %d per read)"
+                                                                % (len(offs) - 1, int(offs[-1]), int(offs[-1]) // max(1, len(offs) - 1)),
+                                                    "cells_per_step": dc["cells"], "value": dc["cells"] / (dc["ms"] * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": dc["ms"],
+                                                    "reads_cut_into_pieces": int(dc["stats_timed"].n_cut_reads), "ms_per_step_without_cutting": dn["ms"],
+                                                    "value_without_cutting": dn["cells"] / (dn["ms"] * 1e-3) / 1e9,
+                                                    "parity_check": {"reads": len(offs) - 1, "mismatching_reads_or_entries": bad, "checked": "n_u, n_v, u[] of every read against the oracle"}}
+                    wc = dc = dn = oref = None
             except Exception as e:      # noqa: BLE001
                 others[name] = {"error": repr(e)[:300]}
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MM2B_ABI_VERSION 3
+#define MM2B_ABI_VERSION 4
 
 /* == mm128_t (minimap.h:53).  x = rev<<63 | rid<<32 | ref_pos;  y = seg_id<<48 | flags(40..43) | q_span<<32 | q_pos */
 typedef struct { uint64_t x, y; } mm2b_anchor_t;
@@ -66,6 +66,7 @@ typedef struct {
 	int64_t h2d_bytes, d2h_bytes;    /* bytes copied host->device / device->host by this call */
 	int64_t n_packed_subs, n_raw_subs; /* sub-batches whose anchors went over as 8-byte words + runs / as 16-byte mm128_t */
 	double  pack_ms, gather_ms;      /* summed wall time of the host-side packing / b[] gathering tasks (over all helper threads) */
+	int64_t n_cut_reads;             /* long reads cut at x-gap cut points (chain.c:192) into pieces filled by warps of their own */
 } mm2b_stats_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */

@@ -44,7 +44,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_reads", "n_anchors", "n_chains", "n_chained", "cells_issued", "cells_ref", "window_cells", "n_general_reads")] + \
                [(k, C.c_double) for k in ("h2d_ms", "kernel_ms", "d2h_ms")] + [("n_heavy_reads", C.c_int64)] + \
-               [(k, C.c_int64) for k in ("h2d_bytes", "d2h_bytes", "n_packed_subs", "n_raw_subs")] + [(k, C.c_double) for k in ("pack_ms", "gather_ms")]
+               [(k, C.c_int64) for k in ("h2d_bytes", "d2h_bytes", "n_packed_subs", "n_raw_subs")] + [(k, C.c_double) for k in ("pack_ms", "gather_ms")] + [("n_cut_reads", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -36,6 +36,8 @@ void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed);
 
 using namespace mm2b;
 
+static constexpr int SEG_CAP = 16384;       // reads cut into pieces per batch at most; further long reads stay whole
+
 struct mm2b_workspace {
 	int device, n_sms;
 	int64_t max_anchors, max_reads;
@@ -46,6 +48,9 @@ struct mm2b_workspace {
 	int heavy_on;               // MM2B_HEAVY (default 1)
 	long long heavy_min_cells;  // MM2B_HEAVY_MIN_CELLS: estimated window cells from which a read counts as heavy
 	int64_t longest_hint;       // mm2b_ws_set_longest_read: longest read of the next batch, or -1
+	int seg_on, seg_min_read, seg_min_piece;    // MM2B_SEG (default 1), MM2B_SEG_MIN_READ, MM2B_SEG_MIN_PIECE: long-read segmenting
+	SegRead *seg_reads;         // SEG_CAP reads cut per batch at most
+	int32_t *seg_items, *seg_done;
 	int *small;                 // [0] work counter, [2] heavy-read count, [3] heavy-read cursor, [64..320) length buckets
 	unsigned long long *counters;   // [0..5) statistics, [6..8) output cursors
 	int32_t *dbg_fpv;           // 3 * max_anchors when MM2B_KEEP_FPV=1
@@ -141,6 +146,9 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	{ const char *e = getenv("MM2B_COUNT_CELLS"); ws->count_cells = e && atoi(e) > 0; }
 	{ const char *e = getenv("MM2B_HEAVY"); ws->heavy_on = e ? atoi(e) != 0 : 1; }
 	{ const char *e = getenv("MM2B_HEAVY_MIN_CELLS"); ws->heavy_min_cells = e ? atoll(e) : 16ll << 20; }
+	{ const char *e = getenv("MM2B_SEG"); ws->seg_on = e ? atoi(e) != 0 : 1; }
+	{ const char *e = getenv("MM2B_SEG_MIN_READ"); ws->seg_min_read = e && atoi(e) > 0 ? atoi(e) : 8192; }
+	{ const char *e = getenv("MM2B_SEG_MIN_PIECE"); ws->seg_min_piece = e && atoi(e) > 0 ? atoi(e) : 2048; }
 	cudaDeviceGetAttribute(&ws->n_sms, cudaDevAttrMultiProcessorCount, device);
 	const size_t sz_scratch = (size_t)max_anchors * SCRATCH_BYTES_PER_ANCHOR;
 	const size_t sz_order = (size_t)max_reads * sizeof(int32_t);
@@ -150,7 +158,10 @@ mm2b_workspace_t *mm2b_ws_create(int device, int64_t max_anchors, int64_t max_re
 	       && cuda_ok(cudaMalloc(&ws->heavy_list, sz_order), "cudaMalloc(heavy_list)")
 	       && cuda_ok(cudaMalloc(&ws->heavy_flag, (size_t)max_reads), "cudaMalloc(heavy_flag)")
 	       && cuda_ok(cudaMalloc(&ws->small, 512 * sizeof(int)), "cudaMalloc(small)")
-	       && cuda_ok(cudaMalloc(&ws->counters, 8 * sizeof(unsigned long long)), "cudaMalloc(counters)");
+	       && cuda_ok(cudaMalloc(&ws->counters, 8 * sizeof(unsigned long long)), "cudaMalloc(counters)")
+	       && cuda_ok(cudaMalloc(&ws->seg_reads, SEG_CAP * sizeof(SegRead)), "cudaMalloc(seg_reads)")
+	       && cuda_ok(cudaMalloc(&ws->seg_items, SEG_CAP * SEG_MAX_PIECES * sizeof(int32_t)), "cudaMalloc(seg_items)")
+	       && cuda_ok(cudaMalloc(&ws->seg_done, SEG_CAP * sizeof(int32_t)), "cudaMalloc(seg_done)");
 	ws->bytes = sz_scratch + 2 * sz_order + (size_t)max_reads + 512 * sizeof(int) + 64;
 	if (ok && keep && atoi(keep) > 0) {
 		ok = cuda_ok(cudaMalloc(&ws->dbg_fpv, (size_t)max_anchors * 12), "cudaMalloc(dbg_fpv)");
@@ -169,6 +180,7 @@ void mm2b_ws_destroy(mm2b_workspace_t *ws)
 	if (ws->ev_k1[0]) cudaEventDestroy(ws->ev_k1[0]);
 	if (ws->ev_k1[1]) cudaEventDestroy(ws->ev_k1[1]);
 	cudaFree(ws->scratch), cudaFree(ws->order), cudaFree(ws->heavy_list), cudaFree(ws->heavy_flag), cudaFree(ws->small), cudaFree(ws->counters), cudaFree(ws->dbg_fpv);
+	cudaFree(ws->seg_reads), cudaFree(ws->seg_items), cudaFree(ws->seg_done);
 	free(ws);
 }
 
@@ -204,11 +216,19 @@ static int chain_device(mm2b_workspace_t *ws, const mm2b_params_t *par, int64_t 
 	// (same-segment genomic cost) and its ring holds a whole window; the cell tally is a warp-per-read feature.
 	// a window has at most max_iter cells: a batch whose longest read has fewer than heavy_min_cells / max_iter anchors has no heavy read
 	const bool may_have_heavy = ws->longest_hint < 0 || (ws->longest_hint >= 64 && ws->longest_hint * (int64_t)par->max_iter >= ws->heavy_min_cells);
+	// Long reads with usable x-gap cut points are cut into pieces (long-read segmenting, chain_kernels.cu); like the heavy-read kernel
+	// this is off while cells are tallied or f/p/v are kept for tests.
+	const bool may_have_long = ws->longest_hint < 0 || ws->longest_hint >= ws->seg_min_read;
 	ws->longest_hint = -1;
 	if (ws->heavy_on && may_have_heavy && !ws->count_cells && !par->is_cdna && par->gap_scale == 1.0f && par->n_segs <= 1 && par->bw >= 0 && par->bw < (1 << 24)
 	    && par->max_dist_x > 0 && par->max_dist_y > 0 && par->max_iter > heavy_min_window() && (int64_t)par->max_iter + 64 <= heavy_ring_slots()) {
 		ba.heavy_flag = ws->heavy_flag, ba.heavy_list = ws->heavy_list, ba.heavy_count = ws->small + 2, ba.heavy_counter = ws->small + 3;
 		ba.heavy_min_cells = ws->heavy_min_cells, ba.heavy_cap = ws->n_sms;
+	}
+	if (ws->seg_on && may_have_long && !ws->count_cells && !ws->dbg_fpv && par->max_dist_x > 0) {
+		ba.heavy_flag = ws->heavy_flag;
+		ba.seg_reads = ws->seg_reads, ba.seg_items = ws->seg_items, ba.seg_done = ws->seg_done, ba.seg_ctl = ws->small + 8;
+		ba.seg_cap = SEG_CAP, ba.seg_min_read = ws->seg_min_read, ba.seg_min_piece = ws->seg_min_piece;
 	}
 	cudaEventRecord(ws->ev_k1[0], stream);
 	launches += launch_chain(ba, ws->n_sms, stream);
@@ -264,7 +284,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	int prev = -1;
 	cudaGetDevice(&prev);
 	if (prev != ws->device) cudaSetDevice(ws->device);
-	unsigned long long c[5] = {0, 0, 0, 0, 0};
+	unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
 	int64_t tot[2] = {0, 0};
 	bool ok = cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize")
 	       && cuda_ok(cudaMemcpy(c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
@@ -276,7 +296,7 @@ int mm2b_ws_stats(mm2b_workspace_t *ws, void *stream_, mm2b_stats_t *st)
 	st->n_reads = ws->last_reads, st->n_anchors = ws->last_anchors;
 	st->n_chains = tot[0], st->n_chained = tot[1];
 	st->cells_issued = (int64_t)c[0] * 32, st->n_general_reads = (int64_t)c[1], st->cells_ref = (int64_t)c[2], st->window_cells = (int64_t)c[3];
-	st->n_heavy_reads = (int64_t)c[4];
+	st->n_heavy_reads = (int64_t)c[4], st->n_cut_reads = (int64_t)c[5];
 	if (prev >= 0 && prev != ws->device) cudaSetDevice(prev);
 	return ok ? MM2B_OK : MM2B_ERR_CUDA;
 }

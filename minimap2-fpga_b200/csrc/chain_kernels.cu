@@ -600,9 +600,11 @@ __device__ __forceinline__ void chain_block(const DpConst &c, const ReadCtx &rc,
 // st_i = max(lower_bound{s : x_s + max_dist_x >= x_i}, i - max_iter) since the input is sorted by x.  Anchors whose window is empty
 // (isolated seed hits: ~40 % of a noisy ONT read) are final at that point; only the others take the sequential step.
 // ---------------------------------------------------------------------------------------------------------------
-template <int RING, bool GENERAL, bool COUNT, bool COOP>
+// RANGED: fill only the anchors [k_begin, k_end) of the read, where k_begin is a cut point — a[k_begin].x > a[k_begin - 1].x + max_dist_x,
+// so no anchor from k_begin on can reach one before it (chain.c:192) and the piece is an independent DP (long-read segmenting).
+template <int RING, bool GENERAL, bool COUNT, bool COOP, bool RANGED = false>
 __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, bool lo_safe, int32_t *smem, int32_t *coop, int lane,
-                        unsigned long long &n_chunks64, unsigned long long &n_cells64, unsigned long long &n_window64)
+                        unsigned long long &n_chunks64, unsigned long long &n_cells64, unsigned long long &n_window64, int k_begin = 0, int k_end = 0)
 {
 	Ring ring;
 	ring.a = (int4*)smem, ring.b = (int2*)(smem + 4 * RING), ring.coop = coop;
@@ -615,13 +617,14 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 	c.is_cdna = par.is_cdna != 0, c.avg = avg, c.gap_scale = (double)par.gap_scale;
 	const uint64_t win = (uint64_t)(int64_t)par.max_dist_x;
 	unsigned n_chunks = 0, n_cells = 0;
-	int st_carry = 0;           // window start of the previous block's last anchor (window starts never move backwards)
-	int run_carry = 0;          // first anchor of the run of equal high words (strand, rid) the previous block ended in
+	const int kb = RANGED ? k_begin : 0, ke = RANGED ? k_end : n;
+	int st_carry = kb;          // window start of the previous block's last anchor (window starts never move backwards)
+	int run_carry = kb;         // first anchor of the run of equal high words (strand, rid) the previous block ended in
 	uint32_t hi_carry = 0;      // ... and that high word
 
-	for (int base = 0; base < n; base += 32) {
+	for (int base = kb & ~31; base < ke; base += 32) {
 		const int k = base + lane;
-		const bool in = k < n;
+		const bool in = k < ke && (!RANGED || k >= kb);
 		uint64_t x = 0, y = 0;
 		if (in) {
 			const ulonglong2 t = __ldg(A + k);
@@ -645,7 +648,7 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 		const uint32_t xh = (uint32_t)(x >> 32);
 		uint32_t xh_prev = __shfl_up_sync(FULL, xh, 1);
 		if (lane == 0) xh_prev = hi_carry;
-		const unsigned chg = __ballot_sync(FULL, in && (k == 0 || xh != xh_prev)) & (lanemask_lt(lane) | (1u << lane));
+		const unsigned chg = __ballot_sync(FULL, in && (k == kb || xh != xh_prev)) & (lanemask_lt(lane) | (1u << lane));
 		const int run_k = chg ? base + (31 - __clz(chg)) : run_carry;
 		// Lower bound by halving steps (no data-dependent branch, the same trip count for all lanes): pos = last index known to
 		// be out of reach, starting just before the range.
@@ -693,7 +696,7 @@ __device__ void dp_fill(const mm2b_params_t &par, const ReadCtx &rc, float avg, 
 		unsigned todo = __ballot_sync(FULL, in && st_k < k);
 		const bool deep_block = __any_sync(FULL, in && st_k < ring_lo);    // some window in this block reaches below the ring
 		{
-			const int last_lane = (n - base < 32 ? n - base : 32) - 1;
+			const int last_lane = (ke - base < 32 ? ke - base : 32) - 1;
 			st_carry = __shfl_sync(FULL, st_k, last_lane);
 			run_carry = __shfl_sync(FULL, run_k, last_lane);
 			hi_carry = __shfl_sync(FULL, xh, last_lane);
@@ -1117,6 +1120,192 @@ chain_reads_kernel(const BatchArgs args)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Long-read segmenting.  If a[k].x > a[k-1].x + max_dist_x then no anchor from k on can have a predecessor before k (chain.c:192: the
+// window start st moves up to k and never back), so the DP over [k, ...) does not depend on anything before k: k is a cut point
+// and the pieces between cut points are independent fills.  A read whose cut points give at least two pieces of seg_min_piece
+// anchors (reads spanning several loci: chimeric reads, repeats with copies further apart than max_dist_x) is cut here; its pieces
+// are filled concurrently by different warps and the warp that finishes the read's last piece runs the extraction, which is per
+// read (chain.c:348-422).  A read that is one collinear chain has no usable cut point: most of a simulated read's cut points
+// isolate single seed hits, and those are settled 32 at a time by the fill anyway.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) segment_kernel(const BatchArgs args)
+{
+	__shared__ int32_t starts[SEG_MAX_PIECES + 1];
+	__shared__ unsigned long long sum_s;
+	__shared__ unsigned seg_diff_s, max_xl_s;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t win = (uint64_t)(int64_t)args.par.max_dist_x;
+	// One CTA per long read.  The processing order (longest reads first, 8 length buckets per octave) says where the long reads are:
+	// slots are taken until the reads are clearly shorter than seg_min_read.
+	for (int64_t slot = blockIdx.x; slot < args.n_reads; slot += gridDim.x) {
+		const int64_t r = args.order ? args.order[slot] : slot;
+		const int64_t o = args.off[r], n64 = args.off[r + 1] - o;
+		if (args.order && n64 * 10 < (int64_t)args.seg_min_read * 9) break;           // (block-uniform) the rest of the order is shorter still
+		if (n64 < args.seg_min_read || n64 >= (1ll << 31) || args.heavy_flag[r]) continue;
+		const int n = (int)n64, n_blocks = (n + 31) >> 5;
+		const ulonglong2 *A = (const ulonglong2*)(args.a + o);
+		uint8_t *scr = args.scratch + (size_t)o * SCRATCH_BYTES_PER_ANCHOR;
+		int32_t *T = (int32_t*)(scr + 20 * (size_t)n);
+		uint32_t *cutw = (uint32_t*)(scr + 24 * (size_t)n);                 // the read's U region: one word of cut flags per 32 anchors
+		if (threadIdx.x == 0) sum_s = 0, seg_diff_s = 0, max_xl_s = 0;
+		__syncthreads();
+		uint64_t sum = 0;
+		uint32_t seg_diff = 0, max_xl = 0;
+		const uint32_t seg0 = (uint32_t)(__ldg(&A[0].y) >> SEG_SHIFT & 0xff);
+		// Pass 1, all warps, no dependency between blocks of 32 anchors: which anchors are cut points, and the sums the read's
+		// prologue needs (chain.c:46-49); t[] is zeroed here for the pieces' fills.
+#pragma unroll 2
+		for (int blk = warp; blk < n_blocks; blk += 8) {
+			const int k = (blk << 5) + lane;
+			uint64_t x = 0, xp = 0;
+			if (k < n) {
+				const ulonglong2 t = __ldg(A + k);
+				x = t.x;
+				sum += t.y >> 32 & 0xff;
+				seg_diff |= (uint32_t)(t.y >> SEG_SHIFT & 0xff) ^ seg0;
+				max_xl = max_xl > (uint32_t)t.x ? max_xl : (uint32_t)t.x;
+				T[k] = 0;
+				if (k > 0) xp = __ldg(&A[k - 1].x);
+			}
+			// (no cut where x + max_dist_x wraps: fewer cuts are always correct)
+			const unsigned cuts = __ballot_sync(FULL, k < n && k > 0 && xp + win >= xp && x > xp + win);
+			if (lane == 0) cutw[blk] = cuts;
+		}
+#pragma unroll
+		for (int d = 16; d; d >>= 1) {
+			sum += __shfl_xor_sync(FULL, sum, d);
+			seg_diff |= __shfl_xor_sync(FULL, seg_diff, d);
+			const uint32_t m = __shfl_xor_sync(FULL, max_xl, d);
+			max_xl = max_xl > m ? max_xl : m;
+		}
+		if (lane == 0) atomicAdd(&sum_s, (unsigned long long)sum), atomicOr(&seg_diff_s, seg_diff), atomicMax(&max_xl_s, max_xl);
+		__syncthreads();                                                    // cutw[] and the sums are in place (block-scope visibility)
+		if (warp != 0) continue;
+		sum = sum_s, seg_diff = seg_diff_s, max_xl = max_xl_s;
+		// Pass 2: a piece must hold seg_min_piece anchors that HAVE a predecessor in reach (the sequential work of the fill; an anchor
+		// that is a cut point is an isolated seed hit as far as what lies before it goes), and starts at the first cut point where
+		// the running count since the previous start has got there.  Lane = block of 32 anchors, 32 blocks per step; a piece spans at
+		// least seg_min_piece >= 1024 anchors, so a step holds at most one start.
+		int n_p = 1, work = 0, work_at_start = 0;
+		if (lane == 0) starts[0] = 0;
+		__syncwarp();
+		for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+			const int blk = b0 + lane;
+			unsigned cuts = 0, valid = 0;
+			if (blk < n_blocks) {
+				cuts = cutw[blk];
+				const int left = n - (blk << 5);
+				valid = left >= 32 ? FULL : ((1u << left) - 1u);
+				if (blk == 0) valid &= ~1u;                                 // anchor 0 has nothing before it
+			}
+			const unsigned linked = valid & ~cuts;
+			int incl = __popc(linked);
+			const int mine = incl;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int v = __shfl_up_sync(FULL, incl, d);
+				if (lane >= d) incl += v;
+			}
+			const int w_before = work + incl - mine;                        // linked anchors before this block
+			// first cut point of this block with at least `need` linked anchors of the block in front of it
+			const int need = work_at_start + args.seg_min_piece - w_before;
+			unsigned cand = cuts;
+			if (need > 0) {
+				if (need > mine) cand = 0;
+				else {
+					const unsigned p = __fns(linked, 0, need);                 // position of the need-th linked anchor
+					cand = cuts & ~((2u << p) - 1u);                         // cut points after it
+				}
+			}
+			const unsigned has = __ballot_sync(FULL, cand != 0);
+			if (has && n_p < SEG_MAX_PIECES) {
+				const int bl = lowest_lane(has);
+				const int cl = lowest_lane(__shfl_sync(FULL, cand, bl));
+				const unsigned lk = __shfl_sync(FULL, linked, bl);
+				const int wb = __shfl_sync(FULL, w_before, bl);
+				if (lane == 0) starts[n_p] = ((b0 + bl) << 5) + cl;
+				++n_p, work_at_start = wb + __popc(lk & lanemask_lt(cl));
+			}
+			work += __shfl_sync(FULL, incl, 31);
+		}
+		if (work - work_at_start < args.seg_min_piece && n_p > 1) --n_p;     // a tail with little work stays with the piece before it
+		if (n_p < 2) continue;
+		const bool lo_safe = args.par.max_dist_x >= 0 && (uint64_t)max_xl + (uint64_t)args.par.max_dist_x < (1ull << 32);
+		const bool general = seg_diff != 0 || args.par.is_cdna || args.par.gap_scale != 1.0f || args.par.bw >= (1 << 24) || args.par.bw < 0
+		                  || args.par.n_segs > 1 || args.par.max_dist_x <= 0 || args.par.max_dist_y <= 0;
+		int idx = 0, item0 = 0;
+		if (lane == 0) {
+			idx = atomicAdd(&args.seg_ctl[0], 1);
+			if (idx < args.seg_cap) item0 = atomicAdd(&args.seg_ctl[1], n_p);
+		}
+		idx = __shfl_sync(FULL, idx, 0), item0 = __shfl_sync(FULL, item0, 0);
+		if (idx >= args.seg_cap) continue;                                   // (more long reads than room: the rest stay whole)
+		__syncwarp();
+		SegRead *sr = args.seg_reads + idx;
+		if (lane == 0) {
+			sr->read = (int32_t)r, sr->n_pieces = n_p, sr->flags = (lo_safe ? 1 : 0) | (general ? 2 : 0);
+			sr->avg = __double2float_rn(__ddiv_rn(__dmul_rn(.01, (double)__ull2float_rn(sum)), (double)n64));     // chain.c:49
+			sr->start[n_p] = n;
+			args.seg_done[idx] = 0;
+			args.heavy_flag[r] = 2;
+		}
+		if (lane < n_p) sr->start[lane] = starts[lane], args.seg_items[item0 + lane] = idx << 8 | lane;
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
+chain_pieces_kernel(const BatchArgs args)
+{
+	__shared__ __align__(16) int32_t smem_ring[WARPS_PER_CTA][RING_ARRAYS * LIGHT_RING];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int32_t *ring = smem_ring[warp];
+	unsigned long long n_chunks = 0, n_general = 0, n_cells = 0, n_window = 0;
+	int n_items = 0;
+	if (lane == 0) n_items = args.seg_ctl[1];
+	n_items = __shfl_sync(FULL, n_items, 0);
+	for (;;) {
+		int it = 0;
+		if (lane == 0) it = atomicAdd(&args.seg_ctl[2], 1);
+		__syncwarp();
+		it = __shfl_sync(FULL, it, 0);
+		if (it >= n_items) break;
+		const int item = args.seg_items[it], idx = item >> 8, piece = item & 0xff;
+		const SegRead *sr = args.seg_reads + idx;
+		const int64_t r = sr->read, o = args.off[r];
+		ReadCtx rc;
+		rc.n = (int)(args.off[r + 1] - o);
+		rc.A = (const ulonglong2*)(args.a + o);
+		uint8_t *s = args.scratch + (size_t)o * SCRATCH_BYTES_PER_ANCHOR;
+		const size_t n = (size_t)rc.n;
+		rc.F = (int32_t*)s, rc.P = (int32_t*)(s + 4 * n), rc.X = (uint64_t*)(s + 8 * n);
+		rc.V = (int32_t*)(s + 16 * n), rc.T = (int32_t*)(s + 20 * n), rc.U = (uint64_t*)(s + 24 * n);
+		const int flags = __shfl_sync(FULL, sr->flags, 0);                   // (through a shuffle: warp-uniform by construction)
+		const int k0 = sr->start[piece], k1 = sr->start[piece + 1];
+		if (flags & 2) {
+			++n_general;
+			dp_fill<LIGHT_RING, true, false, false, true>(args.par, rc, sr->avg, (flags & 1) != 0, ring, nullptr, lane, n_chunks, n_cells, n_window, k0, k1);
+		} else dp_fill<LIGHT_RING, false, false, false, true>(args.par, rc, sr->avg, (flags & 1) != 0, ring, nullptr, lane, n_chunks, n_cells, n_window, k0, k1);
+		__threadfence();                                                    // this piece's f / p / v / t before the count below
+		int done = 0;
+		if (lane == 0) done = atomicAdd(&args.seg_done[idx], 1);
+		__syncwarp();
+		done = __shfl_sync(FULL, done, 0);
+		if (done != sr->n_pieces - 1) continue;
+		__threadfence();                                                    // the read's last piece: every other piece is in place
+		int n_u = 0, n_v = 0, status = MM2B_READ_OK;
+		unsigned long long uo = 0, bo = 0;
+		OutArgs out;
+		out.cursor = args.out_cursor, out.u = args.u, out.b = (ulonglong2*)args.b, out.bi = args.bi;
+		extract_chains(args.par, rc, out, ring, lane, n_u, n_v, status, uo, bo);
+		if (lane == 0) args.n_u[r] = n_u, args.n_v[r] = n_v, args.status[r] = status, args.u_off[r] = (int64_t)uo, args.b_off[r] = (int64_t)bo;
+		__syncwarp();
+	}
+	if (lane == 0 && n_general) atomicAdd(&args.counters[1], n_general);
+	if (blockIdx.x == 0 && threadIdx.x == 0) args.counters[5] = (unsigned long long)(args.seg_ctl[0] < args.seg_cap ? args.seg_ctl[0] : args.seg_cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1h: heavy reads, one CTA per read (see "Heavy reads" above).  Warp 0 is the read's warp; the others serve its long scans.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int HEAVY_SMEM_BYTES = (RING_ARRAYS * HEAVY_RING + COOP_WORDS) * 4;
@@ -1330,13 +1519,13 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 {
 	if (args.n_reads <= 0) return 0;
 	cudaMemsetAsync(args.work_counter, 0, sizeof(int), stream);
-	cudaMemsetAsync(args.counters, 0, 5 * sizeof(unsigned long long), stream);
+	cudaMemsetAsync(args.counters, 0, 6 * sizeof(unsigned long long), stream);
 	cudaMemsetAsync(args.out_cursor, 0, 2 * sizeof(unsigned long long), stream);
 	int64_t ctas = (args.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const int64_t resident = (int64_t)n_sms * CTAS_PER_SM;
 	if (ctas > resident) ctas = resident;
 	int launches = 1;
-	if (args.heavy_flag) {          // classify, then the heavy reads on CTAs of their own (same stream: a heavy read outlasts everything else anyway)
+	if (args.heavy_list) {          // classify, then the heavy reads on CTAs of their own (same stream: a heavy read outlasts everything else anyway)
 		static bool attr_set[64];
 		int dev = 0;
 		cudaGetDevice(&dev);
@@ -1348,6 +1537,12 @@ int launch_chain(const BatchArgs &args, int n_sms, cudaStream_t stream)
 		const int64_t warps_needed = args.n_reads, blocks = (warps_needed + 7) / 8;
 		classify_heavy_kernel<<<(int)(blocks > 4 * n_sms ? 4 * n_sms : blocks), 256, 0, stream>>>(args);
 		chain_heavy_kernel<<<n_sms, HEAVY_WARPS * 32, HEAVY_SMEM_BYTES, stream>>>(args);
+		launches += 2;
+	} else if (args.heavy_flag) cudaMemsetAsync(args.heavy_flag, 0, (size_t)args.n_reads, stream);
+	if (args.heavy_flag && args.seg_reads) {            // cut the long reads that can be cut, fill their pieces side by side
+		cudaMemsetAsync(args.seg_ctl, 0, 4 * sizeof(int), stream);
+		segment_kernel<<<(int)(args.n_reads > 8 * n_sms ? 8 * n_sms : args.n_reads), 256, 0, stream>>>(args);
+		chain_pieces_kernel<<<n_sms * 4, WARPS_PER_CTA * 32, 0, stream>>>(args);
 		launches += 2;
 	}
 	if (args.count_cells) chain_reads_kernel<true><<<(int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args);

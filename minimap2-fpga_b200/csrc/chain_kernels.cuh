@@ -30,7 +30,7 @@ struct BatchArgs {
 	int32_t *bi;                    // ... their indices inside the read (4 B each) are wanted instead
 	const int32_t *order;           // processing order (longest reads first) or nullptr
 	int *work_counter;              // persistent-warp work queue
-	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells, [3] window cells, [4] reads taken by the heavy-read kernel
+	unsigned long long *counters;   // [0] chunks issued, [1] reads on the general path, [2] reference-semantics cells, [3] window cells, [4] reads taken by the heavy-read kernel, [5] reads cut into pieces
 	int32_t *dbg_fpv;               // optional 3 x n_anchors int32 (f, p, v) copy for tests, or nullptr
 	int64_t n_anchors;
 	int count_cells;                // tally reference-semantics cells / issued chunks (statistics only; costs kernel time)
@@ -40,6 +40,21 @@ struct BatchArgs {
 	int *heavy_count, *heavy_counter;   // adjacent ints: length of heavy_list, its work-queue cursor
 	long long heavy_min_cells;      // a read is heavy when its estimated window cells reach this (and its mean window is long)
 	int heavy_cap;                  // at most this many reads per batch (one wave of CTAs): the kernel buys latency, not throughput
+	// long reads cut at their x-gap cut points (chain.c:192) into pieces that are filled by warps of their own; all null / 0 when off.
+	// A read that is cut gets heavy_flag = 2, so the warp-per-read kernel leaves it alone.
+	struct SegRead *seg_reads;      // the reads that are cut (at most seg_cap)
+	int32_t *seg_items;             // work items: index into seg_reads << 8 | piece
+	int *seg_ctl;                   // [0] reads cut, [1] work items, [2] work-queue cursor
+	int32_t *seg_done;              // per cut read: pieces filled so far
+	int seg_cap, seg_min_read, seg_min_piece;
+};
+
+constexpr int SEG_MAX_PIECES = 16;
+struct SegRead {
+	int32_t read, n_pieces;
+	float avg;                      // avg_qspan_scaled of the whole read (chain.c:49)
+	int32_t flags;                  // 1: low words suffice for the window search, 2: general scoring path
+	int32_t start[SEG_MAX_PIECES + 1];
 };
 
 // launchers (all asynchronous on `stream`); each returns the number of kernels it launched

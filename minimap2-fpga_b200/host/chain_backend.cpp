@@ -237,7 +237,7 @@ struct Job {
 	std::condition_variable cv;
 	int workers_left = 0;       // guarded by mu; the caller leaves when it reaches 0
 	// stats
-	std::atomic<int64_t> n_chains{0}, n_chained{0}, cells_issued{0}, cells_ref{0}, window_cells{0}, n_general{0}, n_heavy{0};
+	std::atomic<int64_t> n_chains{0}, n_chained{0}, cells_issued{0}, cells_ref{0}, window_cells{0}, n_general{0}, n_heavy{0}, n_cut{0};
 	std::atomic<int64_t> h2d_bytes{0}, d2h_bytes{0}, n_packed{0}, n_raw{0};
 	double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, pack_ms = 0, gather_ms = 0;   // guarded by mu
 };
@@ -505,7 +505,7 @@ bool stage_issue(Slot &s, Job *job, int si, bool packed)
 	  && cuda_ok(cudaMemcpyAsync(job->status + sb.r0, s.d_status, nr * 4, cudaMemcpyDeviceToHost, st), "D2H status")
 	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
 	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
-	  && cuda_ok(cudaMemcpyAsync(s.h_cnt, mm2b_ws_counters_dev(s.ws), 40, cudaMemcpyDeviceToHost, st), "D2H counters")
+	  && cuda_ok(cudaMemcpyAsync(s.h_cnt, mm2b_ws_counters_dev(s.ws), 48, cudaMemcpyDeviceToHost, st), "D2H counters")
 	  && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord")
 	  && cuda_ok(cudaLaunchHostFunc(st, slot_signal_counts, &s), "cudaLaunchHostFunc");
 	job->h2d_bytes += h2d, job->d2h_bytes += nr * 12 + (nr + 1) * 16 + 40;
@@ -580,7 +580,7 @@ void stage_finish(Slot &s, Job *job)
 		cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]), cudaEventElapsedTime(&ker, s.ev[1], s.ev[2]);
 		cudaEventElapsedTime(&d2h0, s.ev[2], s.ev[3]), cudaEventElapsedTime(&d2h1, s.ev[4], s.ev[5]);
 		job->cells_issued += (int64_t)s.h_cnt[0] * 32, job->n_general += (int64_t)s.h_cnt[1], job->cells_ref += (int64_t)s.h_cnt[2], job->window_cells += (int64_t)s.h_cnt[3];
-		job->n_heavy += (int64_t)s.h_cnt[4];
+		job->n_heavy += (int64_t)s.h_cnt[4], job->n_cut += (int64_t)s.h_cnt[5];
 		std::lock_guard<std::mutex> lk(job->mu);
 		job->h2d_ms += h2d, job->kernel_ms += ker, job->d2h_ms += d2h0 + d2h1;
 	}
@@ -1158,7 +1158,7 @@ int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t
 		memset(stats, 0, sizeof(*stats));
 		stats->n_reads = n_reads, stats->n_anchors = n_anchors, stats->n_chains = job.n_chains, stats->n_chained = job.n_chained;
 		stats->cells_issued = job.cells_issued, stats->cells_ref = job.cells_ref, stats->window_cells = job.window_cells, stats->n_general_reads = job.n_general;
-		stats->n_heavy_reads = job.n_heavy;
+		stats->n_heavy_reads = job.n_heavy, stats->n_cut_reads = job.n_cut;
 		stats->h2d_ms = job.h2d_ms, stats->kernel_ms = job.kernel_ms, stats->d2h_ms = job.d2h_ms;
 		stats->h2d_bytes = job.h2d_bytes, stats->d2h_bytes = job.d2h_bytes, stats->n_packed_subs = job.n_packed, stats->n_raw_subs = job.n_raw;
 		stats->pack_ms = job.pack_ms, stats->gather_ms = job.gather_ms;

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(L, n), "C ABI symbol missing from the library: " + n
     binding = pkg("binding")
     assert sorted(binding.EXPORTS) == names, "binding.EXPORTS out of sync with the header"
-    assert binding.load().mm2b_abi_version() == 3
+    assert binding.load().mm2b_abi_version() == 4
 
 
 def test_params_struct_layout_matches_oracle(pkg, oracle):
