@@ -78,6 +78,10 @@ int mm2b_init(int n_devices, const int *devices);
  * the first call that needs the backend waits for it.  Lets a host overlap CUDA start-up with its own (e.g. index loading). */
 int mm2b_init_async(int n_devices, const int *devices);
 void mm2b_shutdown(void);
+/* For a host that calls its clean-up right before the process ends (main.c:430): stops and joins the library's threads but leaves device and
+ * pinned memory to the operating system (un-pinning gigabytes of staging costs as much as mapping a mini-batch).  The library must not be
+ * used afterwards. */
+void mm2b_shutdown_at_exit(void);
 int mm2b_num_devices(void);                 /* devices bound by mm2b_init (0 before) */
 void mm2b_set_counting(int on);             /* the same statistics switch for mm2b_chain_batch / mm_chain_dp (all internal workspaces) */
 int mm2b_cuda_device_count(void);           /* devices visible to the CUDA runtime; <= 0 when there is no usable GPU */

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("MM2B_LIB") or os.path.join(HERE, "libmm2chain_b200.so
 ANCHOR = np.dtype([("x", "<u8"), ("y", "<u8")])
 READ_EMPTY, READ_NO_CHAIN, READ_OK = 0, 1, 2
 
-EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version", "mm2b_ws_set_longest_read",
+EXPORTS = ["mm2b_init", "mm2b_init_async", "mm2b_shutdown", "mm2b_shutdown_at_exit", "mm2b_num_devices", "mm2b_cuda_device_count", "mm2b_last_error", "mm2b_abi_version", "mm2b_ws_set_longest_read",
            "mm2b_host_alloc", "mm2b_host_free", "mm2b_host_reserve", "mm2b_host_pool_trim", "mm2b_reserve_for_mapping", "mm2b_chain_batch", "mm2b_ws_create", "mm2b_ws_destroy", "mm2b_ws_bytes",
            "mm2b_ws_set_counting", "mm2b_set_counting",
            "mm2b_chain_batch_device", "mm2b_chain_batch_device_idx", "mm2b_chain_batch_ex", "mm2b_unpack_anchors_device", "mm2b_pack_anchors", "mm2b_measure_host_copy", "mm2b_ws_stats", "mm2b_ws_chain_kernel_ms", "mm2b_launch_count", "mm2b_ws_copy_fpv", "mm2b_debug_flags", "mm2b_measure_int32_peak",

@@ -888,17 +888,22 @@ void batcher_release(Batcher *bt, Flight *f)
 }
 
 // undo whatever mm2b_init built so far (g.mu held): a failed start-up leaves no device without a worker and no thread behind
-void teardown_locked()
+// release = false: the process is about to exit (mm2b_shutdown_at_exit): stop and join every thread of the library so that none of them
+// is inside CUDA when the runtime goes down, but leave device and pinned memory to the operating system — un-pinning gigabytes of
+// staging takes 0.4-1.2 s on the hosts measured (profiles/r3d_cli_wall.txt), which is as long as mapping a mini-batch.
+void teardown_locked(bool release = true)
 {
-	mm2b_map_backend_shutdown();
+	if (release) mm2b_map_backend_shutdown();
 	for (Device *d : g.devs) {
 		{ std::lock_guard<std::mutex> l2(d->mu); d->stop = true; }
 		d->cv.notify_all();
 	}
 	for (Device *d : g.devs) {
 		if (d->worker.joinable()) d->worker.join();
-		for (auto &s : d->slots) s.destroy();
-		delete d;
+		if (release) {
+			for (auto &s : d->slots) s.destroy();
+			delete d;
+		}
 	}
 	g.devs.clear();
 	for (Batcher *bt : g_batchers) {
@@ -906,16 +911,20 @@ void teardown_locked()
 		bt->cv_disp.notify_all();
 		if (bt->th.joinable()) bt->th.join();
 		if (g.trace) fprintf(stderr, "[mm2b trace] batcher dev %d: %lld reads in %lld flights\n", bt->dev, (long long)bt->n_reqs.load(), (long long)bt->n_flights.load());
-		for (auto &f : bt->fl) {
-			f.slot.destroy();
-			cudaFreeHost(f.h_a), cudaFreeHost(f.h_bi), cudaFreeHost(f.h_u), cudaFreeHost(f.h_cnt);
+		if (release) {
+			for (auto &f : bt->fl) {
+				f.slot.destroy();
+				cudaFreeHost(f.h_a), cudaFreeHost(f.h_bi), cudaFreeHost(f.h_u), cudaFreeHost(f.h_cnt);
+			}
+			delete bt;
 		}
-		delete bt;
 	}
 	g_batchers.clear();
 	g.pool.shutdown();
-	for (auto &e : g.trace_ev0) if (e) { cudaEventDestroy(e); e = nullptr; }
-	mm2b_host_pool_trim();
+	if (release) {
+		for (auto &e : g.trace_ev0) if (e) { cudaEventDestroy(e); e = nullptr; }
+		mm2b_host_pool_trim();
+	}
 	g.up = false;
 }
 
@@ -1062,7 +1071,22 @@ void mm2b_shutdown(void)
 	}
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.up) return;
+	const double t0 = now_ms();
 	teardown_locked();
+	if (g.trace) fprintf(stderr, "[mm2b trace] shutdown: %.3f s\n", (now_ms() - t0) * 1e-3);
+}
+
+void mm2b_shutdown_at_exit(void)
+{
+	{
+		std::lock_guard<std::mutex> lk0(g_init_mu);
+		if (g_init_thread.joinable()) g_init_thread.join();
+	}
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.up) return;
+	const double t0 = now_ms();
+	teardown_locked(false);
+	if (g.trace) fprintf(stderr, "[mm2b trace] shutdown at exit: %.3f s\n", (now_ms() - t0) * 1e-3);
 }
 
 int mm2b_num_devices(void) { return g.up ? (int)g.devs.size() : 0; }

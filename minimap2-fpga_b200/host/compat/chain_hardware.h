@@ -2,7 +2,7 @@
  * the B200 backend instead of the OpenCL/FPGA one.  The three host files that include it keep compiling unchanged:
  *
  *   main.c:367   if (!hardware_init(BUFFER_N, XCLBIN_FILE)) return -1;     -> mm2b_init_async() (CUDA devices, streams, workers)
- *   main.c:430   cleanup();                                                -> mm2b_shutdown()
+ *   main.c:430   cleanup();                                                -> mm2b_shutdown_at_exit()
  *   options.c:95-99,118-122   K1_HW = ONT_K1_HW; ...                       -> the learned HW/SW split is gone: constants are 0
  *   chain.c      is NOT compiled; mm_chain_dp comes from libmm2chain_b200 (same signature, mmpriv.h:65)
  *
@@ -44,6 +44,6 @@ static inline bool hardware_init(long buf_size, char *binary_name)
 	if (buf_size > 0 && !(getenv("MM2B_RESERVE") && atoi(getenv("MM2B_RESERVE")) == 0)) mm2b_reserve_for_mapping((size_t)buf_size);
 	return true;
 }
-static inline void cleanup(void) { mm2b_shutdown(); }
+static inline void cleanup(void) { mm2b_shutdown_at_exit(); }      /* main.c:430: the process ends right after */
 
 #endif
