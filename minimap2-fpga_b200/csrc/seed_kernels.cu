@@ -22,6 +22,7 @@
 #include "seed_kernels.cuh"
 #include "sort_replay.cuh"
 #include <limits.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace mm2b {
@@ -297,6 +298,263 @@ __global__ void __launch_bounds__(SKETCH_TILE) sketch_kernel(const SeedArgs s)
 	if (e.first_m >= 0) push(e.first_m);
 	for (unsigned long long m = e.mask_b; m; m &= m - 1) push(j0 + __ffsll((long long)m) - 1);
 	if (e.last_e >= 0) push(e.last_e);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sketch, eight positions per thread (w >= 8).  The same decisions as sketch_kernel, with the per-position overhead shared: a
+// thread converts its 8 bases with one shared-memory word and a table, rolls the k-mer and its reverse complement from one
+// position to the next (two shifts each, sketch.c:108-109 as written), keeps its 8 hashes in registers, and gets the nine windows
+// around them from w + 16 combinations instead of 9 w comparisons: suffix minima over the w hashes in front of its first position
+// (read from shared memory, newest kept on ties) combined with prefix minima over its own.  A CTA of 256 threads covers 1,920
+// positions after a halo of 128.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int S8_P = 8;
+constexpr int S8_HALO_THREADS = 16;
+constexpr int S8_THREADS = SKETCH8_TILE / S8_P + S8_HALO_THREADS;      // 256
+constexpr int S8_SPAN = S8_THREADS * S8_P;                             // 2,048 positions in shared memory
+static_assert(S8_THREADS % 32 == 0, "the block scans take each warp's total from lane 31");
+constexpr int S8_HALO = S8_HALO_THREADS * S8_P;                        // 128 >= w + k
+
+template <class key_t> struct WinMin { key_t x; int j; bool ties; };
+
+template <bool K32>
+__global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
+{
+	typedef typename std::conditional<K32, uint32_t, uint64_t>::type key_t;
+	constexpr key_t NOKEY = (key_t)~(key_t)0;
+	__shared__ __align__(8) uint8_t raw[S8_SPAN];           // the bases as they come
+	__shared__ uint8_t nt4_tab[256];
+	__shared__ __align__(8) uint16_t pk16[S8_THREADS + 4];  // 2-bit bases, 8 per entry, earlier base in the lower bits (4 entries of padding in front)
+	__shared__ key_t K[S8_SPAN];                            // the hashes (all ones where invalid)
+	__shared__ uint8_t zs8[S8_THREADS];                     // strand bits of a thread's 8 positions
+	__shared__ int warp_val[(S8_THREADS + 31) / 32];
+	__shared__ int tile_s;
+	__shared__ long long excl_s;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int N_WARPS = (S8_THREADS + 31) / 32;
+	if (tid == 0) tile_s = atomicAdd(s.tile_ticket, 1);
+	if (tid < 256) nt4_tab[tid] = (uint8_t)nt4((unsigned)tid);
+	if (tid < 4) pk16[tid] = 0;
+	__syncthreads();
+	const int tile = tile_s;
+	const int r = s.tile_read[tile];
+	const int64_t so = s.seq_off[r];
+	const int L = (int)(s.seq_off[r + 1] - so);
+	const int t0 = (tile - s.tile_off[r]) * SKETCH8_TILE;
+	const int pb = t0 - S8_HALO;                            // position of shared-memory index 0
+	const int k = s.k, w = s.w;
+	const uint64_t mask = (1ull << 2 * k) - 1;
+
+	// 1. the span's bytes, coalesced
+	for (int i = tid; i < S8_SPAN; i += S8_THREADS) {
+		const int pos = pb + i;
+		raw[i] = pos >= 0 && pos < L ? s.seq[so + pos] : (uint8_t)'N';
+	}
+	__syncthreads();
+	// 2. this thread's 8 bases: codes, packed bases, ambiguity bits
+	const int i0 = tid * S8_P, p0 = pb + i0;                // shared index / position of this thread's first base
+	const uint64_t eight = *(const uint64_t*)&raw[i0];
+	unsigned two16 = 0, bad8 = 0;
+#pragma unroll
+	for (int j = 0; j < S8_P; ++j) {
+		const unsigned c = nt4_tab[(eight >> 8 * j) & 0xff];
+		two16 |= (c & 3) << 2 * j;
+		bad8 |= (c >> 2) << j;
+	}
+	pk16[4 + tid] = (uint16_t)two16;
+	// valid bases in front of this thread's first one: distance to the last ambiguous base before it (block-wide max scan), capped
+	int last_bad = bad8 ? i0 + (31 - __clz(bad8)) : -1;     // shared index of this thread's last ambiguous base
+	{
+		int v = last_bad;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int o = __shfl_up_sync(FULL, v, d);
+			if (lane >= d && o > v) v = o;
+		}
+		if (lane == 31) warp_val[warp] = v;
+		__syncthreads();                                    // (also: pk16 is complete)
+		int before = -1;
+		for (int q = 0; q < warp; ++q) before = warp_val[q] > before ? warp_val[q] : before;
+		int excl = __shfl_up_sync(FULL, v, 1);
+		if (lane == 0) excl = -1;
+		last_bad = excl > before ? excl : before;           // last ambiguous base strictly before i0 (-1: none in the span)
+	}
+	int run = last_bad < 0 ? 128 : i0 - 1 - last_bad;       // 128: the run reaches past what is loaded (every threshold is <= w + k <= 92)
+	run = run > 128 ? 128 : run;
+	// 3. the 8 hashes, rolling the two k-mers from the k - 1 bases in front
+	uint64_t fw, rv;
+	{
+		const uint64_t *pk64 = (const uint64_t*)pk16;       // entries tid .. tid + 3 of the padded array = the 32 bases in front of i0
+		const int sh = (tid & 3) * 16;
+		uint64_t prev = pk64[tid >> 2] >> sh;
+		if (sh) prev |= pk64[(tid >> 2) + 1] << (64 - sh);
+		const uint64_t f = k > 1 ? prev >> (64 - 2 * (k - 1)) : 0;     // the k - 1 bases before i0, oldest lowest
+		rv = (f ^ (mask >> 2)) << 2;                        // sketch.c:109 after those bases: complemented, one slot left for the next
+		uint64_t x = __brevll(f);
+		x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+		fw = k > 1 ? x >> (64 - 2 * (k - 1)) : 0;           // sketch.c:108 after those bases: oldest on top
+	}
+	key_t xk[S8_P];
+	int runs[S8_P];
+	unsigned z8 = 0;
+#pragma unroll
+	for (int j = 0; j < S8_P; ++j) {
+		const unsigned c = (two16 >> 2 * j) & 3;
+		fw = (fw << 2 | c) & mask;                          // sketch.c:108
+		rv = rv >> 2 | (uint64_t)(3 ^ c) << 2 * (k - 1);    // sketch.c:109
+		run = (bad8 >> j & 1) ? 0 : (run < 128 ? run + 1 : 128);
+		runs[j] = run;
+		key_t x = NOKEY;
+		if (run >= k) {
+			const unsigned z = fw < rv ? 0 : 1;                // sketch.c:111
+			const uint64_t km = z ? rv : fw;
+			x = K32 ? (key_t)hash32((uint32_t)km, (uint32_t)mask) : (key_t)(hash64(km, mask) << 8 | (uint64_t)k);
+			z8 |= z << j;
+		}
+		xk[j] = x;
+		K[i0 + j] = x;
+	}
+	zs8[tid] = (uint8_t)z8;
+	__syncthreads();
+
+	// 4. windows.  Position j of this thread (j = 0..8, 8 = the next thread's first) looks at o_j .. o_{w-1}, v_0 .. v_{j-1}: the w hashes in
+	//    front of i0 (shared memory) and the thread's own.  Newest minimum and "is that hash there twice" for each.
+	WinMin<key_t> win[S8_P + 1];
+	if (tid >= S8_HALO_THREADS) {
+		WinMin<key_t> suf;                                  // newest minimum of o_i .. o_{w-1}, built from the newest end
+		suf.x = NOKEY, suf.j = i0 - 1, suf.ties = false;    // (nothing yet; an invalid newest entry is its own minimum)
+		auto older = [&](int i) {                           // an older entry joins: it takes over only if strictly smaller
+			const key_t xo = K[i0 - w + i];
+			if (xo < suf.x) suf.x = xo, suf.j = i0 - w + i, suf.ties = false;
+			else if (xo == suf.x) suf.ties = true;
+		};
+		for (int i = w - 1; i > S8_P; --i) older(i);
+#pragma unroll
+		for (int i = S8_P; i >= 0; --i) {
+			if (i < w) older(i);
+			win[i] = suf;
+		}
+		WinMin<key_t> pre;                                  // newest minimum of v_0 .. v_{j-1}
+		pre.x = xk[0], pre.j = i0, pre.ties = false;
+#pragma unroll
+		for (int j = 1; j <= S8_P; ++j) {
+			WinMin<key_t> m = pre;                            // window j = suffix j (older) ++ prefix j (newer)
+			if (j < w) {
+				const WinMin<key_t> o = win[j];
+				if (o.x < pre.x) m = o;
+				else if (o.x == pre.x) m.ties = true;
+			}
+			win[j] = m;
+			if (j < S8_P) {
+				if (xk[j] <= pre.x) pre.ties = xk[j] == pre.x, pre.x = xk[j], pre.j = i0 + j;
+			}
+		}
+	}
+
+	// 5. what mm_sketch pushes at each of the 8 positions (see sketch_kernel): counted first, written after the offsets are known
+	unsigned f_first = 0, f_last = 0, f_ties = 0;           // per position: A/B pushes the old minimum; E; the rare equal-hash lists must be walked
+	int cnt = 0;
+	if (tid >= S8_HALO_THREADS) {
+#pragma unroll
+		for (int j = 0; j < S8_P; ++j) {
+			const int i = i0 + j, t = p0 + j;
+			if (t >= L) break;
+			const int l = runs[j];
+			const key_t xm = win[j].x, xt = xk[j];
+			const int jm = win[j].j;
+			int after = jm;
+			if (l == w + k - 1 && xm != NOKEY && win[j].ties) {
+				f_ties |= 1u << j;
+				for (int q = i - w + 1; q < i; ++q) cnt += K[q] == xm && q != jm;
+			}
+			if (xt <= xm) {
+				if (l >= w + k && xm != NOKEY) f_first |= 1u << j, ++cnt;
+				after = i;
+			} else if (jm == i - w) {
+				if (l >= w + k - 1 && xm != NOKEY) f_first |= 1u << j, ++cnt;
+				const key_t xn = win[j + 1].x;
+				const int jn = win[j + 1].j;
+				if (l >= w + k - 1 && xn != NOKEY && win[j + 1].ties) {
+					f_ties |= 1u << (8 + j);
+					for (int q = i - w + 1; q <= i; ++q) cnt += K[q] == xn && q != jn;
+				}
+				after = jn;
+			}
+			if (t == L - 1 && K[after] != NOKEY) f_last |= 1u << j, ++cnt;
+		}
+	}
+	// block-wide exclusive scan of the counts
+	int incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int o = __shfl_up_sync(FULL, incl, d);
+		if (lane >= d) incl += o;
+	}
+	__syncthreads();                                        // (warp_val is reused)
+	if (lane == 31) warp_val[warp] = incl;
+	__syncthreads();
+	int before = 0, total = 0;
+	for (int q = 0; q < N_WARPS; ++q) {
+		const int v = warp_val[q];
+		if (q < warp) before += v;
+		total += v;
+	}
+	// decoupled look-back: how many minimizers the tiles before this one pushed.  Warp 0 looks at 32 predecessors at a time.
+	if (warp == 0) {
+		volatile unsigned long long *state = s.tile_state;
+		const unsigned long long F1 = 1ull << 62, F2 = 2ull << 62, VAL = F1 - 1;
+		long long excl = 0;
+		if (tile > 0) {
+			if (lane == 0) state[tile] = F1 | (unsigned long long)total;
+			__syncwarp();
+			for (int top = tile - 1; top >= 0; top -= 32) {
+				const int p = top - lane;
+				unsigned long long v = F2;
+				if (p >= 0) while (((v = state[p]) >> 62) == 0) { }
+				const unsigned done = __ballot_sync(FULL, v >> 62 == 2);
+				const int stop = done ? __ffs((int)done) - 1 : 32;
+				long long part = lane <= stop ? (long long)(v & VAL) : 0;
+#pragma unroll
+				for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+				excl += part;
+				if (done) break;
+			}
+		}
+		if (lane == 0) {
+			state[tile] = F2 | (unsigned long long)(excl + total);
+			s.tile_excl[tile] = excl;
+			if (tile == s.n_tiles - 1) s.tile_excl[s.n_tiles] = excl + total;
+			excl_s = excl;
+		}
+	}
+	__syncthreads();
+	if (cnt == 0) return;
+	const long long at = excl_s + before + (incl - cnt);
+	if (at + cnt > s.mv_cap) return;                        // (the host sees the total and comes back with a larger buffer)
+	ulonglong2 *dst = s.mv + at;
+	auto push = [&](int q) {                                // sketch.c:115 (rid 0): x = hash << 8 | span, y = position << 1 | strand
+		const uint64_t x = K32 ? (uint64_t)K[q] << 8 | (uint64_t)k : (uint64_t)K[q];
+		*dst++ = make_ulonglong2(x, (uint64_t)(uint32_t)(pb + q) << 1 | (zs8[q >> 3] >> (q & 7) & 1));
+	};
+#pragma unroll
+	for (int j = 0; j < S8_P; ++j) {
+		const int i = i0 + j, t = p0 + j;
+		if (t >= L) break;
+		const key_t xm = win[j].x;
+		const int jm = win[j].j, jn = win[j + 1].j;
+		if (f_ties >> j & 1)
+			for (int q = i - w + 1; q < i; ++q) if (K[q] == xm && q != jm) push(q);
+		if (f_first >> j & 1) push(jm);
+		if (f_ties >> (8 + j) & 1) {
+			const key_t xn = win[j + 1].x;
+			for (int q = i - w + 1; q <= i; ++q) if (K[q] == xn && q != jn) push(q);
+		}
+		if (f_last >> j & 1) {
+			const key_t xt = xk[j];
+			push(xt <= xm ? i : (jm == i - w ? jn : jm));
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -808,12 +1066,23 @@ int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, 
 	return 1;
 }
 
+int sketch_tile_positions(int w)
+{
+	static const bool off = getenv("MM2B_SKETCH8") && atoi(getenv("MM2B_SKETCH8")) == 0;
+	return w >= S8_P && !off ? SKETCH8_TILE : SKETCH_TILE;
+}
+
 int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 {
 	if (s.n_tiles <= 0) return 0;
 	cudaMemsetAsync(s.tile_state, 0, (size_t)s.n_tiles * 8, stream);
 	cudaMemsetAsync(s.tile_ticket, 0, sizeof(int), stream);
 	const bool k32 = 2 * s.k < 32;
+	if (sketch_tile_positions(s.w) == SKETCH8_TILE) {       // eight positions per thread
+		if (k32) sketch8_kernel<true><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
+		else sketch8_kernel<false><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
+		return 1;
+	}
 #define MM2B_SKETCH(W_) do { if (k32) sketch_kernel<true, W_><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s); else sketch_kernel<false, W_><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s); } while (0)
 	switch (s.w) {                          // the presets' window sizes get an unrolled scan (options.c:82-150: 5, 10, 11, 19)
 	case 5: MM2B_SKETCH(5); break;

@@ -6,7 +6,8 @@
 
 namespace mm2b {
 
-constexpr int SKETCH_TILE = 512;        // positions per CTA of the sketch kernels
+constexpr int SKETCH_TILE = 512;        // positions per CTA of the one-position-per-thread sketch kernel (w < 8)
+constexpr int SKETCH8_TILE = 1920;      // ... of the eight-positions-per-thread kernel (240 threads + 16 for the halo = 8 full warps)
 constexpr int SKETCH_MAX_W = 64;        // window sizes the emission masks cover
 constexpr int SKETCH_MAX_K = 28;        // mm_sketch's own limit (sketch.c:84)
 
@@ -52,6 +53,7 @@ struct SeedArgs {
 
 int launch_index_build(const DeviceIndex &ix, const uint64_t *d_keys, const uint64_t *d_vals, cudaStream_t stream);
 int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, const uint64_t *raw_minimizers, int32_t *occ, uint64_t *hv, cudaStream_t stream);
+int sketch_tile_positions(int w);        // positions per tile of the kernel launch_sketch will use for this window size
 int launch_sketch(const SeedArgs &s, cudaStream_t stream);
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream);      // out[0..n]: exclusive prefix, out[n] = total
 int launch_read_offsets(const SeedArgs &s, cudaStream_t stream);                            // mv_off[r] = tile_excl[tile_off[r]]

@@ -188,7 +188,8 @@ bool run_sub(Call &call, Ctx &c, int si)
 	CK(cudaSetDevice(c.device), "cudaSetDevice");
 
 	// ---- offsets and tiles (host), sequences to the device
-	const int64_t max_tiles = S / SKETCH_TILE + R + 1;
+	const int64_t tile_pos = sketch_tile_positions(ix->w);
+	const int64_t max_tiles = S / tile_pos + R + 1;
 	if (max_tiles >= (1ll << 31) || S >= (1ll << 40)) { set_error("%s%s", "mm2b_map_batch: sub-batch too large", ""); return false; }
 	if (!c.h_small.ensure((size_t)(R + 1) * 12 + 64) || !c.h_tiles.ensure((size_t)max_tiles * 4)) return false;
 	int64_t *h_seq_off = (int64_t*)c.h_small.p;
@@ -198,7 +199,7 @@ bool run_sub(Call &call, Ctx &c, int si)
 		h_seq_off[r] = call.seq_off[sb.r0 + r] - s0;
 		h_tile_off[r] = (int32_t)n_tiles64;
 		if (r < R) {
-			const int64_t nt = (call.seq_off[sb.r0 + r + 1] - call.seq_off[sb.r0 + r] + SKETCH_TILE - 1) / SKETCH_TILE;
+			const int64_t nt = (call.seq_off[sb.r0 + r + 1] - call.seq_off[sb.r0 + r] + tile_pos - 1) / tile_pos;
 			for (int64_t q = 0; q < nt; ++q) h_tile_read[n_tiles64 + q] = (int32_t)r;
 			n_tiles64 += nt;
 		}
