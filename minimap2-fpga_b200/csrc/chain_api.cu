@@ -19,6 +19,7 @@ static std::mutex g_pin_mu;
 static std::vector<std::pair<size_t, void*>> g_pin_free;        // pooled pinned blocks: (bytes, pointer)
 static std::unordered_map<void*, size_t> g_pin_size;            // every live block handed out by mm2b_host_alloc
 static size_t g_pin_pooled = 0, g_pin_pool_max = (size_t)16 << 30;
+static std::atomic<int64_t> g_pin_misses{0};                    // requests the pool could not serve (each one a cudaHostAlloc)
 
 void set_error(const char *fmt, const char *a, const char *b)
 {
@@ -31,6 +32,7 @@ bool cuda_ok(cudaError_t e, const char *what)
 	return false;
 }
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long pin_pool_misses() { return (long)g_pin_misses.load(std::memory_order_relaxed); }
 
 }  // namespace mm2b
 
@@ -94,6 +96,7 @@ void *mm2b_host_alloc(size_t bytes)
 		}
 	}
 	void *p = 0;
+	g_pin_misses.fetch_add(1, std::memory_order_relaxed);
 	if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocPortable), "cudaHostAlloc")) return 0;
 	std::lock_guard<std::mutex> lk(g_pin_mu);
 	g_pin_size[p] = bytes;

@@ -315,17 +315,19 @@ constexpr int S8_SPAN = S8_THREADS * S8_P;                             // 2,048 
 static_assert(S8_THREADS % 32 == 0, "the block scans take each warp's total from lane 31");
 constexpr int S8_HALO = S8_HALO_THREADS * S8_P;                        // 128 >= w + k
 
+#define KI(i_) ((i_) + ((i_) >> 3))                            // index into the padded hash array: a warp's stride-8 accesses hit 32 banks
+
 template <class key_t> struct WinMin { key_t x; int j; bool ties; };
 
-template <bool K32>
-__global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
+template <bool K32, int CTAS>
+__global__ void __launch_bounds__(S8_THREADS, CTAS) sketch8_kernel(const SeedArgs s)
 {
 	typedef typename std::conditional<K32, uint32_t, uint64_t>::type key_t;
 	constexpr key_t NOKEY = (key_t)~(key_t)0;
-	__shared__ __align__(8) uint8_t raw[S8_SPAN];           // the bases as they come
+	__shared__ __align__(16) uint8_t raw[S8_SPAN + 16];     // the bases as they come, from the 16-byte boundary at or below the span's first
 	__shared__ uint8_t nt4_tab[256];
 	__shared__ __align__(8) uint16_t pk16[S8_THREADS + 4];  // 2-bit bases, 8 per entry, earlier base in the lower bits (4 entries of padding in front)
-	__shared__ key_t K[S8_SPAN];                            // the hashes (all ones where invalid)
+	__shared__ key_t K[S8_SPAN + S8_SPAN / 8];              // the hashes (all ones where invalid); one slot of padding per 8: KI()
 	__shared__ uint8_t zs8[S8_THREADS];                     // strand bits of a thread's 8 positions
 	__shared__ int warp_val[(S8_THREADS + 31) / 32];
 	__shared__ int tile_s;
@@ -346,15 +348,28 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 	const int k = s.k, w = s.w;
 	const uint64_t mask = (1ull << 2 * k) - 1;
 
-	// 1. the span's bytes, coalesced
-	for (int i = tid; i < S8_SPAN; i += S8_THREADS) {
-		const int pos = pb + i;
-		raw[i] = pos >= 0 && pos < L ? s.seq[so + pos] : (uint8_t)'N';
+	// 1. the span's bytes, 16 at a time from aligned addresses (bytes of the neighbouring reads come along and are masked below)
+	const int64_t g0 = so + pb, g0a = g0 & ~15ll;           // offset of the span in the sub-batch's sequences; may be negative
+	if (tid <= S8_SPAN / 16) {
+		const int64_t c = g0a + 16 * tid;
+		uint4 v = make_uint4(0x4e4e4e4eu, 0x4e4e4e4eu, 0x4e4e4e4eu, 0x4e4e4e4eu);
+		if (c >= 0 && c < s.seq_len) v = __ldg((const uint4*)(s.seq + c));     // (the buffer is padded to 16 bytes past seq_len)
+		*(uint4*)&raw[16 * tid] = v;
 	}
 	__syncthreads();
 	// 2. this thread's 8 bases: codes, packed bases, ambiguity bits
 	const int i0 = tid * S8_P, p0 = pb + i0;                // shared index / position of this thread's first base
-	const uint64_t eight = *(const uint64_t*)&raw[i0];
+	uint64_t eight;
+	{
+		const int o = (int)(g0 - g0a) + i0, sh = (o & 7) * 8;
+		const uint64_t lo = *(const uint64_t*)&raw[o & ~7], hi = *(const uint64_t*)&raw[(o & ~7) + 8];
+		eight = sh ? lo >> sh | hi << (64 - sh) : lo;
+		if (p0 < 0 || p0 + S8_P > L) {                      // outside the read: 'N'
+#pragma unroll
+			for (int j = 0; j < S8_P; ++j)
+				if (p0 + j < 0 || p0 + j >= L) eight = (eight & ~(0xffull << 8 * j)) | 0x4eull << 8 * j;
+		}
+	}
 	unsigned two16 = 0, bad8 = 0;
 #pragma unroll
 	for (int j = 0; j < S8_P; ++j) {
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 			z8 |= z << j;
 		}
 		xk[j] = x;
-		K[i0 + j] = x;
+		K[KI(i0 + j)] = x;
 	}
 	zs8[tid] = (uint8_t)z8;
 	__syncthreads();
@@ -425,7 +440,7 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 		WinMin<key_t> suf;                                  // newest minimum of o_i .. o_{w-1}, built from the newest end
 		suf.x = NOKEY, suf.j = i0 - 1, suf.ties = false;    // (nothing yet; an invalid newest entry is its own minimum)
 		auto older = [&](int i) {                           // an older entry joins: it takes over only if strictly smaller
-			const key_t xo = K[i0 - w + i];
+			const key_t xo = K[KI(i0 - w + i)];
 			if (xo < suf.x) suf.x = xo, suf.j = i0 - w + i, suf.ties = false;
 			else if (xo == suf.x) suf.ties = true;
 		};
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 			int after = jm;
 			if (l == w + k - 1 && xm != NOKEY && win[j].ties) {
 				f_ties |= 1u << j;
-				for (int q = i - w + 1; q < i; ++q) cnt += K[q] == xm && q != jm;
+				for (int q = i - w + 1; q < i; ++q) cnt += K[KI(q)] == xm && q != jm;
 			}
 			if (xt <= xm) {
 				if (l >= w + k && xm != NOKEY) f_first |= 1u << j, ++cnt;
@@ -477,11 +492,11 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 				const int jn = win[j + 1].j;
 				if (l >= w + k - 1 && xn != NOKEY && win[j + 1].ties) {
 					f_ties |= 1u << (8 + j);
-					for (int q = i - w + 1; q <= i; ++q) cnt += K[q] == xn && q != jn;
+					for (int q = i - w + 1; q <= i; ++q) cnt += K[KI(q)] == xn && q != jn;
 				}
 				after = jn;
 			}
-			if (t == L - 1 && K[after] != NOKEY) f_last |= 1u << j, ++cnt;
+			if (t == L - 1 && K[KI(after)] != NOKEY) f_last |= 1u << j, ++cnt;
 		}
 	}
 	// block-wide exclusive scan of the counts
@@ -534,7 +549,7 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 	if (at + cnt > s.mv_cap) return;                        // (the host sees the total and comes back with a larger buffer)
 	ulonglong2 *dst = s.mv + at;
 	auto push = [&](int q) {                                // sketch.c:115 (rid 0): x = hash << 8 | span, y = position << 1 | strand
-		const uint64_t x = K32 ? (uint64_t)K[q] << 8 | (uint64_t)k : (uint64_t)K[q];
+		const uint64_t x = K32 ? (uint64_t)K[KI(q)] << 8 | (uint64_t)k : (uint64_t)K[KI(q)];
 		*dst++ = make_ulonglong2(x, (uint64_t)(uint32_t)(pb + q) << 1 | (zs8[q >> 3] >> (q & 7) & 1));
 	};
 #pragma unroll
@@ -544,11 +559,11 @@ __global__ void __launch_bounds__(S8_THREADS) sketch8_kernel(const SeedArgs s)
 		const key_t xm = win[j].x;
 		const int jm = win[j].j, jn = win[j + 1].j;
 		if (f_ties >> j & 1)
-			for (int q = i - w + 1; q < i; ++q) if (K[q] == xm && q != jm) push(q);
+			for (int q = i - w + 1; q < i; ++q) if (K[KI(q)] == xm && q != jm) push(q);
 		if (f_first >> j & 1) push(jm);
 		if (f_ties >> (8 + j) & 1) {
 			const key_t xn = win[j + 1].x;
-			for (int q = i - w + 1; q <= i; ++q) if (K[q] == xn && q != jn) push(q);
+			for (int q = i - w + 1; q <= i; ++q) if (K[KI(q)] == xn && q != jn) push(q);
 		}
 		if (f_last >> j & 1) {
 			const key_t xt = xk[j];
@@ -587,6 +602,25 @@ __global__ void __launch_bounds__(1024) scan_kernel(const T *in, int64_t *out, i
 		__syncthreads();
 	}
 	if (tid == 0) out[n] = carry_s;
+}
+
+// Zeroing by a kernel rather than cudaMemsetAsync: small memsets can be routed to a copy engine, where they wait behind other
+// sub-batches' output copies.
+__global__ void zero_words_kernel(unsigned long long *p, int64_t n, unsigned long long *q, int64_t nq)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = 0;
+	if (i < nq) q[i] = 0;
+}
+
+// A few device scalars stored straight into mapped host memory.  The host needs them to size the next stage; as 8-byte D2H copies
+// they queued behind other sub-batches' output copies on the copy engine and every pipeline context stalled there for milliseconds.
+__global__ void export_scalars_kernel(volatile int64_t *host, const int64_t *a, const int64_t *b, const int *c)
+{
+	if (a) host[0] = *a;
+	if (b) host[1] = *b;
+	if (c) host[2] = *c;
+	__threadfence_system();
 }
 
 __global__ void read_offsets_kernel(const SeedArgs s)
@@ -649,16 +683,16 @@ __global__ void __launch_bounds__(256) matches_kernel(const SeedArgs s)
 		const ulonglong2 *mv = s.mv + m0;
 		int rep_len = 0, prev_en = 0, n_mp = 0;
 		long long n_a = 0;
+		ulonglong2 q_next = make_ulonglong2(0, 0);          // the next 32 minimizers are on their way while these are worked on
+		int t_next = 0;
+		if (lane < n) q_next = __ldg(mv + lane), t_next = __ldg(s.occ + m0 + lane);
 		for (int base = 0; base < n; base += 32) {
 			const int i = base + lane;
 			const bool in = i < n;
-			uint64_t x = 0, y = 0;
-			int t = 0;
-			if (in) {
-				const ulonglong2 q = __ldg(mv + i);
-				x = q.x, y = q.y;
-				t = s.occ[m0 + i];
-			}
+			const uint64_t x = q_next.x, y = q_next.y;
+			const int t = t_next;
+			if (i + 32 < n) q_next = __ldg(mv + i + 32), t_next = __ldg(s.occ + m0 + i + 32);
+			else q_next = make_ulonglong2(0, 0), t_next = 0;
 			__syncwarp();
 			const int q_span = (int)(x & 0xff), q_pos = (int)(uint32_t)y;
 			const bool high = in && t >= s.max_occ, match = in && t < s.max_occ;
@@ -740,11 +774,37 @@ __device__ void expand_read(const SeedArgs &s, const DeviceIndex &ix, int64_t r,
 	}
 }
 
-__global__ void __launch_bounds__(256) expand_kernel(const SeedArgs s, const DeviceIndex ix)
+// The whole sub-batch at once, one thread per minimizer: where a minimizer's anchors go is already known (arel, a_off), so nothing
+// orders the threads; the read a minimizer belongs to is found by bisection over mv_off (a table that stays in L1/L2).
+__global__ void __launch_bounds__(256) expand_kernel(const SeedArgs s, const DeviceIndex ix, int64_t n_mv)
 {
-	const int lane = threadIdx.x & 31;
-	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-	for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < s.n_reads; r += n_warps) expand_read(s, ix, r, lane, s.a_tmp);
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_mv) return;
+	const int rel = s.arel[i];
+	if (rel < 0) return;
+	int lo = 0, hi = (int)s.n_reads;                        // mv_off[lo] <= i < mv_off[hi]
+	while (hi - lo > 1) {
+		const int mid = (lo + hi) >> 1;
+		if (__ldg(s.mv_off + mid) <= i) lo = mid; else hi = mid;
+	}
+	const int64_t r = lo, m0 = __ldg(s.mv_off + r), m1 = __ldg(s.mv_off + r + 1);
+	const int qlen = (int)(s.seq_off[r + 1] - s.seq_off[r]);
+	ulonglong2 *a = s.a_tmp + s.a_off[r] + rel;
+	const ulonglong2 q = __ldg(s.mv + i);
+	const uint64_t x = q.x, y = q.y, v = s.hv[i];
+	const int t = s.occ[i];
+	const bool tandem = (i > m0 && __ldg(&s.mv[i - 1].x) >> 8 == x >> 8) || (i < m1 - 1 && __ldg(&s.mv[i + 1].x) >> 8 == x >> 8);     // map.c:113-115
+	const uint32_t q_pos = (uint32_t)y;
+	const uint64_t q_span = x & 0xff;
+	const uint64_t ay_f = q_span << 32 | (q_pos >> 1) | (y >> 32) << 48 | (tandem ? SEED_TANDEM : 0);                                // map.c:232-234, :239
+	const uint64_t ay_r = q_span << 32 | (uint32_t)(qlen - (int)((q_pos >> 1) + 1 - (uint32_t)q_span) - 1) | (y >> 32) << 48 | (tandem ? SEED_TANDEM : 0);     // map.c:235-238
+	const uint64_t *pos = ix.pos + (v >> 32);
+	for (int h = 0; h < t; ++h) {
+		const uint64_t rr = t == 1 ? v : __ldg(pos + h);   // index.c:90-96
+		const uint32_t rpos = (uint32_t)rr >> 1;
+		const bool fwd = (rr & 1) == (q_pos & 1);
+		a[h] = make_ulonglong2((fwd ? 0 : 1ull << 63) | (rr & 0xffffffff00000000ull) | rpos, fwd ? ay_f : ay_r);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1075,12 +1135,14 @@ int sketch_tile_positions(int w)
 int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 {
 	if (s.n_tiles <= 0) return 0;
-	cudaMemsetAsync(s.tile_state, 0, (size_t)s.n_tiles * 8, stream);
-	cudaMemsetAsync(s.tile_ticket, 0, sizeof(int), stream);
+	zero_words_kernel<<<(unsigned)((s.n_tiles + 255) / 256), 256, 0, stream>>>(s.tile_state, s.n_tiles, (unsigned long long*)s.tile_ticket, 1);    // (the ticket owns 8 bytes)
 	const bool k32 = 2 * s.k < 32;
 	if (sketch_tile_positions(s.w) == SKETCH8_TILE) {       // eight positions per thread
-		if (k32) sketch8_kernel<true><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
-		else sketch8_kernel<false><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
+		static const bool occ3 = getenv("MM2B_SKETCH8_CTAS") && atoi(getenv("MM2B_SKETCH8_CTAS")) == 3;     // register budget for 3 or 4 CTAs per SM
+		if (k32 && occ3) sketch8_kernel<true, 3><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
+		else if (k32) sketch8_kernel<true, 4><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
+		else if (occ3) sketch8_kernel<false, 3><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
+		else sketch8_kernel<false, 4><<<s.n_tiles, S8_THREADS, 0, stream>>>(s);
 		return 1;
 	}
 #define MM2B_SKETCH(W_) do { if (k32) sketch_kernel<true, W_><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s); else sketch_kernel<false, W_><<<s.n_tiles, SKETCH_TILE, 0, stream>>>(s); } while (0)
@@ -1098,6 +1160,12 @@ int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream)
 {
 	scan_kernel<int64_t><<<1, 1024, 0, stream>>>(in, out, n);
+	return 1;
+}
+
+int launch_export_scalars(int64_t *host_mapped, const int64_t *a, const int64_t *b, const int *c, cudaStream_t stream)
+{
+	export_scalars_kernel<<<1, 1, 0, stream>>>(host_mapped, a, b, c);
 	return 1;
 }
 
@@ -1121,17 +1189,17 @@ int launch_matches(const SeedArgs &s, int n_sms, cudaStream_t stream)
 	return 1;
 }
 
-int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream)
+int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int64_t n_mv, cudaStream_t stream)
 {
-	if (s.n_reads <= 0) return 0;
-	expand_kernel<<<warp_grid(s.n_reads, n_sms, 8), 256, 0, stream>>>(s, ix);
+	if (s.n_reads <= 0 || n_mv <= 0) return 0;
+	expand_kernel<<<(unsigned)((n_mv + 255) / 256), 256, 0, stream>>>(s, ix, n_mv);
 	return 1;
 }
 
 int launch_sort(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream)
 {
 	if (s.n_reads <= 0) return 0;
-	cudaMemsetAsync(s.tie_count, 0, 4 * sizeof(int), stream);
+	zero_words_kernel<<<1, 32, 0, stream>>>((unsigned long long*)s.tie_count, 2, nullptr, 0);
 	sort_kernel<<<warp_grid(s.n_reads, n_sms, SORT_WARPS), SORT_WARPS * 32, 0, stream>>>(s);
 	constexpr int replay_bytes = REPLAY_SMEM * 16 + 768 * 4 + REPLAY_WORK * 12;
 	static bool attr_set[64];

@@ -25,7 +25,8 @@ struct DeviceIndex {
 // One sub-batch of reads in HBM, stage by stage.
 struct SeedArgs {
 	int64_t n_reads;
-	const uint8_t *seq;         // concatenated ASCII bases
+	const uint8_t *seq;         // concatenated ASCII bases (16-byte aligned, readable for 16 bytes past seq_len)
+	int64_t seq_len;
 	const int64_t *seq_off;     // [n_reads + 1]
 	const int32_t *tile_off;    // [n_reads + 1] first sketch tile of every read
 	const int32_t *tile_read;   // [n_tiles] the read every tile belongs to
@@ -56,9 +57,10 @@ int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, 
 int sketch_tile_positions(int w);        // positions per tile of the kernel launch_sketch will use for this window size
 int launch_sketch(const SeedArgs &s, cudaStream_t stream);
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream);      // out[0..n]: exclusive prefix, out[n] = total
+int launch_export_scalars(int64_t *host_mapped, const int64_t *a, const int64_t *b, const int *c, cudaStream_t stream);   // host_mapped[0..2] = *a, *b, *c (null: left alone)
 int launch_read_offsets(const SeedArgs &s, cudaStream_t stream);                            // mv_off[r] = tile_excl[tile_off[r]]
 int launch_matches(const SeedArgs &s, int n_sms, cudaStream_t stream);                      // collect_matches per read
-int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream);
+int launch_expand(const SeedArgs &s, const DeviceIndex &ix, int64_t n_mv, cudaStream_t stream);      // collect_seed_hits into a_tmp, one thread per minimizer
 int launch_sort(const SeedArgs &s, const DeviceIndex &ix, int n_sms, cudaStream_t stream);  // stable sort + exact replay of the reads with equal keys
 
 }  // namespace mm2b

@@ -123,8 +123,12 @@ struct Device;
 struct Slot {
 	int device = -1;
 	Device *owner = nullptr;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[6] = {};     // 0 start, 1 h2d done, 2 kernels done, 3 counts d2h done, 4 out d2h start, 5 out d2h done
+	// Kernels, input copies and output copies each have their own stream.  On one stream, a sub-batch's input copy is ordered after
+	// the slot's previous output copy, and the marker that releases it waits in the device-to-host copy queue behind the other
+	// slots' pending outputs; small count copies wait there too.  Measured on the seeding pipeline (profiles/r3g_trace_*.txt).
+	cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+	cudaEvent_t ev[6] = {};     // 0 start, 1 h2d done, 2 kernels done, 3 totals on the host, 4 out d2h start, 5 out d2h done
+	int64_t *h_tot = nullptr, *d_tot = nullptr;         // mapped: chains / chained anchors of the sub-batch, stored by a kernel
 	mm2b_workspace_t *ws = nullptr;
 	int64_t cap_anchors = 0, cap_reads = 0, cap_runs = 0;
 	int64_t *d_off = nullptr, *d_u_off = nullptr, *d_b_off = nullptr;
@@ -154,9 +158,16 @@ struct Slot {
 		device = dev, owner = own;
 		if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
 		if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		static const bool one = getenv("MM2B_ONE_STREAM") && atoi(getenv("MM2B_ONE_STREAM")) > 0;      // the old layout, for comparison
+		if (one) in_stream = out_stream = stream;
+		else if (!cuda_ok(cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+		         !cuda_ok(cudaStreamCreateWithFlags(&out_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!cuda_ok(cudaHostAlloc((void**)&h_tot, 64, cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc") ||
+		    !cuda_ok(cudaHostGetDevicePointer((void**)&d_tot, h_tot, 0), "cudaHostGetDevicePointer")) return false;
 		for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
 		return true;
 	}
+	void sync_all() { cudaStreamSynchronize(in_stream), cudaStreamSynchronize(stream), cudaStreamSynchronize(out_stream); }
 	void release()
 	{
 		if (device < 0) return;
@@ -177,7 +188,10 @@ struct Slot {
 		release();
 		if (device < 0) return;
 		for (auto &e : ev) if (e) cudaEventDestroy(e);
+		if (in_stream && in_stream != stream) cudaStreamDestroy(in_stream);
+		if (out_stream && out_stream != stream) cudaStreamDestroy(out_stream);
 		if (stream) cudaStreamDestroy(stream);
+		if (h_tot) cudaFreeHost(h_tot), h_tot = d_tot = nullptr;
 		device = -1;
 	}
 	bool ensure(int64_t n_anchors, int64_t n_reads)
@@ -186,7 +200,7 @@ struct Slot {
 		const int64_t na = std::max<int64_t>(n_anchors + n_anchors / 4, std::max<int64_t>(cap_anchors, 1024));
 		const int64_t nr = std::max<int64_t>(n_reads + n_reads / 4, std::max<int64_t>(cap_reads, 64));
 		const int64_t nruns = na / 4 + 64;
-		cudaStreamSynchronize(stream);
+		sync_all();
 		release();
 		ws = mm2b_ws_create(device, na, nr);
 		if (!ws) return false;
@@ -433,8 +447,8 @@ void start_pack(Slot &s, Job *job, int si)
 				if (pc.buf[k] && pack_chunk(src, i0, i1, pc.buf[k] - i0, s.h_xruns + (int64_t)c * cap, s.n_xr[c], s.h_yruns + (int64_t)c * cap, s.n_yr[c], cap, false)) {
 					cudaSetDevice(s.device);
 					if (!pc.ev[k][s.device]) cudaEventCreateWithFlags(&pc.ev[k][s.device], cudaEventDisableTiming);
-					if (cudaMemcpyAsync(s.d_lo + i0, pc.buf[k], (size_t)n * 8, cudaMemcpyHostToDevice, s.stream) != cudaSuccess ||
-					    cudaEventRecord(pc.ev[k][s.device], s.stream) != cudaSuccess) s.pack_overflow.store(2);
+					if (cudaMemcpyAsync(s.d_lo + i0, pc.buf[k], (size_t)n * 8, cudaMemcpyHostToDevice, s.in_stream) != cudaSuccess ||
+					    cudaEventRecord(pc.ev[k][s.device], s.in_stream) != cudaSuccess) s.pack_overflow.store(2);
 					else pc.busy_dev[k] = s.device;
 				} else s.pack_overflow.store(1);
 			}
@@ -471,24 +485,25 @@ bool stage_issue(Slot &s, Job *job, int si, bool packed)
 		if (r > 0 && s.h_off[r] - s.h_off[r - 1] > longest) longest = s.h_off[r] - s.h_off[r - 1];
 	}
 	mm2b_ws_set_longest_read(s.ws, longest);          // lets the device call skip the heavy-read kernel when no read can qualify
-	cudaStream_t st = s.stream;
+	cudaStream_t st = s.stream, sti = s.in_stream;
 	s.packed = packed;
-	bool ok = cuda_ok(cudaEventRecord(s.ev[0], st), "cudaEventRecord")
-	       && cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D off");
+	bool ok = cuda_ok(cudaEventRecord(s.ev[0], sti), "cudaEventRecord")
+	       && cuda_ok(cudaMemcpyAsync(s.d_off, s.h_off, (nr + 1) * 8, cudaMemcpyHostToDevice, sti), "H2D off");
 	int64_t h2d = (nr + 1) * 8;
 	if (ok && na > 0) {
 		if (packed) {
-			ok = (s.ring_copied || cuda_ok(cudaMemcpyAsync(s.d_lo, s.h_lo, (size_t)na * 8, cudaMemcpyHostToDevice, st), "H2D packed anchors"))
-			  && cuda_ok(cudaMemcpyAsync(s.d_xruns, s.h_xruns, (size_t)s.n_xruns * 8, cudaMemcpyHostToDevice, st), "H2D x runs")
-			  && cuda_ok(cudaMemcpyAsync(s.d_yruns, s.h_yruns, (size_t)s.n_yruns * 8, cudaMemcpyHostToDevice, st), "H2D y runs")
-			  && mm2b_unpack_anchors_device(s.device, na, s.d_lo, s.d_xruns, s.n_xruns, s.d_yruns, s.n_yruns, s.d_a, st) == MM2B_OK;
+			ok = (s.ring_copied || cuda_ok(cudaMemcpyAsync(s.d_lo, s.h_lo, (size_t)na * 8, cudaMemcpyHostToDevice, sti), "H2D packed anchors"))
+			  && cuda_ok(cudaMemcpyAsync(s.d_xruns, s.h_xruns, (size_t)s.n_xruns * 8, cudaMemcpyHostToDevice, sti), "H2D x runs")
+			  && cuda_ok(cudaMemcpyAsync(s.d_yruns, s.h_yruns, (size_t)s.n_yruns * 8, cudaMemcpyHostToDevice, sti), "H2D y runs");
 			h2d += na * 8 + ((int64_t)s.n_xruns + s.n_yruns) * 8;
 		} else {
-			ok = cuda_ok(cudaMemcpyAsync(s.d_a, job->a + a0, (size_t)na * 16, cudaMemcpyHostToDevice, st), "H2D anchors");
+			ok = cuda_ok(cudaMemcpyAsync(s.d_a, job->a + a0, (size_t)na * 16, cudaMemcpyHostToDevice, sti), "H2D anchors");
 			h2d += na * 16;
 		}
 	}
-	ok = ok && cuda_ok(cudaEventRecord(s.ev[1], st), "cudaEventRecord");
+	ok = ok && cuda_ok(cudaEventRecord(s.ev[1], sti), "cudaEventRecord")
+	        && (sti == st || cuda_ok(cudaStreamWaitEvent(st, s.ev[1], 0), "cudaStreamWaitEvent"));
+	if (ok && na > 0 && packed) ok = mm2b_unpack_anchors_device(s.device, na, s.d_lo, s.d_xruns, s.n_xruns, s.d_yruns, s.n_yruns, s.d_a, st) == MM2B_OK;
 	if (!ok) return false;
 	int rc;
 	if (job->device_gather) {
@@ -499,31 +514,32 @@ bool stage_issue(Slot &s, Job *job, int si, bool packed)
 	}
 	if (rc != MM2B_OK) return false;
 	s.sig.store(0);
-	ok = cuda_ok(cudaEventRecord(s.ev[2], st), "cudaEventRecord")
-	  && cuda_ok(cudaMemcpyAsync(job->n_u + sb.r0, s.d_n_u, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_u")
-	  && cuda_ok(cudaMemcpyAsync(job->n_v + sb.r0, s.d_n_v, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_v")
-	  && cuda_ok(cudaMemcpyAsync(job->status + sb.r0, s.d_status, nr * 4, cudaMemcpyDeviceToHost, st), "D2H status")
-	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
-	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
-	  && cuda_ok(cudaMemcpyAsync(s.h_cnt, mm2b_ws_counters_dev(s.ws), 48, cudaMemcpyDeviceToHost, st), "D2H counters")
-	  && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord")
+	// the two totals the host sizes the output copies by are stored into mapped host memory by a kernel; the per-read counts
+	// travel with the outputs
+	ok = cuda_ok(cudaEventRecord(s.ev[2], st), "cudaEventRecord");
+	mm2b::count_launches(mm2b::launch_export_scalars(s.d_tot, s.d_u_off + nr, s.d_b_off + nr, nullptr, st));
+	ok = ok && cuda_ok(cudaEventRecord(s.ev[3], st), "cudaEventRecord")
 	  && cuda_ok(cudaLaunchHostFunc(st, slot_signal_counts, &s), "cudaLaunchHostFunc");
 	job->h2d_bytes += h2d, job->d2h_bytes += nr * 12 + (nr + 1) * 16 + 40;
 	if (packed) job->n_packed += 1; else job->n_raw += 1;
 	return ok;
 }
 
-// counts are on the host: publish offsets, enqueue the D2H of exactly the packed u[] and b[] / bi[] bytes
+// the totals are on the host: enqueue the D2H of the per-read counts and of exactly the packed u[] and b[] / bi[] bytes
 bool stage_outputs(Slot &s, Job *job)
 {
 	const SubBatch sb = job->subs[s.sub];
 	const int64_t nr = sb.r1 - sb.r0, a0 = job->off[sb.r0];
-	const int64_t tot_u = s.h_u_off[nr], tot_b = s.h_b_off[nr];
-	// sub-batch outputs are packed from the sub-batch's own anchor offset: they always fit there since n_v <= n per read
-	for (int64_t r = 0; r < nr; ++r) job->u_off[sb.r0 + r] = a0 + s.h_u_off[r], job->b_off[sb.r0 + r] = a0 + s.h_b_off[r];
-	cudaStream_t st = s.stream;
+	const int64_t tot_u = ((volatile int64_t*)s.h_tot)[0], tot_b = ((volatile int64_t*)s.h_tot)[1];
+	cudaStream_t st = s.out_stream;
 	bool ok = cuda_ok(cudaEventRecord(s.ev[4], st), "cudaEventRecord")
-	       && (tot_u == 0 || cuda_ok(cudaMemcpyAsync(job->u + a0, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"));
+	  && cuda_ok(cudaMemcpyAsync(job->n_u + sb.r0, s.d_n_u, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_u")
+	  && cuda_ok(cudaMemcpyAsync(job->n_v + sb.r0, s.d_n_v, nr * 4, cudaMemcpyDeviceToHost, st), "D2H n_v")
+	  && cuda_ok(cudaMemcpyAsync(job->status + sb.r0, s.d_status, nr * 4, cudaMemcpyDeviceToHost, st), "D2H status")
+	  && cuda_ok(cudaMemcpyAsync(s.h_u_off, s.d_u_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off")
+	  && cuda_ok(cudaMemcpyAsync(s.h_b_off, s.d_b_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off")
+	  && cuda_ok(cudaMemcpyAsync(s.h_cnt, mm2b_ws_counters_dev(s.ws), 48, cudaMemcpyDeviceToHost, st), "D2H counters")
+	  && (tot_u == 0 || cuda_ok(cudaMemcpyAsync(job->u + a0, s.d_u, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u"));
 	int64_t d2h = tot_u * 8;
 	if (ok && tot_b > 0) {
 		if (job->device_gather) {
@@ -601,7 +617,7 @@ void device_worker(Device *d)
 	};
 	auto fail_slot = [&](Slot &s) {              // nothing of this sub-batch may still be in flight towards the caller's buffers
 		job_fail(s.job);
-		cudaStreamSynchronize(s.stream);
+		s.sync_all();
 		while (s.host_left.load() > 0) std::this_thread::yield();
 		release_slot(s);
 	};
@@ -641,7 +657,7 @@ void device_worker(Device *d)
 				} else if (s.stage == 2) {                                  // kernels + counts
 					if (s.sig.load(std::memory_order_acquire) < 1) continue;
 					progressed = true;
-					if (job->failed.load() || !cuda_ok(cudaEventQuery(s.ev[3]), "counts copy") || !stage_outputs(s, job)) { fail_slot(s); continue; }
+					if (job->failed.load() || !cuda_ok(cudaEventQuery(s.ev[3]), "totals") || !stage_outputs(s, job)) { fail_slot(s); continue; }
 					s.stage = 3;
 				} else if (s.stage == 3) {                                  // outputs
 					if (s.sig.load(std::memory_order_acquire) < 2) continue;
@@ -649,6 +665,10 @@ void device_worker(Device *d)
 					if (job->failed.load() || !cuda_ok(cudaEventQuery(s.ev[5]), "output copy")) { fail_slot(s); continue; }
 					stage_finish(s, job);
 					const SubBatch sb = job->subs[s.sub];
+					{       // sub-batch outputs are packed from the sub-batch's own anchor offset: they always fit there since n_v <= n per read
+						const int64_t a0 = job->off[sb.r0];
+						for (int64_t r = 0; r < sb.r1 - sb.r0; ++r) job->u_off[sb.r0 + r] = a0 + s.h_u_off[r], job->b_off[sb.r0 + r] = a0 + s.h_b_off[r];
+					}
 					if (job->b && !job->device_gather && s.h_b_off[sb.r1 - sb.r0] > 0) {
 						start_gather(s, job);
 						s.stage = 4;

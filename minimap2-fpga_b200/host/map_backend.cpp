@@ -9,7 +9,9 @@
 // No collective, no NCCL: nothing is exchanged between devices.
 #include <cuda_runtime_api.h>
 #include <algorithm>
+#include <array>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -66,8 +68,12 @@ struct PinBuf {                             // pinned host buffer that only grow
 
 // One pipeline context: a stream and everything a sub-batch needs on its device
 struct Ctx {
-	int device = -1, n_sms = 0;
-	cudaStream_t stream = nullptr;
+	int device = -1, n_sms = 0, id = 0;
+	// Kernels, input copies and output copies each have their own stream.  With everything on one stream the inputs of a sub-batch were
+	// ordered after the same context's previous output copy, and the marker that releases them sat in the device-to-host copy queue
+	// behind every other context's pending outputs: no input moved until all outputs had (profiles/r3g_trace_one_stream.txt).
+	cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+	cudaEvent_t ev_in = nullptr;
 	cudaEvent_t ev[6] = {};
 	DevBuf<uint8_t> seq;
 	DevBuf<int64_t> seq_off, tile_excl, mv_off, n_a, a_off, u_off, b_off;
@@ -79,14 +85,20 @@ struct Ctx {
 	DevBuf<int> small;
 	mm2b_workspace_t *ws = nullptr;
 	int64_t ws_anchors = 0, ws_reads = 0;
-	PinBuf h_small, h_read, h_tiles;    // offsets in / totals out; per-read results; tile -> read map
+	PinBuf h_small, h_read, h_tiles;    // offsets in; per-read results; tile -> read map
+	int64_t *h_scal = nullptr, *d_scal = nullptr;      // 4 scalars the kernels store straight into host memory (mapped), and the device's address of them
 	bool create(int dev)
 	{
 		device = dev;
 		if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
 		cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
 		if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!cuda_ok(cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!cuda_ok(cudaStreamCreateWithFlags(&out_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!cuda_ok(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming), "cudaEventCreate")) return false;
 		for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
+		if (!cuda_ok(cudaHostAlloc((void**)&h_scal, 64, cudaHostAllocMapped), "cudaHostAlloc") || !cuda_ok(cudaHostGetDevicePointer((void**)&d_scal, h_scal, 0), "cudaHostGetDevicePointer")) return false;
+		memset(h_scal, 0, 64);
 		return small.ensure(16, "cudaMalloc");
 	}
 	void destroy()
@@ -94,11 +106,15 @@ struct Ctx {
 		if (device < 0) return;
 		cudaSetDevice(device);
 		if (stream) cudaStreamSynchronize(stream);
+		if (in_stream) cudaStreamSynchronize(in_stream), cudaStreamDestroy(in_stream), in_stream = nullptr;
+		if (out_stream) cudaStreamSynchronize(out_stream), cudaStreamDestroy(out_stream), out_stream = nullptr;
+		if (ev_in) cudaEventDestroy(ev_in), ev_in = nullptr;
 		seq.release(), seq_off.release(), tile_excl.release(), tile_state.release(), mv_off.release(), n_a.release(), a_off.release(), u_off.release(), b_off.release();
 		tile_off.release(), tile_read.release(), occ.release(), arel.release(), rep_len.release(), n_mini_pos.release(), tie_list.release();
 		n_u.release(), n_v.release(), status.release(), mini_pos.release(), hv.release(), u.release(), mv.release(), a.release(), a_tmp.release(), b.release(), small.release();
 		mm2b_ws_destroy(ws), ws = nullptr;
 		h_small.release(), h_read.release(), h_tiles.release();
+		if (h_scal) cudaFreeHost(h_scal), h_scal = d_scal = nullptr;
 		for (auto &e : ev) if (e) cudaEventDestroy(e);
 		if (stream) cudaStreamDestroy(stream);
 		device = -1;
@@ -122,7 +138,9 @@ Ctx *ctx_acquire(int device)
 				return c;
 			}
 	}
+	static std::atomic<int> n_made{0};
 	Ctx *c = new Ctx();
+	c->id = n_made.fetch_add(1);
 	if (!c->create(device)) { c->destroy(); delete c; return nullptr; }
 	return c;
 }
@@ -170,6 +188,12 @@ struct Call {
 	double sketch_ms = 0, seed_ms = 0, sort_ms = 0, chain_ms = 0;
 	int64_t tot_mini = 0, tot_anchors = 0, tot_chains = 0, tot_chained = 0, n_tie = 0, h2d = 0, d2h = 0, cells = 0;
 	DebugOut *dbg = nullptr;
+	// MM2B_MAP_TRACE=1: where every sub-batch spent its time (host clock at the syncs, device clock at the stage events)
+	bool trace = false;
+	std::chrono::steady_clock::time_point t0;
+	cudaEvent_t base_ev = nullptr;
+	std::vector<std::array<float, 15>> rows;
+	long misses0 = 0;
 };
 
 #define CK(expr, what) do { if (!cuda_ok((expr), what)) return false; } while (0)
@@ -186,6 +210,10 @@ bool run_sub(Call &call, Ctx &c, int si)
 	mm2b_map_result_t *res = call.res;
 	cudaStream_t st = c.stream;
 	CK(cudaSetDevice(c.device), "cudaSetDevice");
+	static const bool use_ev = !(getenv("MM2B_MAP_EVENTS") && atoi(getenv("MM2B_MAP_EVENTS")) == 0);
+	float host_t[7] = {0, 0, 0, 0, 0, 0, 0};
+	auto stamp = [&](int i) { if (call.trace) host_t[i] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - call.t0).count(); };
+	stamp(0);
 
 	// ---- offsets and tiles (host), sequences to the device
 	const int64_t tile_pos = sketch_tile_positions(ix->w);
@@ -205,20 +233,27 @@ bool run_sub(Call &call, Ctx &c, int si)
 		}
 	}
 	const int32_t n_tiles = (int32_t)n_tiles64;
-	if (!c.seq.ensure(S + 8, "cudaMalloc(seq)") || !c.seq_off.ensure(R + 1, "cudaMalloc") || !c.tile_off.ensure(R + 1, "cudaMalloc") ||
+	if (!c.seq.ensure(S + 32, "cudaMalloc(seq)") || !c.seq_off.ensure(R + 1, "cudaMalloc") || !c.tile_off.ensure(R + 1, "cudaMalloc") ||
 	    !c.tile_read.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_state.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_excl.ensure(n_tiles + 2, "cudaMalloc") || !c.mv_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.rep_len.ensure(R + 1, "cudaMalloc") || !c.n_mini_pos.ensure(R + 1, "cudaMalloc") || !c.n_a.ensure(R + 1, "cudaMalloc") || !c.a_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.tie_list.ensure(R + 1, "cudaMalloc") || !c.n_u.ensure(R + 1, "cudaMalloc") || !c.n_v.ensure(R + 1, "cudaMalloc") || !c.status.ensure(R + 1, "cudaMalloc") ||
 	    !c.u_off.ensure(R + 2, "cudaMalloc") || !c.b_off.ensure(R + 2, "cudaMalloc")) return false;
-	CK(cudaEventRecord(c.ev[0], st), "cudaEventRecord");
-	if (S > 0) CK(cudaMemcpyAsync(c.seq.p, call.seq + s0, (size_t)S, cudaMemcpyHostToDevice, st), "H2D sequences");
-	CK(cudaMemcpyAsync(c.seq_off.p, h_seq_off, (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, st), "H2D seq_off");
-	CK(cudaMemcpyAsync(c.tile_off.p, h_tile_off, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st), "H2D tile_off");
-	if (n_tiles) CK(cudaMemcpyAsync(c.tile_read.p, h_tile_read, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st), "H2D tile_read");
+	static const bool one_stream = getenv("MM2B_MAP_ONE_STREAM") && atoi(getenv("MM2B_MAP_ONE_STREAM")) > 0;     // the old layout, for comparison
+	cudaStream_t st_in = one_stream ? st : c.in_stream, st_out = one_stream ? st : c.out_stream;
+	if (use_ev) CK(cudaEventRecord(c.ev[0], st_in), "cudaEventRecord");
+	if (S > 0) CK(cudaMemcpyAsync(c.seq.p, call.seq + s0, (size_t)S, cudaMemcpyHostToDevice, st_in), "H2D sequences");
+	CK(cudaMemcpyAsync(c.seq_off.p, h_seq_off, (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, st_in), "H2D seq_off");
+	CK(cudaMemcpyAsync(c.tile_off.p, h_tile_off, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st_in), "H2D tile_off");
+	if (n_tiles) CK(cudaMemcpyAsync(c.tile_read.p, h_tile_read, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st_in), "H2D tile_read");
+	if (!one_stream) {
+		CK(cudaEventRecord(c.ev_in, st_in), "cudaEventRecord");
+		CK(cudaStreamWaitEvent(st, c.ev_in, 0), "cudaStreamWaitEvent");
+	}
+	stamp(1);
 
 	SeedArgs a;
 	memset(&a, 0, sizeof(a));
-	a.n_reads = R, a.seq = c.seq.p, a.seq_off = c.seq_off.p, a.tile_off = c.tile_off.p, a.tile_read = c.tile_read.p, a.n_tiles = n_tiles;
+	a.n_reads = R, a.seq = c.seq.p, a.seq_len = S, a.seq_off = c.seq_off.p, a.tile_off = c.tile_off.p, a.tile_read = c.tile_read.p, a.n_tiles = n_tiles;
 	a.k = ix->k, a.w = ix->w, a.max_occ = call.seed.max_occ;
 	a.tile_state = c.tile_state.p, a.tile_ticket = c.small.p + 8, a.tile_excl = c.tile_excl.p, a.mv_off = c.mv_off.p;
 	a.rep_len = c.rep_len.p, a.n_mini_pos = c.n_mini_pos.p, a.n_a = c.n_a.p, a.a_off = c.a_off.p, a.tie_list = c.tie_list.p, a.tie_count = c.small.p;
@@ -226,8 +261,7 @@ bool run_sub(Call &call, Ctx &c, int si)
 	// ---- sketch: one pass into a buffer sized for the usual density of minimizers (2 / (w + 1) per base, and half as much again);
 	//      (sync: how many there are) and once more into a larger buffer in the rare case that was not enough
 	int launches = 0;
-	int64_t *h_tot = (int64_t*)((char*)c.h_small.p + (size_t)(R + 1) * 12);       // 8-byte aligned: (R+1)*12 is a multiple of 4 only ...
-	h_tot = (int64_t*)(((uintptr_t)h_tot + 7) & ~(uintptr_t)7);                   // ... so round up (64 spare bytes were reserved)
+	volatile int64_t *h_tot = c.h_scal;         // totals arrive by a store from the device, not by a copy (see export_scalars_kernel)
 	int64_t n_mv = 0;
 	if (!c.mv.ensure(std::max<int64_t>(c.mv.cap, 3 * S / (ix->w + 1) + 1024), "cudaMalloc(mv)")) return false;
 	static const bool tiny_first = getenv("MM2B_TEST_SMALL_MV") && atoi(getenv("MM2B_TEST_SMALL_MV")) > 0;     // test hook: force the second attempt
@@ -236,9 +270,10 @@ bool run_sub(Call &call, Ctx &c, int si)
 		h_tot[0] = 0;
 		if (n_tiles > 0) {
 			launches += launch_sketch(a, st);
-			CK(cudaMemcpyAsync(h_tot, c.tile_excl.p + n_tiles, 8, cudaMemcpyDeviceToHost, st), "D2H minimizer total");
+			launches += launch_export_scalars(c.d_scal, c.tile_excl.p + n_tiles, nullptr, nullptr, st);
 		}
 		CK(cudaStreamSynchronize(st), "sketch");
+		stamp(2);
 		n_mv = h_tot[0];
 		if (n_mv <= a.mv_cap) break;
 		if (attempt == 1 || !c.mv.ensure(n_mv + 1, "cudaMalloc(mv)")) { if (attempt == 1) set_error("%s%s", "mm2b_map_batch: minimizer buffer", ""); return false; }
@@ -246,22 +281,23 @@ bool run_sub(Call &call, Ctx &c, int si)
 	if (!c.occ.ensure(n_mv + 1, "cudaMalloc") || !c.hv.ensure(n_mv + 1, "cudaMalloc") || !c.arel.ensure(n_mv + 1, "cudaMalloc") || !c.mini_pos.ensure(n_mv + 1, "cudaMalloc")) return false;
 	a.occ = c.occ.p, a.hv = c.hv.p, a.arel = c.arel.p, a.mini_pos = c.mini_pos.p;
 	launches += launch_read_offsets(a, st);
-	CK(cudaEventRecord(c.ev[1], st), "cudaEventRecord");
+	if (use_ev) CK(cudaEventRecord(c.ev[1], st), "cudaEventRecord");
 
 	// ---- index probes, matches, (sync: how many anchors)
 	launches += launch_index_lookup(*ix, n_mv, c.mv.p, nullptr, c.occ.p, c.hv.p, st);
 	launches += launch_matches(a, c.n_sms, st);
 	launches += launch_scan_i64(c.n_a.p, c.a_off.p, R, st);
-	CK(cudaMemcpyAsync(h_tot, c.a_off.p + R, 8, cudaMemcpyDeviceToHost, st), "D2H anchor total");
+	launches += launch_export_scalars(c.d_scal, c.a_off.p + R, nullptr, nullptr, st);
 	CK(cudaStreamSynchronize(st), "matches");
+	stamp(3);
 	const int64_t n_anchors = h_tot[0];
 	if (n_anchors >= (1ll << 31)) { set_error("%s%s", "mm2b_map_batch: more than 2^31 anchors in one sub-batch", ""); return false; }
 	if (!c.a.ensure(n_anchors + 1, "cudaMalloc(a)") || !c.a_tmp.ensure(n_anchors + 1, "cudaMalloc(a_tmp)")) return false;
 	a.a = c.a.p, a.a_tmp = c.a_tmp.p;
-	launches += launch_expand(a, *ix, c.n_sms, st);
-	CK(cudaEventRecord(c.ev[2], st), "cudaEventRecord");
+	launches += launch_expand(a, *ix, n_mv, st);
+	if (use_ev) CK(cudaEventRecord(c.ev[2], st), "cudaEventRecord");
 	launches += launch_sort(a, *ix, c.n_sms, st);
-	CK(cudaEventRecord(c.ev[3], st), "cudaEventRecord");
+	if (use_ev) CK(cudaEventRecord(c.ev[3], st), "cudaEventRecord");
 
 	// ---- per-read results staging: [n_u][n_v][status][rep_len][n_mini_pos] int32, then [n_a][mv_off][u_off][b_off] int64 (+1 entries)
 	if (!c.h_read.ensure((size_t)(R + 2) * (5 * 4 + 4 * 8) + 64)) return false;
@@ -269,7 +305,6 @@ bool run_sub(Call &call, Ctx &c, int si)
 	int64_t *h_i64 = (int64_t*)(((uintptr_t)(h_i32 + 5 * (R + 1)) + 7) & ~(uintptr_t)7);
 	int32_t *h_n_u = h_i32, *h_n_v = h_i32 + (R + 1), *h_status = h_i32 + 2 * (R + 1), *h_rep = h_i32 + 3 * (R + 1), *h_nmp = h_i32 + 4 * (R + 1);
 	int64_t *h_n_a = h_i64, *h_mv_off = h_i64 + (R + 1), *h_u_off = h_i64 + 2 * (R + 1), *h_b_off = h_i64 + 3 * (R + 1);
-	int *h_tie = (int*)(h_tot + 1);
 
 	if (call.chain) {
 		if (n_anchors > c.ws_anchors || R > c.ws_reads) {
@@ -283,19 +318,16 @@ bool run_sub(Call &call, Ctx &c, int si)
 		mm2b_ws_set_counting(c.ws, mm2b_counting());
 		if (mm2b_chain_batch_device(c.ws, call.chain, R, n_anchors, c.a_off.p, (const mm2b_anchor_t*)c.a.p, c.n_u.p, c.n_v.p, c.status.p, c.u_off.p, c.b_off.p,
 		                            c.u.p, (mm2b_anchor_t*)c.b.p, st) != MM2B_OK) return false;
-		CK(cudaEventRecord(c.ev[4], st), "cudaEventRecord");
-		CK(cudaMemcpyAsync(h_n_u, c.n_u.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st), "D2H n_u");
-		CK(cudaMemcpyAsync(h_n_v, c.n_v.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st), "D2H n_v");
-		CK(cudaMemcpyAsync(h_status, c.status.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st), "D2H status");
-		CK(cudaMemcpyAsync(h_u_off, c.u_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H u_off");
-		CK(cudaMemcpyAsync(h_b_off, c.b_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H b_off");
-	} else CK(cudaEventRecord(c.ev[4], st), "cudaEventRecord");
-	CK(cudaMemcpyAsync(h_rep, c.rep_len.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st), "D2H rep_len");
-	CK(cudaMemcpyAsync(h_nmp, c.n_mini_pos.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st), "D2H n_mini_pos");
-	CK(cudaMemcpyAsync(h_n_a, c.n_a.p, (size_t)R * 8, cudaMemcpyDeviceToHost, st), "D2H n_a");
-	CK(cudaMemcpyAsync(h_mv_off, c.mv_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H mv_off");
-	CK(cudaMemcpyAsync(h_tie, c.small.p, 4, cudaMemcpyDeviceToHost, st), "D2H tie count");
-	CK(cudaStreamSynchronize(st), "chain");
+		if (use_ev) CK(cudaEventRecord(c.ev[4], st), "cudaEventRecord");
+		launches += launch_export_scalars(c.d_scal, c.u_off.p + R, c.b_off.p + R, c.small.p, st);
+	} else {
+		if (use_ev) CK(cudaEventRecord(c.ev[4], st), "cudaEventRecord");
+		launches += launch_export_scalars(c.d_scal, nullptr, nullptr, c.small.p, st);
+	}
+	CK(cudaStreamSynchronize(st), "chain");         // (sync: how many chains and chained anchors come back)
+	const int64_t tot_u = call.chain ? h_tot[0] : 0, tot_b = call.chain ? h_tot[1] : 0;
+	const int n_tie_reads = (int)h_tot[2];
+	stamp(4);
 	CK(cudaGetLastError(), "kernels");
 	count_launches(launches);
 
@@ -307,10 +339,13 @@ bool run_sub(Call &call, Ctx &c, int si)
 
 	if (call.dbg) {                             // debug: bring the intermediate products back
 		DebugOut &d = *call.dbg;
+		CK(cudaMemcpy(h_rep, c.rep_len.p, (size_t)R * 4, cudaMemcpyDeviceToHost), "D2H rep_len");
+		CK(cudaMemcpy(h_nmp, c.n_mini_pos.p, (size_t)R * 4, cudaMemcpyDeviceToHost), "D2H n_mini_pos");
+		CK(cudaMemcpy(h_mv_off, c.mv_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost), "D2H mv_off");
 		d.mv_off.assign(h_mv_off, h_mv_off + R + 1);
 		d.a_off.resize((size_t)R + 1);
 		d.mv.resize((size_t)n_mv), d.a.resize((size_t)n_anchors), d.mini_pos.resize((size_t)n_mv);
-		d.rep_len.assign(h_rep, h_rep + R), d.n_mini_pos.assign(h_nmp, h_nmp + R), d.n_tie = h_tie[0];
+		d.rep_len.assign(h_rep, h_rep + R), d.n_mini_pos.assign(h_nmp, h_nmp + R), d.n_tie = n_tie_reads;
 		CK(cudaMemcpy(d.a_off.data(), c.a_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost), "D2H a_off");
 		if (n_mv) CK(cudaMemcpy(d.mv.data(), c.mv.p, (size_t)n_mv * 16, cudaMemcpyDeviceToHost), "D2H mv");
 		if (n_mv) CK(cudaMemcpy(d.mini_pos.data(), c.mini_pos.p, (size_t)n_mv * 4, cudaMemcpyDeviceToHost), "D2H mini_pos");
@@ -318,14 +353,27 @@ bool run_sub(Call &call, Ctx &c, int si)
 		return true;
 	}
 
-	// ---- outputs into this sub-batch's segment
-	const int64_t tot_u = h_u_off[R], tot_b = h_b_off[R];
+	// ---- outputs into this sub-batch's segment (the kernels are done: the host has just waited for their totals)
 	Segment *seg = call.priv->segs[(size_t)si];
 	if (!seg->u.ensure((size_t)(tot_u + 1) * 8) || !seg->b.ensure((size_t)(tot_b + 1) * 16) || !seg->mp.ensure((size_t)(n_mv + 1) * 4)) return false;
-	if (tot_u) CK(cudaMemcpyAsync(seg->u.p, c.u.p, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st), "D2H u");
-	if (tot_b) CK(cudaMemcpyAsync(seg->b.p, c.b.p, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st), "D2H b");
-	if (n_mv) CK(cudaMemcpyAsync(seg->mp.p, c.mini_pos.p, (size_t)n_mv * 4, cudaMemcpyDeviceToHost, st), "D2H mini_pos");
-	CK(cudaEventRecord(c.ev[5], st), "cudaEventRecord");
+	if (tot_u) CK(cudaMemcpyAsync(seg->u.p, c.u.p, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st_out), "D2H u");
+	if (tot_b) CK(cudaMemcpyAsync(seg->b.p, c.b.p, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st_out), "D2H b");
+	if (n_mv) CK(cudaMemcpyAsync(seg->mp.p, c.mini_pos.p, (size_t)n_mv * 4, cudaMemcpyDeviceToHost, st_out), "D2H mini_pos");
+	if (call.chain) {
+		CK(cudaMemcpyAsync(h_n_u, c.n_u.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H n_u");
+		CK(cudaMemcpyAsync(h_n_v, c.n_v.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H n_v");
+		CK(cudaMemcpyAsync(h_status, c.status.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H status");
+		CK(cudaMemcpyAsync(h_u_off, c.u_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st_out), "D2H u_off");
+		CK(cudaMemcpyAsync(h_b_off, c.b_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st_out), "D2H b_off");
+	}
+	CK(cudaMemcpyAsync(h_rep, c.rep_len.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H rep_len");
+	CK(cudaMemcpyAsync(h_nmp, c.n_mini_pos.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H n_mini_pos");
+	CK(cudaMemcpyAsync(h_n_a, c.n_a.p, (size_t)R * 8, cudaMemcpyDeviceToHost, st_out), "D2H n_a");
+	CK(cudaMemcpyAsync(h_mv_off, c.mv_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st_out), "D2H mv_off");
+	if (use_ev) CK(cudaEventRecord(c.ev[5], st_out), "cudaEventRecord");
+	stamp(5);
+	CK(cudaStreamSynchronize(st_out), "outputs");
+	stamp(6);
 	call.priv->seg_u[(size_t)si] = (uint64_t*)seg->u.p, call.priv->seg_b[(size_t)si] = (mm2b_anchor_t*)seg->b.p, call.priv->seg_mp[(size_t)si] = (uint32_t*)seg->mp.p;
 	for (int64_t r = 0; r < R; ++r) {
 		const int64_t g = sb.r0 + r;
@@ -333,13 +381,21 @@ bool run_sub(Call &call, Ctx &c, int si)
 		res->n_mini[g] = (int32_t)(h_mv_off[r + 1] - h_mv_off[r]), res->seg[g] = si;
 		res->n_a[g] = h_n_a[r], res->u_off[g] = h_u_off[r], res->b_off[g] = h_b_off[r], res->mp_off[g] = h_mv_off[r];
 	}
-	CK(cudaStreamSynchronize(st), "outputs");
 	float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
-	cudaEventElapsedTime(&t01, c.ev[0], c.ev[1]), cudaEventElapsedTime(&t12, c.ev[1], c.ev[2]);
-	cudaEventElapsedTime(&t23, c.ev[2], c.ev[3]), cudaEventElapsedTime(&t34, c.ev[3], c.ev[4]);
+	if (use_ev) {
+		cudaEventElapsedTime(&t01, c.ev[0], c.ev[1]), cudaEventElapsedTime(&t12, c.ev[1], c.ev[2]);
+		cudaEventElapsedTime(&t23, c.ev[2], c.ev[3]), cudaEventElapsedTime(&t34, c.ev[3], c.ev[4]);
+	}
 	std::lock_guard<std::mutex> lk(call.mu);
+	if (call.trace && call.base_ev) {
+		std::array<float, 15> row;
+		row[0] = (float)si, row[1] = (float)c.id;
+		for (int i = 0; i < 7; ++i) row[2 + i] = host_t[i];
+		for (int i = 0; i < 6; ++i) { row[9 + i] = 0; if (use_ev) cudaEventElapsedTime(&row[9 + i], call.base_ev, c.ev[i]); }
+		call.rows.push_back(row);
+	}
 	call.sketch_ms += t01, call.seed_ms += t12, call.sort_ms += t23, call.chain_ms += t34;
-	call.tot_mini += n_mv, call.tot_anchors += n_anchors, call.tot_chains += tot_u, call.tot_chained += tot_b, call.n_tie += h_tie[0], call.cells += cells;
+	call.tot_mini += n_mv, call.tot_anchors += n_anchors, call.tot_chains += tot_u, call.tot_chained += tot_b, call.n_tie += n_tie_reads, call.cells += cells;
 	call.h2d += S + (R + 1) * 12, call.d2h += tot_u * 8 + tot_b * 16 + n_mv * 4 + R * 28 + (R + 1) * 24;
 	return true;
 }
@@ -357,7 +413,7 @@ void worker(Call *call, int device)
 		const int si = call->next.fetch_add(1);
 		if (si >= (int)call->subs.size()) break;
 		if (!run_sub(*call, *c, si)) {
-			cudaStreamSynchronize(c->stream);
+			cudaStreamSynchronize(c->in_stream), cudaStreamSynchronize(c->stream), cudaStreamSynchronize(c->out_stream);
 			std::lock_guard<std::mutex> lk(call->mu);
 			if (!call->failed.exchange(1)) snprintf(call->err, sizeof(call->err), "%s", mm2b_last_error());
 			break;
@@ -392,10 +448,26 @@ void run_call(Call &call)
 	const int n_dev = (int)call.idx->dev.size();
 	const int per_dev = (int)env_ll("MM2B_MAP_CTX", 6);      // measured: 2 / 3 / 4 / 6 contexts -> 1.09 / 1.19 / 1.27 / 1.37 M reads/s (profiles/r2r_front_sweep.txt)
 	const int n_workers = (int)std::min<int64_t>((int64_t)n_dev * per_dev, (int64_t)call.subs.size());
+	static const bool trace = getenv("MM2B_MAP_TRACE") && atoi(getenv("MM2B_MAP_TRACE")) > 0;
+	cudaStream_t base_st = nullptr;
+	if (trace && n_dev == 1 && !call.dbg && cudaSetDevice(call.idx->dev[0].device) == cudaSuccess && cudaStreamCreateWithFlags(&base_st, cudaStreamNonBlocking) == cudaSuccess) {
+		call.trace = true, call.t0 = std::chrono::steady_clock::now(), call.misses0 = pin_pool_misses();
+		cudaEventCreate(&call.base_ev);
+		cudaEventRecord(call.base_ev, base_st);
+		cudaStreamSynchronize(base_st);
+	}
 	std::vector<std::thread> th;
 	for (int i = 1; i < n_workers; ++i) th.emplace_back(worker, &call, call.idx->dev[(size_t)(i % n_dev)].device);
 	if (n_workers > 0) worker(&call, call.idx->dev[0].device);
 	for (auto &t : th) t.join();
+	if (call.trace) {
+		std::sort(call.rows.begin(), call.rows.end());
+		fprintf(stderr, "[mm2b trace] sub ctx | host: start inputs-enqueued sketch-sync matches-sync chain-sync outputs-enqueued outputs-sync | device: h2d-start sketch-end seed-end sort-end chain-end d2h-end (ms since the call began); pinned-pool misses during the call: %ld\n", pin_pool_misses() - call.misses0);
+		for (const auto &r : call.rows)
+			fprintf(stderr, "[mm2b trace] %3d %2d | %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f | %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f\n", (int)r[0], (int)r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14]);
+		cudaEventDestroy(call.base_ev);
+		cudaStreamDestroy(base_st);
+	}
 }
 
 }  // namespace

@@ -21,6 +21,7 @@ settings += [dict(MM2B_PACK_INFLIGHT=str(k), MM2B_PACK_RING=str(r)) for r in (1,
 settings += [dict(MM2B_PACK_INFLIGHT=str(k), MM2B_PACK_RING="1", MM2B_SUB_ANCHORS=str(4 << 20)) for k in (1, 2, 99)]
 settings += [dict(MM2B_PACK_INFLIGHT=str(k), MM2B_PACK_RING="1", MM2B_PACK_CHUNK=str(c << 10)) for k in (2, 99) for c in (16, 32, 256)]
 settings += [dict(MM2B_PACK_INFLIGHT="99", MM2B_PACK_RING="1", MM2B_HOST_THREADS=str(t)) for t in (6, 10)]
+if os.environ.get("E2E_QUICK"): settings = [dict(MM2B_PACK_INFLIGHT="0"), dict(MM2B_PACK_INFLIGHT="99", MM2B_PACK_RING="1")]     # raw input, everything packed
 for env in settings:
     for k, v in env.items():
         os.environ[k] = v
