@@ -780,16 +780,14 @@ __global__ void __launch_bounds__(256) expand_kernel(const SeedArgs s, const Dev
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_mv) return;
+	const int rel = s.arel[i];
+	if (rel < 0) return;
 	int lo = 0, hi = (int)s.n_reads;                        // mv_off[lo] <= i < mv_off[hi]
 	while (hi - lo > 1) {
 		const int mid = (lo + hi) >> 1;
 		if (__ldg(s.mv_off + mid) <= i) lo = mid; else hi = mid;
 	}
 	const int64_t r = lo, m0 = __ldg(s.mv_off + r), m1 = __ldg(s.mv_off + r + 1);
-	// the reads' mini_pos lists, closed up for the trip to the host (matches_kernel left each at its read's minimizer offset)
-	if (s.mp_pack && i - m0 < s.n_mini_pos[r]) s.mp_pack[s.mp_off[r] + (i - m0)] = s.mini_pos[i];
-	const int rel = s.arel[i];
-	if (rel < 0) return;
 	const int qlen = (int)(s.seq_off[r + 1] - s.seq_off[r]);
 	ulonglong2 *a = s.a_tmp + s.a_off[r] + rel;
 	const ulonglong2 q = __ldg(s.mv + i);
@@ -1162,12 +1160,6 @@ int launch_sketch(const SeedArgs &s, cudaStream_t stream)
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream)
 {
 	scan_kernel<int64_t><<<1, 1024, 0, stream>>>(in, out, n);
-	return 1;
-}
-
-int launch_scan_i32(const int32_t *in, int64_t *out, int64_t n, cudaStream_t stream)
-{
-	scan_kernel<int32_t><<<1, 1024, 0, stream>>>(in, out, n);
 	return 1;
 }
 

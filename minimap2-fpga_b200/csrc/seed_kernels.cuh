@@ -44,8 +44,6 @@ struct SeedArgs {
 	uint64_t *hv;               // per minimizer: the table's value word
 	int32_t *arel;              // per minimizer: first anchor of this minimizer inside its read (matches only)
 	uint32_t *mini_pos;         // per read at mv_off[r]: query positions of the matches (map.c:117)
-	const int64_t *mp_off;      // [n_reads + 1] exclusive prefix of n_mini_pos
-	uint32_t *mp_pack;          // the same lists at mp_off[r], written by the expansion (null: not wanted)
 	int32_t *rep_len, *n_mini_pos;
 	int64_t *n_a;               // per read
 	const int64_t *a_off;       // [n_reads + 1] exclusive prefix of n_a
@@ -59,7 +57,6 @@ int launch_index_lookup(const DeviceIndex &ix, int64_t n, const ulonglong2 *mv, 
 int sketch_tile_positions(int w);        // positions per tile of the kernel launch_sketch will use for this window size
 int launch_sketch(const SeedArgs &s, cudaStream_t stream);
 int launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t stream);      // out[0..n]: exclusive prefix, out[n] = total
-int launch_scan_i32(const int32_t *in, int64_t *out, int64_t n, cudaStream_t stream);
 int launch_export_scalars(int64_t *host_mapped, const int64_t *a, const int64_t *b, const int *c, cudaStream_t stream);   // host_mapped[0..2] = *a, *b, *c (null: left alone)
 int launch_read_offsets(const SeedArgs &s, cudaStream_t stream);                            // mv_off[r] = tile_excl[tile_off[r]]
 int launch_matches(const SeedArgs &s, int n_sms, cudaStream_t stream);                      // collect_matches per read

@@ -76,10 +76,10 @@ struct Ctx {
 	cudaEvent_t ev_in = nullptr;
 	cudaEvent_t ev[6] = {};
 	DevBuf<uint8_t> seq;
-	DevBuf<int64_t> seq_off, tile_excl, mv_off, n_a, a_off, u_off, b_off, mp_off;
+	DevBuf<int64_t> seq_off, tile_excl, mv_off, n_a, a_off, u_off, b_off;
 	DevBuf<unsigned long long> tile_state;
 	DevBuf<int32_t> tile_off, tile_read, occ, arel, rep_len, n_mini_pos, tie_list, n_u, n_v, status;
-	DevBuf<uint32_t> mini_pos, mp_pack;
+	DevBuf<uint32_t> mini_pos;
 	DevBuf<uint64_t> hv, u;
 	DevBuf<ulonglong2> mv, a, a_tmp, b;
 	DevBuf<int> small;
@@ -109,7 +109,7 @@ struct Ctx {
 		if (in_stream) cudaStreamSynchronize(in_stream), cudaStreamDestroy(in_stream), in_stream = nullptr;
 		if (out_stream) cudaStreamSynchronize(out_stream), cudaStreamDestroy(out_stream), out_stream = nullptr;
 		if (ev_in) cudaEventDestroy(ev_in), ev_in = nullptr;
-		seq.release(), seq_off.release(), tile_excl.release(), tile_state.release(), mv_off.release(), n_a.release(), a_off.release(), u_off.release(), b_off.release(), mp_off.release(), mp_pack.release();
+		seq.release(), seq_off.release(), tile_excl.release(), tile_state.release(), mv_off.release(), n_a.release(), a_off.release(), u_off.release(), b_off.release();
 		tile_off.release(), tile_read.release(), occ.release(), arel.release(), rep_len.release(), n_mini_pos.release(), tie_list.release();
 		n_u.release(), n_v.release(), status.release(), mini_pos.release(), hv.release(), u.release(), mv.release(), a.release(), a_tmp.release(), b.release(), small.release();
 		mm2b_ws_destroy(ws), ws = nullptr;
@@ -237,7 +237,7 @@ bool run_sub(Call &call, Ctx &c, int si)
 	    !c.tile_read.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_state.ensure(n_tiles + 1, "cudaMalloc") || !c.tile_excl.ensure(n_tiles + 2, "cudaMalloc") || !c.mv_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.rep_len.ensure(R + 1, "cudaMalloc") || !c.n_mini_pos.ensure(R + 1, "cudaMalloc") || !c.n_a.ensure(R + 1, "cudaMalloc") || !c.a_off.ensure(R + 2, "cudaMalloc") ||
 	    !c.tie_list.ensure(R + 1, "cudaMalloc") || !c.n_u.ensure(R + 1, "cudaMalloc") || !c.n_v.ensure(R + 1, "cudaMalloc") || !c.status.ensure(R + 1, "cudaMalloc") ||
-	    !c.u_off.ensure(R + 2, "cudaMalloc") || !c.b_off.ensure(R + 2, "cudaMalloc") || !c.mp_off.ensure(R + 2, "cudaMalloc")) return false;
+	    !c.u_off.ensure(R + 2, "cudaMalloc") || !c.b_off.ensure(R + 2, "cudaMalloc")) return false;
 	static const bool one_stream = getenv("MM2B_MAP_ONE_STREAM") && atoi(getenv("MM2B_MAP_ONE_STREAM")) > 0;     // the old layout, for comparison
 	cudaStream_t st_in = one_stream ? st : c.in_stream, st_out = one_stream ? st : c.out_stream;
 	if (use_ev) CK(cudaEventRecord(c.ev[0], st_in), "cudaEventRecord");
@@ -287,26 +287,24 @@ bool run_sub(Call &call, Ctx &c, int si)
 	launches += launch_index_lookup(*ix, n_mv, c.mv.p, nullptr, c.occ.p, c.hv.p, st);
 	launches += launch_matches(a, c.n_sms, st);
 	launches += launch_scan_i64(c.n_a.p, c.a_off.p, R, st);
-	launches += launch_scan_i32(c.n_mini_pos.p, c.mp_off.p, R, st);
-	launches += launch_export_scalars(c.d_scal, c.a_off.p + R, c.mp_off.p + R, nullptr, st);
+	launches += launch_export_scalars(c.d_scal, c.a_off.p + R, nullptr, nullptr, st);
 	CK(cudaStreamSynchronize(st), "matches");
 	stamp(3);
-	const int64_t n_anchors = h_tot[0], tot_mp = h_tot[1];
+	const int64_t n_anchors = h_tot[0];
 	if (n_anchors >= (1ll << 31)) { set_error("%s%s", "mm2b_map_batch: more than 2^31 anchors in one sub-batch", ""); return false; }
 	if (!c.a.ensure(n_anchors + 1, "cudaMalloc(a)") || !c.a_tmp.ensure(n_anchors + 1, "cudaMalloc(a_tmp)")) return false;
-	if (!c.mp_pack.ensure(tot_mp + 1, "cudaMalloc(mini_pos)")) return false;
-	a.a = c.a.p, a.a_tmp = c.a_tmp.p, a.mp_off = c.mp_off.p, a.mp_pack = call.dbg ? nullptr : c.mp_pack.p;
+	a.a = c.a.p, a.a_tmp = c.a_tmp.p;
 	launches += launch_expand(a, *ix, n_mv, st);
 	if (use_ev) CK(cudaEventRecord(c.ev[2], st), "cudaEventRecord");
 	launches += launch_sort(a, *ix, c.n_sms, st);
 	if (use_ev) CK(cudaEventRecord(c.ev[3], st), "cudaEventRecord");
 
-	// ---- per-read results staging: [n_u][n_v][status][rep_len][n_mini_pos] int32, then [n_a][mv_off][u_off][b_off][mp_off] int64 (+1 entries)
-	if (!c.h_read.ensure((size_t)(R + 2) * (5 * 4 + 5 * 8) + 64)) return false;
+	// ---- per-read results staging: [n_u][n_v][status][rep_len][n_mini_pos] int32, then [n_a][mv_off][u_off][b_off] int64 (+1 entries)
+	if (!c.h_read.ensure((size_t)(R + 2) * (5 * 4 + 4 * 8) + 64)) return false;
 	int32_t *h_i32 = (int32_t*)c.h_read.p;
 	int64_t *h_i64 = (int64_t*)(((uintptr_t)(h_i32 + 5 * (R + 1)) + 7) & ~(uintptr_t)7);
 	int32_t *h_n_u = h_i32, *h_n_v = h_i32 + (R + 1), *h_status = h_i32 + 2 * (R + 1), *h_rep = h_i32 + 3 * (R + 1), *h_nmp = h_i32 + 4 * (R + 1);
-	int64_t *h_n_a = h_i64, *h_mv_off = h_i64 + (R + 1), *h_u_off = h_i64 + 2 * (R + 1), *h_b_off = h_i64 + 3 * (R + 1), *h_mp_off = h_i64 + 4 * (R + 1);
+	int64_t *h_n_a = h_i64, *h_mv_off = h_i64 + (R + 1), *h_u_off = h_i64 + 2 * (R + 1), *h_b_off = h_i64 + 3 * (R + 1);
 
 	if (call.chain) {
 		if (n_anchors > c.ws_anchors || R > c.ws_reads) {
@@ -357,10 +355,10 @@ bool run_sub(Call &call, Ctx &c, int si)
 
 	// ---- outputs into this sub-batch's segment (the kernels are done: the host has just waited for their totals)
 	Segment *seg = call.priv->segs[(size_t)si];
-	if (!seg->u.ensure((size_t)(tot_u + 1) * 8) || !seg->b.ensure((size_t)(tot_b + 1) * 16) || !seg->mp.ensure((size_t)(tot_mp + 1) * 4)) return false;
+	if (!seg->u.ensure((size_t)(tot_u + 1) * 8) || !seg->b.ensure((size_t)(tot_b + 1) * 16) || !seg->mp.ensure((size_t)(n_mv + 1) * 4)) return false;
 	if (tot_u) CK(cudaMemcpyAsync(seg->u.p, c.u.p, (size_t)tot_u * 8, cudaMemcpyDeviceToHost, st_out), "D2H u");
 	if (tot_b) CK(cudaMemcpyAsync(seg->b.p, c.b.p, (size_t)tot_b * 16, cudaMemcpyDeviceToHost, st_out), "D2H b");
-	if (tot_mp) CK(cudaMemcpyAsync(seg->mp.p, c.mp_pack.p, (size_t)tot_mp * 4, cudaMemcpyDeviceToHost, st_out), "D2H mini_pos");
+	if (n_mv) CK(cudaMemcpyAsync(seg->mp.p, c.mini_pos.p, (size_t)n_mv * 4, cudaMemcpyDeviceToHost, st_out), "D2H mini_pos");
 	if (call.chain) {
 		CK(cudaMemcpyAsync(h_n_u, c.n_u.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H n_u");
 		CK(cudaMemcpyAsync(h_n_v, c.n_v.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H n_v");
@@ -372,7 +370,6 @@ bool run_sub(Call &call, Ctx &c, int si)
 	CK(cudaMemcpyAsync(h_nmp, c.n_mini_pos.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st_out), "D2H n_mini_pos");
 	CK(cudaMemcpyAsync(h_n_a, c.n_a.p, (size_t)R * 8, cudaMemcpyDeviceToHost, st_out), "D2H n_a");
 	CK(cudaMemcpyAsync(h_mv_off, c.mv_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st_out), "D2H mv_off");
-	CK(cudaMemcpyAsync(h_mp_off, c.mp_off.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st_out), "D2H mp_off");
 	if (use_ev) CK(cudaEventRecord(c.ev[5], st_out), "cudaEventRecord");
 	stamp(5);
 	CK(cudaStreamSynchronize(st_out), "outputs");
@@ -382,7 +379,7 @@ bool run_sub(Call &call, Ctx &c, int si)
 		const int64_t g = sb.r0 + r;
 		res->status[g] = h_status[r], res->n_u[g] = h_n_u[r], res->n_v[g] = h_n_v[r], res->rep_len[g] = h_rep[r], res->n_mini_pos[g] = h_nmp[r];
 		res->n_mini[g] = (int32_t)(h_mv_off[r + 1] - h_mv_off[r]), res->seg[g] = si;
-		res->n_a[g] = h_n_a[r], res->u_off[g] = h_u_off[r], res->b_off[g] = h_b_off[r], res->mp_off[g] = h_mp_off[r];
+		res->n_a[g] = h_n_a[r], res->u_off[g] = h_u_off[r], res->b_off[g] = h_b_off[r], res->mp_off[g] = h_mv_off[r];
 	}
 	float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
 	if (use_ev) {
@@ -399,7 +396,7 @@ bool run_sub(Call &call, Ctx &c, int si)
 	}
 	call.sketch_ms += t01, call.seed_ms += t12, call.sort_ms += t23, call.chain_ms += t34;
 	call.tot_mini += n_mv, call.tot_anchors += n_anchors, call.tot_chains += tot_u, call.tot_chained += tot_b, call.n_tie += n_tie_reads, call.cells += cells;
-	call.h2d += S + (R + 1) * 12, call.d2h += tot_u * 8 + tot_b * 16 + tot_mp * 4 + R * 28 + (R + 1) * 32;
+	call.h2d += S + (R + 1) * 12, call.d2h += tot_u * 8 + tot_b * 16 + n_mv * 4 + R * 28 + (R + 1) * 24;
 	return true;
 }
 
