@@ -129,7 +129,8 @@ int mm2b_chain_batch(const mm2b_params_t *par, int64_t n_reads, const int64_t *o
  *                                 memory bandwidth is plentiful compared with the PCIe link).
  * mm2b_chain_batch itself (b[] out as anchors) sends the input raw and gathers on the device: with 16 B per chained anchor coming back the
  * host's memory system is busy enough, and packing next to it measured slower.  Environment overrides (tuning): MM2B_PACK=1 (pack there
- * too), MM2B_PACK_INFLIGHT=n, MM2B_GATHER=host|device, MM2B_HOST_THREADS=n. */
+ * too), MM2B_PACK_INFLIGHT=n, MM2B_GATHER=host|device, MM2B_HOST_THREADS=n, MM2B_ONE_STREAM=1 (copies and kernels of a pipeline slot on
+ * one stream instead of three: slower, kept for comparison). */
 enum { MM2B_F_RAW_INPUT = 1, MM2B_F_DEVICE_GATHER = 2, MM2B_F_HOST_GATHER = 4 };
 int mm2b_chain_batch_ex(const mm2b_params_t *par, int64_t n_reads, const int64_t *off, const mm2b_anchor_t *a,
                         int32_t *n_u, int32_t *n_v, int32_t *status, int64_t *u_off, int64_t *b_off,

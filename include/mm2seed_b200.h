@@ -83,7 +83,11 @@ typedef struct {
 
 /* Sketch, seed, sort and chain `n_reads` reads.  Read r is seq[seq_off[r] .. seq_off[r+1]) as the ASCII bases bseq.c hands to
  * mm_map_frag (any byte that is not ACGTacgt counts as ambiguous, sketch.c:9-26).  Reads are sharded over the bound devices in
- * sub-batches; results come back in input order.  Blocking; thread-safe.  Returns MM2B_OK or an error code; *out is NULL on error. */
+ * sub-batches; results come back in input order.  Blocking; thread-safe.  Returns MM2B_OK or an error code; *out is NULL on error.
+ * Environment overrides (tuning / diagnosis): MM2B_MAP_CTX=n pipeline contexts per device (default 6), MM2B_MAP_SUB_BYTES=n bytes of
+ * sequence per sub-batch (default 64 MiB), MM2B_MAP_RAMP=0 equal sub-batches from the start, MM2B_MAP_TRACE=1 per-sub-batch timeline on
+ * stderr, MM2B_MAP_ONE_STREAM=1 copies and kernels of a context on one stream (slower: kept for comparison), MM2B_SKETCH8=0 the
+ * one-position-per-thread sketch kernel for every window size, MM2B_SKETCH8_CTAS=3 its 80-register build. */
 int mm2b_map_batch(mm2b_index_t *idx, const mm2b_seed_params_t *seed, const mm2b_params_t *chain,
                    int64_t n_reads, const int64_t *seq_off, const char *seq, mm2b_map_result_t **out);
 void mm2b_map_result_release(mm2b_map_result_t *res);
