@@ -2,7 +2,8 @@
   * pinned against the reference itself — oracle/_ref/mm2-seed-ref runs the reference's own collect_minimizers / collect_seed_hits
     (map.c:64-78, :215-247) on generated reads and records minimizers, sorted anchors, rep_len and mini_pos;
   * pinned against a committed fixture of those records (tests/golden/seed_golden.npz, written by tests/golden/make_seed_golden.py);
-  * the position-parallel formulation the sketch kernel uses, modelled in Python, against the sequential restatement."""
+  * the position-parallel formulations the two sketch kernels use (one position per thread; eight per thread), modelled in Python,
+    against the sequential restatement."""
 import hashlib
 import os
 
@@ -161,3 +162,133 @@ def test_position_parallel_sketch_equals_the_sequential_one(seed_oracle):
             ref = seed_oracle.sketch(s, w, k)
             mod = model_sketch(s, w, k)
             assert len(ref) == len(mod) and all((int(a["x"]), int(a["y"])) == m for a, m in zip(ref, mod)), (w, k, s)
+
+
+def _brev64(x):
+    return int("{:064b}".format(x)[::-1], 2)
+
+
+def model_sketch8(seq, w, k, TILE=1920, P=8, HALO_THREADS=16):
+    """What sketch8_kernel (csrc/seed_kernels.cu) computes, thread by thread: 8 consecutive positions per thread, the k-mer and its
+    reverse complement rolled from the k - 1 bases in front (taken from the neighbours' packed words), the nine windows around the
+    thread's positions from suffix minima over the w hashes in front of its first position combined with prefix minima over its
+    own (newest minimum + 'hash occurs twice'), tiles of 1,920 positions after a halo of 128."""
+    L = len(seq)
+    mask = (1 << 2 * k) - 1
+    M64 = (1 << 64) - 1
+    threads = TILE // P + HALO_THREADS
+    span, halo = threads * P, HALO_THREADS * P
+    out = []
+    for t0 in range(0, L, TILE):
+        pb = t0 - halo
+        raw = [seq[pb + i] if 0 <= pb + i < L else ord("N") for i in range(span)]
+        pk16, bad8s = [0] * (threads + 4), [0] * threads
+        for tid in range(threads):
+            two = bad = 0
+            for j in range(P):
+                c = CODE.get(raw[tid * P + j], 4)
+                two |= (c & 3) << 2 * j
+                bad |= (c >> 2) << j
+            pk16[4 + tid], bad8s[tid] = two, bad
+        K, Z, RUN = [NONE] * span, [0] * span, [0] * span
+        last_bad = -1                                       # block-wide max scan in the kernel
+        for tid in range(threads):
+            i0 = tid * P
+            run = 128 if last_bad < 0 else min(128, i0 - 1 - last_bad)
+            prev = 0
+            for e in range(4):
+                prev |= pk16[tid + e] << (16 * e)            # the 32 bases in front of i0, oldest lowest
+            f = prev >> (64 - 2 * (k - 1)) if k > 1 else 0
+            rv = ((f ^ (mask >> 2)) << 2) & M64
+            x = _brev64(f)
+            x = ((x >> 1) & 0x5555555555555555) | ((x & 0x5555555555555555) << 1)
+            fw = x >> (64 - 2 * (k - 1)) if k > 1 else 0
+            for j in range(P):
+                c = (pk16[4 + tid] >> 2 * j) & 3
+                fw = ((fw << 2) | c) & mask
+                rv = (rv >> 2) | ((3 ^ c) << 2 * (k - 1))
+                run = 0 if (bad8s[tid] >> j) & 1 else min(128, run + 1)
+                RUN[i0 + j] = run
+                if run >= k:
+                    z = 0 if fw < rv else 1
+                    K[i0 + j], Z[i0 + j] = _hash64(rv if z else fw, mask) << 8 | k, z
+            if bad8s[tid]:
+                last_bad = i0 + bad8s[tid].bit_length() - 1
+        for tid in range(HALO_THREADS, threads):
+            i0 = tid * P
+            p0 = pb + i0
+            xk = K[i0:i0 + P]
+            suf = [NONE, i0 - 1, False]
+            win = [None] * (P + 1)
+
+            def older(i):
+                xo = K[i0 - w + i]
+                if xo < suf[0]:
+                    suf[0], suf[1], suf[2] = xo, i0 - w + i, False
+                elif xo == suf[0]:
+                    suf[2] = True
+            for i in range(w - 1, P, -1):
+                older(i)
+            for i in range(P, -1, -1):
+                if i < w:
+                    older(i)
+                win[i] = tuple(suf)
+            pre = [xk[0], i0, False]
+            for j in range(1, P + 1):
+                m = list(pre)
+                if j < w:
+                    o = win[j]
+                    if o[0] < pre[0]:
+                        m = list(o)
+                    elif o[0] == pre[0]:
+                        m[2] = True
+                win[j] = tuple(m)
+                if j < P and xk[j] <= pre[0]:
+                    pre = [xk[j], i0 + j, xk[j] == pre[0]]
+            for j in range(P):
+                i, t = i0 + j, p0 + j
+                if t >= L:
+                    break
+                l, (xm, jm, ties), xt = RUN[i], win[j], xk[j]
+                em, after = [], jm
+                if l == w + k - 1 and xm != NONE and ties:
+                    em += [q for q in range(i - w + 1, i) if K[q] == xm and q != jm]
+                if xt <= xm:
+                    if l >= w + k and xm != NONE:
+                        em.append(jm)
+                    after = i
+                elif jm == i - w:
+                    if l >= w + k - 1 and xm != NONE:
+                        em.append(jm)
+                    xn, jn, tn = win[j + 1]
+                    if l >= w + k - 1 and xn != NONE and tn:
+                        em += [q for q in range(i - w + 1, i + 1) if K[q] == xn and q != jn]
+                    after = jn
+                if t == L - 1 and K[after] != NONE:
+                    em.append(after)
+                out += [(K[q], (pb + q) << 1 | Z[q]) for q in em]
+    return out
+
+
+def test_eight_positions_per_thread_sketch_equals_the_sequential_one(seed_oracle):
+    rng = np.random.default_rng(2)
+    cases = []
+    for it, L in enumerate([1, 7, 8, 9, 24, 25, 100, 127, 128, 129, 300, 1919, 1920, 1921, 2047, 2048, 3839, 3841, 4100]):
+        kind = it % 5
+        if kind == 0:
+            s = bytes(rng.choice(list(b"ACGT"), L))
+        elif kind == 1:
+            s = bytes(rng.choice(list(b"ACGTN"), L, p=[.24, .24, .24, .24, .04]))
+        elif kind == 2:
+            s = bytes(rng.choice(list(b"AC"), L))
+        elif kind == 3:
+            s = bytes(rng.choice(list(b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAN"), L))
+        else:
+            u = bytes(rng.choice(list(b"ACGT"), int(rng.integers(1, 12))))
+            s = (u * (L // len(u) + 1))[:L]
+        cases.append(s)
+    for s in cases:
+        for w, k in ((10, 15), (10, 19), (19, 19), (11, 21), (8, 3), (64, 27)):
+            ref = seed_oracle.sketch(s, w, k)
+            mod = model_sketch8(s, w, k)
+            assert len(ref) == len(mod) and all((int(a["x"]), int(a["y"])) == m for a, m in zip(ref, mod)), (w, k, len(s))
